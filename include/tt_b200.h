@@ -1,0 +1,156 @@
+/*
+ * tt_b200.h -- C ABI of the B200-native retrieval hot path (libtt_b200.so).
+ *
+ * One index = one row-major matrix of leaf embeddings resident in HBM plus four int32
+ * relation arrays describing the hierarchical node tree.  The library replaces, for that
+ * index, the numeric work behind the two objects the reference constructs at
+ *   /root/reference/src/tensortruth/rag_engine.py:639-645   (and again :674-679)
+ *       base         = index.as_retriever(similarity_top_k=k)      -> tt_scan_* + tt_rescore_topk
+ *       am_retriever = AutoMergingRetriever(base, storage_context) -> tt_automerge
+ * and, for a corpus row-sharded over several GPUs (not in the reference),
+ * the k-way merge after the all-gather                              -> tt_merge_topk.
+ *
+ * Conventions
+ *   - extern "C"; every entry point returns 0 (TT_OK) or a negative TT_ERR_* code and never
+ *     throws; tt_last_error() gives the message for the calling thread.
+ *   - All pointers are DEVICE pointers unless the name ends in _host.  The library never
+ *     allocates or frees device memory: the caller (PyTorch) owns corpus, outputs, workspace.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*) and is asynchronous;
+ *     nothing here synchronises.  The calls are CUDA-graph capturable.
+ *   - Ordering rule everywhere: key descending, ties -> smaller id first.  ids are global row
+ *     ordinals (id_base + local row) and must stay below 2^32.
+ *   - There is no CPU implementation behind this ABI.
+ */
+#ifndef TT_B200_H
+#define TT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TT_OK 0
+#define TT_ERR_INVALID (-1)     /* bad argument */
+#define TT_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
+#define TT_ERR_UNSUPPORTED (-3) /* shape/alignment this build has no kernel for */
+#define TT_ERR_WORKSPACE (-4)   /* workspace too small */
+
+#define TT_DTYPE_BF16 0
+#define TT_DTYPE_F32 1
+
+/* score_mode: what ChromaVectorStore would surface for the row. */
+#define TT_SCORE_COSINE 0        /* key = score = f32(<q,c>/(|q||c|))                         */
+#define TT_SCORE_CHROMA_L2_EXP 1 /* d = f32(|q|^2+|c|^2-2<q,c>); key = -d; score = f32(exp(-d)) */
+
+/* scan variants */
+#define TT_SCAN_AUTO 0
+#define TT_SCAN_SIMT 1    /* CUDA-core fp32 streaming scan (any dim % 8 == 0)                  */
+#define TT_SCAN_TCGEN05 2 /* TMA + tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), dim % 64 == 0   */
+
+int tt_version(void);
+const char* tt_last_error(void);
+
+/* Number of shortlists (= persistent CTAs) a scan on `device` emits per query. */
+int tt_scan_num_lists(int device);
+
+/* Largest kprime (shortlist length per CTA) the scan kernels support. */
+int tt_scan_max_kprime(void);
+
+/*
+ * Query preparation (replaces nothing in the reference -- the embedder hands over fp32):
+ * q_hat = q/|q| in fp32, split into q_hi = bf16(q_hat), q_lo = bf16(q_hat - q_hi), so that two
+ * bf16 MMA columns per query carry 16 mantissa bits of the query through the tensor cores.
+ * q_hi/q_lo: bf16 [n_q, dim].
+ */
+int tt_prepare_queries(const float* q_f32, int n_q, int dim, void* q_hi_bf16, void* q_lo_bf16, void* stream);
+
+/*
+ * Stage 1 -- dense scan + fused on-chip shortlist.  Replaces the vector-store query behind
+ * `index.as_retriever(similarity_top_k=k).retrieve()` (rag_engine.py:639; ChromaVectorStore.query
+ * -> collection.query(query_embeddings, n_results=k)).
+ *
+ * Streams corpus[n_rows, dim] (bf16, row stride row_stride_elems) exactly once per query tile,
+ * scores every row approximately, a(r) = (<q_hi,c_r> + <q_lo,c_r>) * inv_norm[r] (fp32
+ * accumulate; inv_norm may be NULL = 1), and keeps, per persistent CTA l and query b, the
+ * kprime best rows it saw.  The score matrix never reaches HBM.
+ *
+ *   out_ids    int64 [n_q, n_lists*kprime]  global ids (id_base + row), -1 = empty slot
+ *   out_approx float [n_q, n_lists*kprime]  approximate scores of those rows
+ *   out_thresh float [n_q, n_lists]         every row CTA l saw and did NOT emit has
+ *                                           a(r) <= out_thresh[b,l]  (-inf: l emitted all it saw)
+ * q_lo_bf16 may be NULL (hi only: half the tensor work, wider certificate).
+ * variant: TT_SCAN_AUTO | TT_SCAN_SIMT | TT_SCAN_TCGEN05.
+ */
+int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
+                      const float* inv_norm, const void* q_hi_bf16, const void* q_lo_bf16, int n_q,
+                      int kprime, int64_t id_base, int variant,
+                      int64_t* out_ids, float* out_approx, float* out_thresh, void* stream);
+
+/*
+ * Stage 2 -- exact re-score of the shortlist + exact top-k.  Together with stage 1 this is the
+ * exact brute-force result the reference's (approximate, HNSW) query targets.
+ *
+ * For every candidate: dot, |c|^2 in fp64 over the stored values, key/score as TT_SCORE_*
+ * defines, then the k best by (key desc, id asc).
+ *
+ *   cand_ids    int64 [n_q, n_cand]   from stage 1 (-1 entries ignored)
+ *   cand_thresh float [n_q, n_lists]  from stage 1, or NULL
+ *   out_keys    float [n_q, k]        ordering keys (what tt_merge_topk consumes); may be NULL
+ *   out_scores  float [n_q, k]        reported scores; -inf padding
+ *   out_ids     int64 [n_q, k]        -1 padding
+ *   out_margin  float [n_q]           certificate: (k-th exact cosine) - max_l cand_thresh[b,l];
+ *                                     the top-k is proven exact iff margin > the stage-1 error
+ *                                     bound.  +inf when nothing was left out.  NULL ok.
+ *   ws          >= tt_rescore_workspace_bytes(n_q, n_cand) bytes
+ */
+size_t tt_rescore_workspace_bytes(int n_q, int n_cand);
+int tt_rescore_topk(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                    int64_t id_base, const float* q_f32, int n_q,
+                    const int64_t* cand_ids, int n_cand, const float* cand_thresh, int n_lists,
+                    int k, int score_mode,
+                    float* out_keys, float* out_scores, int64_t* out_ids, float* out_margin,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * Exact brute-force scan (fp64 scoring of EVERY row, CUDA cores).  The certificate-failure
+ * fallback and the on-GPU secondary oracle for corpora too large for the CPU oracle.
+ * Same outputs as tt_rescore_topk (no margin: the result is exact by construction).
+ * ws >= tt_scan_exact_workspace_bytes(device, n_q, k).
+ */
+size_t tt_scan_exact_workspace_bytes(int device, int n_q, int k);
+int tt_scan_exact_f64(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                      int64_t id_base, const float* q_f32, int n_q, int k, int score_mode,
+                      float* out_keys, float* out_scores, int64_t* out_ids,
+                      void* ws, size_t ws_bytes, void* stream);
+
+/*
+ * k-way merge of per-shard top-k lists after the all-gather (row-sharded corpus).
+ *   keys float [n_lists, n_q, k_in], ids int64 [n_lists, n_q, k_in]  (rank-major, as all_gather lays them)
+ *   out_scores float [n_q, k_out] (score_mode applied to the merged keys), out_ids int64 [n_q, k_out]
+ */
+int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int n_q, int k_in, int k_out,
+                  int score_mode, float* out_scores, int64_t* out_ids, void* stream);
+
+/*
+ * Stage 3 -- auto-merge.  Replaces AutoMergingRetriever._retrieve after the base retriever
+ * returned (rag_engine.py:641-643; upstream _fill_in_nodes / _get_parents_and_merge /
+ * _try_merging loop, then a stable sort by score).  One CTA per query; float64 scores.
+ *
+ *   ids int64 [n_q, k] (-1 padding at the tail), scores float [n_q, k]
+ *   parent_of, child_count, prev_id, next_id: int32 [n_nodes] (tensor_truth_b200/tree.py)
+ *   out_ids int64 [n_q, max_out], out_scores double [n_q, max_out], out_len int32 [n_q]
+ *   out_len[b] = -1 if the merged list did not fit max_out (or k > tt_automerge_max_k()).
+ */
+int tt_automerge_max_k(void);
+int tt_automerge(const int64_t* ids, const float* scores, int n_q, int k,
+                 const int32_t* parent_of, const int32_t* child_count,
+                 const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
+                 double ratio_thresh, int max_rounds,
+                 int64_t* out_ids, double* out_scores, int32_t* out_len, int max_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TT_B200_H */

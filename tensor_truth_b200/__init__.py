@@ -9,3 +9,16 @@ behind the C ABI declared in ``include/tt_b200.h``; there is no CPU fallback.
 __version__ = "0.1.0"
 
 from .tree import NodeTree, build_uniform_tree, tree_from_relations  # noqa: F401
+from .schema import NodeWithScore, QueryBundle, TextNode  # noqa: F401
+
+
+def __getattr__(name):  # torch-dependent parts load lazily
+    if name in ("DeviceIndex", "SearchResult", "MergeResult"):
+        from . import index
+
+        return getattr(index, name)
+    if name in ("B200VectorIndexRetriever", "B200AutoMergingRetriever", "NodeTable", "build_retriever"):
+        from . import retriever
+
+        return getattr(retriever, name)
+    raise AttributeError(name)

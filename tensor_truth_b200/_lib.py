@@ -1,0 +1,77 @@
+"""ctypes binding of ``libtt_b200.so`` -- the only way the Python host code reaches the GPU kernels.
+
+There is no fallback: if the library is missing or a call fails, this raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtt_b200.so")
+
+OK = 0
+DTYPE_BF16, DTYPE_F32 = 0, 1
+SCORE_COSINE, SCORE_CHROMA_L2_EXP = 0, 1
+SCAN_AUTO, SCAN_SIMT, SCAN_TCGEN05 = 0, 1, 2
+
+# every symbol include/tt_b200.h declares: name -> (restype, argtypes)
+_P, _I, _L, _Z, _D = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
+SIGNATURES = {
+    "tt_version": (_I, []),
+    "tt_last_error": (C.c_char_p, []),
+    "tt_scan_num_lists": (_I, [_I]),
+    "tt_scan_max_kprime": (_I, []),
+    "tt_prepare_queries": (_I, [_P, _I, _I, _P, _P, _P]),
+    "tt_scan_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _I, _P, _P, _P, _P]),
+    "tt_rescore_workspace_bytes": (_Z, [_I, _I]),
+    "tt_rescore_topk": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
+    "tt_scan_exact_workspace_bytes": (_Z, [_I, _I, _I]),
+    "tt_scan_exact_f64": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "tt_merge_topk": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "tt_automerge_max_k": (_I, []),
+    "tt_automerge": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _L, _D, _I, _P, _P, _P, _I, _P]),
+}
+
+
+class TTError(RuntimeError):
+    """A libtt_b200 entry point returned a negative code (message from ``tt_last_error``)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libtt_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """The loaded library.  Raises if it has not been built -- there is no CPU path to fall back to."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python -m tensor_truth_b200.build` "
+                        "(tensor_truth_b200 has no CPU fallback)")
+                L = C.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(L, name)  # AttributeError if the .so does not export what the header declares
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise TTError(rc, lib().tt_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor, or None."""
+    return None if t is None else C.c_void_p(t.data_ptr())

@@ -1,0 +1,230 @@
+// C ABI of libtt_b200.so (include/tt_b200.h): argument checking, variant dispatch, error plumbing.
+// No kernels here; no CPU implementation of anything behind these entry points.
+#include <stdarg.h>
+#include <string.h>
+
+#include "tt_common.cuh"
+
+namespace tt {
+
+// ---- implemented in the kernel translation units
+int launch_prepare_queries(const float* q, int n_q, int dim, void* q_hi, void* q_lo, cudaStream_t st);
+int scan_simt_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
+                     const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
+                     float* out_approx, float* out_thresh, int n_lists, cudaStream_t st);
+int scan_simt_exact(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t stride, const float* q_f32,
+                    int n_q, int kprime, int64_t id_base, int mode, uint64_t* out_packed, int n_lists, cudaStream_t st);
+bool scan_tc_supported(int64_t n_rows, int dim, int64_t stride, int kprime, const void* corpus);
+int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
+                   const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
+                   float* out_approx, float* out_thresh, int n_lists, cudaStream_t st);
+int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
+                   const float* q, int n_q, const int64_t* cand_ids, int n_cand, int mode, uint64_t* packed,
+                   cudaStream_t st);
+int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists, int n_q,
+                  int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys, float* out_scores,
+                  int64_t* out_ids, float* out_margin, cudaStream_t st);
+int launch_automerge(const int64_t* ids, const float* scores, int n_q, int k, const int32_t* parent_of,
+                     const int32_t* child_count, const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
+                     double ratio_thresh, int max_rounds, int64_t* out_ids, double* out_scores, int32_t* out_len,
+                     int max_out, cudaStream_t st);
+int automerge_max_k();
+int kprime_to_E(int kprime);
+
+// ---- error plumbing
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+
+int sm_count(int device) {
+    static int cache[64];
+    if (device < 0 || device >= 64) return 0;
+    if (cache[device] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        cache[device] = n;
+    }
+    return cache[device];
+}
+
+static int exact_kprime(int k) {
+    if (k <= 32) return 32;
+    if (k <= 64) return 64;
+    if (k <= 128) return 128;
+    if (k <= 256) return 256;
+    return -1;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+#define TT_STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int tt_version(void) { return 100; }
+
+const char* tt_last_error(void) { return g_err; }
+
+int tt_scan_num_lists(int device) { return sm_count(device); }
+
+int tt_scan_max_kprime(void) { return 128; }
+
+int tt_prepare_queries(const float* q_f32, int n_q, int dim, void* q_hi_bf16, void* q_lo_bf16, void* stream) {
+    TT_CHECK_ARG(n_q >= 0 && dim > 0, "tt_prepare_queries: n_q=%d dim=%d", n_q, dim);
+    TT_CHECK_ARG(n_q == 0 || (q_f32 && q_hi_bf16), "tt_prepare_queries: null pointer");
+    return launch_prepare_queries(q_f32, n_q, dim, q_hi_bf16, q_lo_bf16, TT_STREAM(stream));
+}
+
+int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
+                      const float* inv_norm, const void* q_hi_bf16, const void* q_lo_bf16, int n_q, int kprime,
+                      int64_t id_base, int variant, int64_t* out_ids, float* out_approx, float* out_thresh,
+                      void* stream) {
+    TT_CHECK_ARG(n_rows >= 0 && n_q >= 0, "tt_scan_topk_bf16: n_rows=%lld n_q=%d", (long long)n_rows, n_q);
+    TT_CHECK_ARG(dim > 0 && dim % 8 == 0, "tt_scan_topk_bf16: dim=%d must be a positive multiple of 8", dim);
+    TT_CHECK_ARG(row_stride_elems >= dim && row_stride_elems % 8 == 0, "tt_scan_topk_bf16: row stride %lld",
+                 (long long)row_stride_elems);
+    TT_CHECK_ARG(kprime == 32 || kprime == 64 || kprime == 128, "tt_scan_topk_bf16: kprime=%d not in {32,64,128}", kprime);
+    TT_CHECK_ARG(id_base >= 0 && id_base + n_rows <= (int64_t(1) << 32), "tt_scan_topk_bf16: ids must stay below 2^32");
+    TT_CHECK_ARG(n_rows < (int64_t(1) << 32), "tt_scan_topk_bf16: shard too large");
+    if (n_q == 0) return TT_OK;
+    TT_CHECK_ARG(q_hi_bf16 && out_ids && out_approx && out_thresh && (n_rows == 0 || corpus_bf16),
+                 "tt_scan_topk_bf16: null pointer");
+    const int n_lists = sm_count(current_device());
+    if (n_lists <= 0) {
+        set_error("tt_scan_topk_bf16: no CUDA device");
+        return TT_ERR_CUDA;
+    }
+    const bool tc_ok = n_rows > 0 && scan_tc_supported(n_rows, dim, row_stride_elems, kprime, corpus_bf16);
+    if (variant == TT_SCAN_AUTO) variant = tc_ok ? TT_SCAN_TCGEN05 : TT_SCAN_SIMT;
+    if (variant == TT_SCAN_TCGEN05) {
+        if (!tc_ok) {
+            set_error("tt_scan_topk_bf16: the tcgen05 variant needs dim %% 128 == 0, 128 <= dim <= 2048, n_rows > 0");
+            return TT_ERR_UNSUPPORTED;
+        }
+        return scan_tc_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, q_lo_bf16, n_q, kprime,
+                              id_base, out_ids, out_approx, out_thresh, n_lists, TT_STREAM(stream));
+    }
+    if (variant == TT_SCAN_SIMT)
+        return scan_simt_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, q_lo_bf16, n_q, kprime,
+                                id_base, out_ids, out_approx, out_thresh, n_lists, TT_STREAM(stream));
+    set_error("tt_scan_topk_bf16: unknown variant %d", variant);
+    return TT_ERR_INVALID;
+}
+
+size_t tt_rescore_workspace_bytes(int n_q, int n_cand) {
+    if (n_q <= 0 || n_cand <= 0) return 0;
+    return size_t(n_q) * size_t(n_cand) * sizeof(uint64_t);
+}
+
+int tt_rescore_topk(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                    int64_t id_base, const float* q_f32, int n_q, const int64_t* cand_ids, int n_cand,
+                    const float* cand_thresh, int n_lists, int k, int score_mode, float* out_keys, float* out_scores,
+                    int64_t* out_ids, float* out_margin, void* ws, size_t ws_bytes, void* stream) {
+    TT_CHECK_ARG(corpus_dtype == TT_DTYPE_BF16 || corpus_dtype == TT_DTYPE_F32, "tt_rescore_topk: dtype %d", corpus_dtype);
+    TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_rescore_topk: score_mode %d",
+                 score_mode);
+    TT_CHECK_ARG(dim > 0 && dim % 8 == 0 && row_stride_elems >= dim && row_stride_elems % 8 == 0,
+                 "tt_rescore_topk: dim=%d stride=%lld", dim, (long long)row_stride_elems);
+    TT_CHECK_ARG(n_q >= 0 && n_cand >= 0 && k >= 1, "tt_rescore_topk: n_q=%d n_cand=%d k=%d", n_q, n_cand, k);
+    TT_CHECK_ARG(id_base >= 0 && id_base + n_rows <= (int64_t(1) << 32), "tt_rescore_topk: ids must stay below 2^32");
+    if (n_q == 0) return TT_OK;
+    TT_CHECK_ARG(q_f32 && out_ids && (n_cand == 0 || cand_ids), "tt_rescore_topk: null pointer");
+    if (ws_bytes < tt_rescore_workspace_bytes(n_q, n_cand) || (n_cand > 0 && !ws)) {
+        set_error("tt_rescore_topk: workspace %zu < %zu bytes", ws_bytes, tt_rescore_workspace_bytes(n_q, n_cand));
+        return TT_ERR_WORKSPACE;
+    }
+    uint64_t* packed = reinterpret_cast<uint64_t*>(ws);
+    int rc = launch_rescore(corpus, corpus_dtype, n_rows, dim, row_stride_elems, id_base, q_f32, n_q, cand_ids, n_cand,
+                            score_mode, packed, TT_STREAM(stream));
+    if (rc) return rc;
+    return launch_select(packed, n_cand, nullptr, nullptr, 0, n_q, 0, k, score_mode, cand_thresh,
+                         cand_thresh ? n_lists : 0, out_keys, out_scores, out_ids, out_margin, TT_STREAM(stream));
+}
+
+size_t tt_scan_exact_workspace_bytes(int device, int n_q, int k) {
+    const int kp = exact_kprime(k);
+    const int n_lists = sm_count(device);
+    if (kp < 0 || n_lists <= 0 || n_q <= 0) return 0;
+    return size_t(n_q) * n_lists * kp * sizeof(uint64_t);
+}
+
+int tt_scan_exact_f64(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                      int64_t id_base, const float* q_f32, int n_q, int k, int score_mode, float* out_keys,
+                      float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes, void* stream) {
+    TT_CHECK_ARG(corpus_dtype == TT_DTYPE_BF16 || corpus_dtype == TT_DTYPE_F32, "tt_scan_exact_f64: dtype %d", corpus_dtype);
+    TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_scan_exact_f64: score_mode %d",
+                 score_mode);
+    TT_CHECK_ARG(dim > 0 && dim % 8 == 0 && row_stride_elems >= dim && row_stride_elems % 8 == 0,
+                 "tt_scan_exact_f64: dim=%d stride=%lld", dim, (long long)row_stride_elems);
+    TT_CHECK_ARG(n_q >= 0 && n_rows >= 0, "tt_scan_exact_f64: n_q=%d n_rows=%lld", n_q, (long long)n_rows);
+    TT_CHECK_ARG(id_base >= 0 && id_base + n_rows <= (int64_t(1) << 32) && n_rows < (int64_t(1) << 32),
+                 "tt_scan_exact_f64: ids must stay below 2^32");
+    const int kp = exact_kprime(k);
+    TT_CHECK_ARG(k >= 1 && kp > 0, "tt_scan_exact_f64: k=%d out of range [1, 256]", k);
+    if (n_q == 0) return TT_OK;
+    TT_CHECK_ARG(q_f32 && out_ids && (n_rows == 0 || corpus), "tt_scan_exact_f64: null pointer");
+    const int dev = current_device();
+    const int n_lists = sm_count(dev);
+    if (n_lists <= 0) {
+        set_error("tt_scan_exact_f64: no CUDA device");
+        return TT_ERR_CUDA;
+    }
+    const size_t need = tt_scan_exact_workspace_bytes(dev, n_q, k);
+    if (ws_bytes < need || !ws) {
+        set_error("tt_scan_exact_f64: workspace %zu < %zu bytes", ws_bytes, need);
+        return TT_ERR_WORKSPACE;
+    }
+    uint64_t* packed = reinterpret_cast<uint64_t*>(ws);
+    int rc = scan_simt_exact(corpus, corpus_dtype, n_rows, dim, row_stride_elems, q_f32, n_q, kp, id_base, score_mode,
+                             packed, n_lists, TT_STREAM(stream));
+    if (rc) return rc;
+    return launch_select(packed, n_lists * kp, nullptr, nullptr, 0, n_q, 0, k, score_mode, nullptr, 0, out_keys,
+                         out_scores, out_ids, nullptr, TT_STREAM(stream));
+}
+
+int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int n_q, int k_in, int k_out, int score_mode,
+                  float* out_scores, int64_t* out_ids, void* stream) {
+    TT_CHECK_ARG(n_lists >= 1 && n_q >= 0 && k_in >= 1 && k_out >= 1, "tt_merge_topk: n_lists=%d n_q=%d k_in=%d k_out=%d",
+                 n_lists, n_q, k_in, k_out);
+    TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_merge_topk: score_mode %d",
+                 score_mode);
+    if (n_q == 0) return TT_OK;
+    TT_CHECK_ARG(keys && ids && out_ids, "tt_merge_topk: null pointer");
+    return launch_select(nullptr, 0, keys, ids, n_lists, n_q, k_in, k_out, score_mode, nullptr, 0, nullptr, out_scores,
+                         out_ids, nullptr, TT_STREAM(stream));
+}
+
+int tt_automerge_max_k(void) { return automerge_max_k(); }
+
+int tt_automerge(const int64_t* ids, const float* scores, int n_q, int k, const int32_t* parent_of,
+                 const int32_t* child_count, const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
+                 double ratio_thresh, int max_rounds, int64_t* out_ids, double* out_scores, int32_t* out_len, int max_out,
+                 void* stream) {
+    TT_CHECK_ARG(n_q >= 0 && k >= 0 && max_out >= 1, "tt_automerge: n_q=%d k=%d max_out=%d", n_q, k, max_out);
+    TT_CHECK_ARG(k <= automerge_max_k(), "tt_automerge: k=%d exceeds tt_automerge_max_k()=%d", k, automerge_max_k());
+    TT_CHECK_ARG(n_nodes >= 0 && n_nodes < (int64_t(1) << 31), "tt_automerge: n_nodes=%lld", (long long)n_nodes);
+    TT_CHECK_ARG(max_rounds >= 1, "tt_automerge: max_rounds=%d", max_rounds);
+    if (n_q == 0) return TT_OK;
+    TT_CHECK_ARG(out_ids && out_scores && out_len && (k == 0 || (ids && scores)), "tt_automerge: null pointer");
+    TT_CHECK_ARG(n_nodes == 0 || (parent_of && child_count && prev_id && next_id), "tt_automerge: null tree array");
+    return launch_automerge(ids, scores, n_q, k, parent_of, child_count, prev_id, next_id, n_nodes, ratio_thresh,
+                            max_rounds, out_ids, out_scores, out_len, max_out, TT_STREAM(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,230 @@
+// Stage 2: exact fp64 re-score of the shortlist, exact top-k selection, shard merge, query prep.
+//
+// With stage 1 this reproduces the exact brute-force target of the vector-store query the
+// reference issues at /root/reference/src/tensortruth/rag_engine.py:639 and the scoring
+// ChromaVectorStore applies to it (cosine here; exp(-squared-L2) in TT_SCORE_CHROMA_L2_EXP).
+#include "tt_common.cuh"
+
+namespace tt {
+
+// ------------------------------------------------------------------ query preparation
+// one CTA per query: q_hat = q/|q| (fp32), hi = bf16(q_hat), lo = bf16(q_hat - hi)
+__global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __restrict__ q, int dim,
+                                                              __nv_bfloat16* __restrict__ q_hi,
+                                                              __nv_bfloat16* __restrict__ q_lo) {
+    __shared__ double red[8];
+    const float* qb = q + size_t(blockIdx.x) * dim;
+    double a = 0.0;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) { double v = qb[d]; a += v * v; }
+    a = warp_sum_f64(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) tot += red[w];
+    const double inv = tot > 0.0 ? 1.0 / sqrt(tot) : 0.0;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) {
+        float qh = float(double(qb[d]) * inv);
+        __nv_bfloat16 hi = __float2bfloat16_rn(qh);
+        size_t o = size_t(blockIdx.x) * dim + d;
+        q_hi[o] = hi;
+        if (q_lo) q_lo[o] = __float2bfloat16_rn(qh - __bfloat162float(hi));
+    }
+}
+
+// ------------------------------------------------------------------ re-score
+// one warp per (query, candidate); fixed summation order (lane-strided, then xor-butterfly).
+template <typename CT>
+__global__ void __launch_bounds__(256) rescore_kernel(const CT* __restrict__ corpus, int64_t n_rows, int dim,
+                                                      int64_t stride, int64_t id_base,
+                                                      const float* __restrict__ q, int n_q,
+                                                      const int64_t* __restrict__ cand_ids, int n_cand, int mode,
+                                                      uint64_t* __restrict__ packed /* [n_q, n_cand] */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+    const int64_t total = int64_t(n_q) * n_cand;
+    const int chunks = dim >> 3;
+    for (int64_t w = warp; w < total; w += n_warps) {
+        const int b = int(w / n_cand);
+        const int64_t id = cand_ids[w];
+        const int64_t row = id - id_base;
+        if (id < 0 || row < 0 || row >= n_rows) {
+            if (lane == 0) packed[w] = 0ull;
+            continue;
+        }
+        const CT* rp = corpus + row * stride;
+        const float* qb = q + size_t(b) * dim;
+        double dot = 0.0, nn = 0.0, qq = 0.0;
+        for (int c = lane; c < chunks; c += 32) {
+            float f[8];
+            if (sizeof(CT) == 2) {
+                uint4 v = *(reinterpret_cast<const uint4*>(rp) + c);
+                unpack_bf16x8(v, f);
+            } else {
+                float4 a = *(reinterpret_cast<const float4*>(rp) + 2 * c);
+                float4 bb = *(reinterpret_cast<const float4*>(rp) + 2 * c + 1);
+                f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = bb.x; f[5] = bb.y; f[6] = bb.z; f[7] = bb.w;
+            }
+            float4 q0 = *(reinterpret_cast<const float4*>(qb) + 2 * c);
+            float4 q1 = *(reinterpret_cast<const float4*>(qb) + 2 * c + 1);
+            const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                double cd = double(f[e]), qd = double(qv[e]);
+                dot += qd * cd;
+                nn += cd * cd;
+                qq += qd * qd;
+            }
+        }
+        dot = warp_sum_f64(dot);
+        nn = warp_sum_f64(nn);
+        qq = warp_sum_f64(qq);
+        if (lane == 0) {
+            float key;
+            if (mode == TT_SCORE_COSINE) {
+                double den = sqrt(qq) * sqrt(nn);
+                key = den > 0.0 ? float(dot / den) : 0.0f;
+            } else {
+                key = -float(qq + nn - 2.0 * dot);
+            }
+            packed[w] = pack_entry(key, uint32_t(id));
+        }
+    }
+}
+
+__device__ __forceinline__ float score_of_key(float key, int mode) {
+    return mode == TT_SCORE_COSINE ? key : float(exp(double(key)));  // key = -d
+}
+
+// ------------------------------------------------------------------ select: one CTA per query
+// Sorts the query's packed candidates in chunks of SEL_CHUNK (carrying the running top-k) and
+// emits the k best.  Input either `packed` [n_q, n_in] or (keys, ids) laid out
+// [n_lists, n_q, k_in] (the all-gather layout) when packed == nullptr.
+constexpr int SEL_THREADS = 1024;
+
+__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __restrict__ packed, int n_in,
+                                                             const float* __restrict__ in_keys,
+                                                             const int64_t* __restrict__ in_ids, int n_lists,
+                                                             int n_q, int k_in, int chunk /* pow2 */, int k,
+                                                             int mode, const float* __restrict__ thresh,
+                                                             int n_thresh, float* __restrict__ out_keys,
+                                                             float* __restrict__ out_scores,
+                                                             int64_t* __restrict__ out_ids,
+                                                             float* __restrict__ out_margin) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    const int total = packed ? n_in : n_lists * k_in;
+    int carried = 0;  // entries [0, carried) of s hold the running top-k
+    for (int base = 0; base < total || base == 0;) {
+        const int room = chunk - carried;
+        const int take = min(room, total - base);
+        for (int i = threadIdx.x; i < room; i += SEL_THREADS) {
+            uint64_t e = 0ull;
+            if (i < take) {
+                const int j = base + i;
+                if (packed) {
+                    e = packed[size_t(b) * n_in + j];
+                } else {
+                    const int l = j / k_in, t = j - l * k_in;
+                    const size_t o = (size_t(l) * n_q + b) * k_in + t;
+                    const int64_t id = in_ids[o];
+                    e = id >= 0 ? pack_entry(in_keys[o], uint32_t(id)) : 0ull;
+                }
+            }
+            s[carried + i] = e;
+        }
+        __syncthreads();
+        block_bitonic_sort_desc(s, chunk);
+        carried = min(k, chunk);
+        base += take;
+        if (take == 0) break;
+    }
+    for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
+        const uint64_t e = i < chunk ? s[i] : 0ull;
+        const size_t o = size_t(b) * k + i;
+        const float key = e ? entry_key(e) : -INFINITY;
+        if (out_keys) out_keys[o] = key;
+        if (out_scores) out_scores[o] = e ? score_of_key(key, mode) : -INFINITY;
+        out_ids[o] = e ? int64_t(entry_id(e)) : int64_t(-1);
+    }
+    if (out_margin) {
+        float m = -INFINITY;
+        if (thresh)
+            for (int i = threadIdx.x; i < n_thresh; i += SEL_THREADS) m = fmaxf(m, thresh[size_t(b) * n_thresh + i]);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < SEL_THREADS / 32; ++w) m = fmaxf(m, red[w]);
+            const uint64_t ek = (k - 1 < chunk) ? s[k - 1] : 0ull;
+            float margin;
+            if (m == -INFINITY) margin = INFINITY;            // nothing was left out of any shortlist
+            else if (mode != TT_SCORE_COSINE) margin = -INFINITY;  // the shortlist is ordered by cosine only
+            else if (!ek) margin = -INFINITY;                 // fewer than k candidates although rows were dropped
+            else margin = entry_key(ek) - m;
+            out_margin[b] = margin;
+        }
+    }
+}
+
+static int pow2_at_least(int n) {
+    int p = 32;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists,
+                  int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys,
+                  float* out_scores, int64_t* out_ids, float* out_margin, cudaStream_t st) {
+    const int total = packed ? n_in : n_lists * k_in;
+    constexpr int MAX_CHUNK = 8192;  // 64 KB of shared memory
+    TT_CHECK_ARG(k >= 1 && k <= MAX_CHUNK / 2, "k=%d out of range [1, %d]", k, MAX_CHUNK / 2);
+    int chunk = pow2_at_least(total > k ? total : k);
+    if (chunk > MAX_CHUNK) chunk = MAX_CHUNK;
+    if (chunk < 2 * k) chunk = pow2_at_least(2 * k);
+    const size_t smem = size_t(chunk) * sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        TT_CUDA_OK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        MAX_CHUNK * int(sizeof(uint64_t))));
+        attr_set = true;
+    }
+    if (n_q == 0) return TT_OK;
+    select_kernel<<<n_q, SEL_THREADS, smem, st>>>(packed, n_in, in_keys, in_ids, n_lists, n_q, k_in, chunk, k, mode,
+                                                  thresh, n_thresh, out_keys, out_scores, out_ids, out_margin);
+    TT_LAUNCH_OK("select_kernel");
+    return TT_OK;
+}
+
+int launch_prepare_queries(const float* q, int n_q, int dim, void* q_hi, void* q_lo, cudaStream_t st) {
+    if (n_q == 0) return TT_OK;
+    prepare_queries_kernel<<<n_q, 256, 0, st>>>(q, dim, reinterpret_cast<__nv_bfloat16*>(q_hi),
+                                                reinterpret_cast<__nv_bfloat16*>(q_lo));
+    TT_LAUNCH_OK("prepare_queries_kernel");
+    return TT_OK;
+}
+
+int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
+                   const float* q, int n_q, const int64_t* cand_ids, int n_cand, int mode, uint64_t* packed,
+                   cudaStream_t st) {
+    const int64_t total = int64_t(n_q) * n_cand;
+    if (total == 0) return TT_OK;
+    const int warps_per_block = 8;
+    int64_t blocks = (total + warps_per_block - 1) / warps_per_block;
+    const int64_t cap = int64_t(sm_count(current_device())) * 16;
+    if (blocks > cap) blocks = cap;
+    if (dtype == TT_DTYPE_BF16)
+        rescore_kernel<__nv_bfloat16><<<int(blocks), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(corpus),
+                                                                  n_rows, dim, stride, id_base, q, n_q, cand_ids,
+                                                                  n_cand, mode, packed);
+    else
+        rescore_kernel<float><<<int(blocks), 256, 0, st>>>(reinterpret_cast<const float*>(corpus), n_rows, dim,
+                                                          stride, id_base, q, n_q, cand_ids, n_cand, mode, packed);
+    TT_LAUNCH_OK("rescore_kernel");
+    return TT_OK;
+}
+
+}  // namespace tt

@@ -1,0 +1,478 @@
+// Stage 1, tensor-core variant: TMA-staged corpus tiles -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM)
+// -> fused on-chip top-K' shortlist.  The score matrix never leaves the SM.
+//
+// Replaces the vector-store query issued through `index.as_retriever(similarity_top_k=k)` at
+// /root/reference/src/tensortruth/rag_engine.py:639 (ChromaVectorStore.query -> collection.query);
+// the exact result is restored by stage 2 (rescore.cu).
+//
+// Shape of one launch ("pass"): up to NQ = N/2 queries, each occupying two MMA columns (hi and lo
+// bf16 halves of the fp32 query), against every 128-row tile of the corpus:
+//
+//      D[128 rows, N] (TMEM, fp32)  =  C_tile[128, dim] (smem via TMA, K-major SW128)  x  Q^T[dim, N] (smem, resident)
+//
+// Persistent grid, one CTA per SM, tiles interleaved (tile t -> CTA t % grid).  Six warps:
+//   warps 0-3  epilogue: tcgen05.ld the accumulator row of "their" corpus row, apply inv_norm, filter
+//              against the per-query threshold, push survivors into a shared-memory candidate list;
+//              rank-select the list back to K' when it fills (threshold := K'-th approximate score)
+//   warp  4    TMA producer: corpus tile ring (STAGES x CH x 16 KB) + the query block once
+//   warp  5    TMEM allocation + single-thread tcgen05.mma issue, double-buffered accumulators
+#include <cuda.h>
+
+#include "tt_common.cuh"
+
+namespace tt {
+
+namespace tc {
+
+constexpr int TILE_ROWS = 128;           // MMA M
+constexpr int CHUNK_COLS = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int CHUNK_BYTES = TILE_ROWS * 128;  // one [128 x 64] bf16 sub-tile
+constexpr int EPI_THREADS = 128;
+constexpr int THREADS = 192;
+constexpr int SMEM_LIMIT = 232448;       // 227 KB
+
+constexpr uint64_t POLICY_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t POLICY_EVICT_LAST = 0x14F0000000000000ull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Spin on the phase parity.  A wait that lasts ~seconds can only be a protocol bug: trap instead of
+// hanging the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spins & 0xfffu) == 0xfffu) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) {
+                printf("tt_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                       threadIdx.x, bar, parity);
+                __trap();
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "l"(policy)
+        : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows are 128 B apart, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3ffffu) >> 4);  // start address
+    d |= uint64_t(1) << 16;                      // leading byte offset (unused with swizzled K-major)
+    d |= uint64_t(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+    d |= uint64_t(1) << 46;                      // descriptor version (sm_100)
+    d |= uint64_t(2) << 61;                      // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128, N.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(TILE_ROWS >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+// barrier + OR-reduction of a predicate over the 128 epilogue threads
+__device__ __forceinline__ bool epi_bar_or(bool pred) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %1, 0;\n\t"
+        "bar.red.or.pred q, 1, %2, p;\n\t"
+        "selp.u32 %0, 1, 0, q;\n\t}"
+        : "=r"(r)
+        : "r"(uint32_t(pred)), "n"(EPI_THREADS)
+        : "memory");
+    return r != 0;
+}
+
+struct Params {
+    const float* inv_norm;
+    int64_t n_rows;
+    int64_t id_base;
+    int n_tiles;
+    int n_chunks;    // dim / 64
+    int stages;      // ring depth
+    int q0;          // first query of this pass
+    int nq_here;     // queries in this pass (<= N/2)
+    int n_q;         // total queries (output row count)
+    int kprime;
+    int cap;         // candidate list capacity per query: kprime + 128, <= 256
+    int has_lo;
+    int64_t* out_ids;
+    float* out_approx;
+    float* out_thresh;
+};
+
+// Dynamic shared memory (base rounded up to 1024 B):
+//   [ Q: n_chunks x N x 128 B ][ ring: stages x CH x 16 KB ][ lists: NQ x cap x 8 B ][ thresh NQ f32 ][ cnt NQ i32 ]
+//   [ barriers: full[stages], empty[stages], q_full, tmem_full[2], tmem_empty[2] ][ tmem base ]
+template <int N, int CH>
+__global__ void __launch_bounds__(THREADS, 1)
+scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_qhi,
+               const __grid_constant__ CUtensorMap map_qlo, const Params p) {
+    constexpr int NQ = N / 2;
+    constexpr int STAGE_BYTES = CH * CHUNK_BYTES;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+    const int q_bytes = p.n_chunks * N * 128;
+    unsigned char* q_s = smem;
+    unsigned char* ring = q_s + q_bytes;
+    uint64_t* lists = reinterpret_cast<uint64_t*>(ring + size_t(p.stages) * STAGE_BYTES);
+    float* thresh_s = reinterpret_cast<float*>(lists + size_t(NQ) * p.cap);
+    int* cnt_s = reinterpret_cast<int*>(thresh_s + NQ);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cnt_s + NQ);  // 8-byte aligned: NQ is a multiple of 8
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + p.stages;
+    uint64_t* q_full = bars + 2 * p.stages;
+    uint64_t* tmem_full = q_full + 1;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my_tiles = (p.n_tiles > int(blockIdx.x)) ? (p.n_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
+    const int steps_per_tile = p.n_chunks / CH;
+    constexpr int TMEM_COLS = (2 * N < 32) ? 32 : 2 * N;  // power of two for N in {16, 32, 64}
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(full_bar + s), 1);
+            mbar_init(smem_u32(empty_bar + s), 1);
+        }
+        mbar_init(smem_u32(q_full), 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(tmem_full + a), 1);
+            mbar_init(smem_u32(tmem_empty + a), EPI_THREADS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < NQ) {
+        thresh_s[threadIdx.x] = -INFINITY;
+        cnt_s[threadIdx.x] = 0;
+    }
+    if (!p.has_lo) {
+        // zero the lo halves of the query block (rows [NQ, N) of every chunk)
+        for (int i = threadIdx.x; i < p.n_chunks * NQ * 32; i += THREADS) {
+            const int c = i / (NQ * 32), r = i - c * (NQ * 32);
+            reinterpret_cast<uint32_t*>(q_s + size_t(c) * N * 128 + NQ * 128)[r] = 0u;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
+                     "r"(uint32_t(TMEM_COLS))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 4) {
+        // ===================================================== TMA producer
+        if (lane == 0 && n_my_tiles > 0) {
+            mbar_expect_tx(smem_u32(q_full), uint32_t(p.n_chunks * (p.has_lo ? N : NQ) * 128));
+            for (int c = 0; c < p.n_chunks; ++c) {
+                tma_load_3d(smem_u32(q_s + size_t(c) * N * 128), &map_qhi, 0, p.q0, c, smem_u32(q_full), POLICY_EVICT_LAST);
+                if (p.has_lo)
+                    tma_load_3d(smem_u32(q_s + size_t(c) * N * 128 + NQ * 128), &map_qlo, 0, p.q0, c, smem_u32(q_full),
+                                POLICY_EVICT_LAST);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_my_tiles; ++i) {
+                const int tile = int(blockIdx.x) + i * int(gridDim.x);
+                for (int s = 0; s < steps_per_tile; ++s) {
+                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
+                    mbar_expect_tx(smem_u32(full_bar + stage), STAGE_BYTES);
+                    tma_load_3d(smem_u32(ring + size_t(stage) * STAGE_BYTES), &map_c, 0, tile * TILE_ROWS, s * CH,
+                                smem_u32(full_bar + stage), POLICY_EVICT_FIRST);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===================================================== MMA issuer (one thread)
+        if (lane == 0 && n_my_tiles > 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(N);
+            mbar_wait(smem_u32(q_full), 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < n_my_tiles; ++i) {
+                const int a = i & 1;
+                mbar_wait(smem_u32(tmem_empty + a), (uint32_t(i >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(a * N);
+                for (int s = 0; s < steps_per_tile; ++s) {
+                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_base = smem_u32(ring + size_t(stage) * STAGE_BYTES);
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const uint32_t b_base = smem_u32(q_s + size_t(s * CH + c) * N * 128);
+#pragma unroll
+                        for (int k = 0; k < CHUNK_COLS / 16; ++k) {
+                            umma_bf16(d_tmem, umma_desc_sw128(a_base + c * CHUNK_BYTES + k * 32),
+                                      umma_desc_sw128(b_base + k * 32), idesc, uint32_t((s | c | k) != 0));
+                        }
+                    }
+                    umma_commit(smem_u32(empty_bar + stage));  // frees the smem slot once these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(smem_u32(tmem_full + a));  // accumulator of this tile complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================== epilogue: 128 threads, thread = corpus row
+        const int t = threadIdx.x;
+        const int nq = p.nq_here;
+        const int kp = p.kprime, cap = p.cap;
+        for (int i = 0; i < n_my_tiles; ++i) {
+            const int a = i & 1;
+            const int tile = int(blockIdx.x) + i * int(gridDim.x);
+            const int64_t row = int64_t(tile) * TILE_ROWS + t;
+            const bool row_ok = row < p.n_rows;
+            float inv = 1.f;
+            if (p.inv_norm && row_ok) inv = __ldg(p.inv_norm + row);
+
+            mbar_wait(smem_u32(tmem_full + a), uint32_t(i >> 1) & 1u);
+            tcgen05_fence_after();
+            float acc[N];
+            const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(a * N);
+#pragma unroll
+            for (int c = 0; c < N; c += 16) tmem_ld_x16(taddr + c, acc + c);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(tmem_empty + a));  // accumulator is in registers: hand TMEM back
+
+            bool pushed = false;
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                if (j < nq) {
+                    const float s = (acc[j] + acc[NQ + j]) * inv;
+                    if (row_ok && s > thresh_s[j]) {
+                        const int slot = atomicAdd(cnt_s + j, 1);  // slot < cap: <= kprime before the tile, +128 at most
+                        lists[size_t(j) * cap + slot] = pack_entry(s, uint32_t(row));
+                        pushed = true;
+                    }
+                }
+            }
+            if (!epi_bar_or(pushed)) continue;
+
+            // ---- some list grew: rank-select every list longer than K' back to its K' best
+            bool any = false;
+            for (int j = 0; j < nq; ++j) {
+                const int n = cnt_s[j];
+                if (n <= kp) continue;
+                any = true;
+                uint64_t* L = lists + size_t(j) * cap;
+                uint64_t e0 = t < n ? L[t] : 0ull, e1 = (t + EPI_THREADS) < n ? L[t + EPI_THREADS] : 0ull;
+                int r0 = 0, r1 = 0;
+                for (int m = 0; m < n; ++m) {
+                    const uint64_t x = L[m];
+                    r0 += x > e0 ? 1 : 0;
+                    r1 += x > e1 ? 1 : 0;
+                }
+                epi_bar_sync();
+                if (t < n && r0 < kp) L[r0] = e0;
+                if (t + EPI_THREADS < n && r1 < kp) L[r1] = e1;
+                if (t < n && r0 == kp - 1) thresh_s[j] = entry_key(e0);
+                if (t + EPI_THREADS < n && r1 == kp - 1) thresh_s[j] = entry_key(e1);
+                if (t == 0) cnt_s[j] = kp;
+            }
+            (void)any;
+            epi_bar_sync();  // unconditional: nobody may push for the next tile while others still read the counts
+        }
+
+        // ---- emit this CTA's shortlist
+        epi_bar_sync();
+        for (int j = 0; j < nq; ++j) {
+            const int n = cnt_s[j];
+            const size_t o = (size_t(p.q0 + j) * gridDim.x + blockIdx.x) * kp;
+            for (int s = t; s < kp; s += EPI_THREADS) {
+                const uint64_t e = s < n ? lists[size_t(j) * cap + s] : 0ull;
+                p.out_ids[o + s] = e ? int64_t(p.id_base + entry_id(e)) : int64_t(-1);
+                p.out_approx[o + s] = e ? entry_key(e) : -INFINITY;
+            }
+            if (t == 0) p.out_thresh[size_t(p.q0 + j) * gridDim.x + blockIdx.x] = thresh_s[j];
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS))
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, dim] bf16 row-major seen as (64 cols, rows, dim/64 chunks); box = (64, box_rows, box_chunks)
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int dim, int64_t stride_elems, int box_rows,
+                    int box_chunks) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return TT_ERR_CUDA;
+    }
+    cuuint64_t dims[3] = {cuuint64_t(CHUNK_COLS), cuuint64_t(rows), cuuint64_t(dim / CHUNK_COLS)};
+    cuuint64_t strides[2] = {cuuint64_t(stride_elems) * 2, cuuint64_t(CHUNK_COLS) * 2};
+    cuuint32_t box[3] = {cuuint32_t(CHUNK_COLS), cuuint32_t(box_rows), cuuint32_t(box_chunks)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for base=%p rows=%lld dim=%d stride=%lld", int(r), base,
+                  (long long)rows, dim, (long long)stride_elems);
+        return TT_ERR_CUDA;
+    }
+    return TT_OK;
+}
+
+template <int N, int CH>
+static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
+                  const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
+                  float* out_thresh, int n_lists, cudaStream_t st) {
+    constexpr int NQ = N / 2;
+    Params p;
+    p.inv_norm = inv_norm;
+    p.n_rows = n_rows;
+    p.id_base = id_base;
+    p.n_tiles = int((n_rows + TILE_ROWS - 1) / TILE_ROWS);
+    p.n_chunks = dim / CHUNK_COLS;
+    p.n_q = n_q;
+    p.kprime = kprime;
+    p.cap = kprime + TILE_ROWS;
+    p.has_lo = q_lo != nullptr;
+    p.out_ids = out_ids;
+    p.out_approx = out_approx;
+    p.out_thresh = out_thresh;
+
+    const size_t q_bytes = size_t(p.n_chunks) * N * 128;
+    const size_t fixed = 1024 /*align slack*/ + q_bytes + size_t(NQ) * p.cap * 8 + size_t(NQ) * 8 + 64;
+    const size_t per_stage = size_t(CH) * CHUNK_BYTES + 16;
+    if (fixed + 2 * per_stage > size_t(SMEM_LIMIT)) {
+        set_error("scan_tc: dim=%d kprime=%d does not fit shared memory with N=%d", dim, kprime, N);
+        return TT_ERR_UNSUPPORTED;
+    }
+    int stages = int((size_t(SMEM_LIMIT) - fixed) / per_stage);
+    if (stages > 16) stages = 16;
+    p.stages = stages;
+    const size_t smem = fixed + size_t(stages) * per_stage;
+
+    CUtensorMap map_c, map_qhi, map_qlo;
+    int rc = make_map(&map_c, corpus, n_rows, dim, stride, TILE_ROWS, CH);
+    if (rc) return rc;
+    rc = make_map(&map_qhi, q_hi, n_q, dim, dim, NQ, 1);
+    if (rc) return rc;
+    rc = make_map(&map_qlo, q_lo ? q_lo : q_hi, n_q, dim, dim, NQ, 1);
+    if (rc) return rc;
+
+    auto kern = scan_tc_kernel<N, CH>;
+    TT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    for (int q0 = 0; q0 < n_q; q0 += NQ) {
+        p.q0 = q0;
+        p.nq_here = (n_q - q0 < NQ) ? n_q - q0 : NQ;
+        kern<<<n_lists, THREADS, smem, st>>>(map_c, map_qhi, map_qlo, p);
+        TT_LAUNCH_OK("scan_tc_kernel");
+    }
+    return TT_OK;
+}
+
+}  // namespace tc
+
+bool scan_tc_supported(int64_t n_rows, int dim, int64_t stride, int kprime, const void* corpus) {
+    return dim % 128 == 0 && dim >= 128 && dim <= 2048 && stride % 8 == 0 && kprime >= 1 && kprime <= 128 &&
+           (reinterpret_cast<uintptr_t>(corpus) % 16) == 0 && n_rows > 0 && n_rows < (int64_t(1) << 31) - 256;
+}
+
+int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
+                   const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
+                   float* out_approx, float* out_thresh, int n_lists, cudaStream_t st) {
+    if (!scan_tc_supported(n_rows, dim, stride, kprime, corpus)) {
+        set_error("scan_tc: unsupported shape (n_rows=%lld dim=%d stride=%lld kprime=%d)", (long long)n_rows, dim,
+                  (long long)stride, kprime);
+        return TT_ERR_UNSUPPORTED;
+    }
+    if (n_q <= 8)
+        return tc::launch<16, 2>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids,
+                                 out_approx, out_thresh, n_lists, st);
+    return tc::launch<32, 2>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids,
+                             out_approx, out_thresh, n_lists, st);
+}
+
+}  // namespace tt

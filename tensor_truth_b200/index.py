@@ -1,0 +1,240 @@
+"""Device-resident index: the leaf-embedding matrix + the node-tree relation arrays in HBM, and the
+three-stage query pipeline over them (scan/shortlist -> exact re-score/top-k -> auto-merge).
+
+This is what replaces, per index, the Chroma collection + docstore pair the reference opens at
+/root/reference/src/tensortruth/rag_engine.py:628-639 and queries through
+``index.as_retriever(similarity_top_k=k)`` / ``AutoMergingRetriever`` (:639-645).  All arithmetic runs
+in ``libtt_b200.so`` (``include/tt_b200.h``); torch only owns the memory and the stream.
+
+HBM layout (one shard):
+  corpus     bf16 [n_rows, dim] row-major       streamed once per query batch by stage 1
+  master     fp32 [n_rows, dim] (optional)      only when the stored embeddings are fp32; stage 2 reads it
+  inv_norm   fp32 [n_rows]                      1/|c_r| of the bf16 rows (stage 1 epilogue)
+  parent_of, child_count, prev_id, next_id   int32 [n_nodes]   (tree.py; replicated on every shard)
+"""
+
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SCAN_AUTO, SCORE_COSINE, check, ptr
+from .tree import NodeTree
+
+# Certificate bounds on |approximate stage-1 score - exact cosine| ("Exactness"):
+EPS_BF16_CORPUS = 2.5e-4   # corpus stored in bf16: split residual + fp32 accumulation + inv_norm rounding
+EPS_F32_CORPUS = 2.3e-3    # fp32 master scanned through a bf16 shadow: + 2^-9 corpus rounding
+
+
+@dataclass
+class SearchResult:
+    keys: torch.Tensor      # float32 [B, k] ordering keys (cosine, or -squared-L2)
+    scores: torch.Tensor    # float32 [B, k] reported scores (cosine, or exp(-squared-L2))
+    ids: torch.Tensor       # int64   [B, k] global row ordinals, -1 padding
+    margin: Optional[torch.Tensor]  # float32 [B] certificate margin (None for the exact scan)
+
+
+@dataclass
+class MergeResult:
+    ids: torch.Tensor       # int64   [B, max_out] node ordinals, -1 padding
+    scores: torch.Tensor    # float64 [B, max_out]
+    lens: torch.Tensor      # int32   [B]
+
+
+def _as_device_corpus(corpus, device):
+    if isinstance(corpus, np.ndarray):
+        if corpus.dtype == np.uint16:  # bf16 bit patterns
+            t = torch.from_numpy(corpus.view(np.int16)).to(device).view(torch.bfloat16)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(corpus, dtype=np.float32)).to(device)
+    else:
+        t = corpus.to(device)
+    if t.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError(f"corpus dtype {t.dtype}: expected bfloat16 or float32")
+    if t.dim() != 2:
+        raise ValueError("corpus must be [n_rows, dim]")
+    return t.contiguous()
+
+
+class DeviceIndex:
+    """One shard of one index on one GPU."""
+
+    def __init__(self, corpus, tree: Optional[NodeTree] = None, inv_norm: Optional[torch.Tensor] = None,
+                 id_base: int = 0, device: Optional[torch.device] = None, kprime: int = 32,
+                 variant: int = SCAN_AUTO, score_mode: int = SCORE_COSINE):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tensor_truth_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        stored = _as_device_corpus(corpus, self.device)
+        if stored.dtype == torch.float32:
+            self.master = stored
+            self.corpus = stored.to(torch.bfloat16)
+            self.eps = EPS_F32_CORPUS
+        else:
+            self.master = None
+            self.corpus = stored
+            self.eps = EPS_BF16_CORPUS
+        self.n_rows, self.dim = int(self.corpus.shape[0]), int(self.corpus.shape[1])
+        if self.dim % 8:
+            raise ValueError("dim must be a multiple of 8")
+        self.id_base = int(id_base)
+        self.kprime = int(kprime)
+        self.variant = int(variant)
+        self.score_mode = int(score_mode)
+        with torch.cuda.device(self.device):
+            self.n_lists = int(self.lib.tt_scan_num_lists(self.device.index or 0))
+        if inv_norm is None:
+            inv_norm = torch.empty(self.n_rows, dtype=torch.float32, device=self.device)
+            step = 1 << 20
+            for lo in range(0, self.n_rows, step):
+                c = self.corpus[lo:lo + step].float()
+                inv_norm[lo:lo + step] = (c * c).sum(dim=1).clamp_min(1e-30).rsqrt()
+        self.inv_norm = inv_norm.to(self.device, torch.float32).contiguous()
+        self.set_tree(tree)
+        self._ws: dict = {}
+        self._lock = threading.Lock()  # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420)
+        self.fallbacks = 0             # queries whose certificate failed and were re-run through the exact scan
+
+    # ------------------------------------------------------------------ tree
+    def set_tree(self, tree: Optional[NodeTree]) -> None:
+        self.tree = tree
+        if tree is None:
+            self.parent_of = self.child_count = self.prev_id = self.next_id = None
+            self.n_nodes = 0
+            return
+        tree.validate()
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(self.device)  # noqa: E731
+        self.parent_of, self.child_count = up(tree.parent_of), up(tree.child_count)
+        self.prev_id, self.next_id = up(tree.prev_id), up(tree.next_id)
+        self.n_nodes = tree.n_nodes
+
+    # ------------------------------------------------------------------ workspaces
+    def _buffers(self, b: int, k: int):
+        key = (b, k)
+        w = self._ws.get(key)
+        if w is None:
+            dev, n_cand = self.device, self.n_lists * self.kprime
+            w = {
+                "q_hi": torch.empty((b, self.dim), dtype=torch.bfloat16, device=dev),
+                "q_lo": torch.empty((b, self.dim), dtype=torch.bfloat16, device=dev),
+                "cand_ids": torch.empty((b, n_cand), dtype=torch.int64, device=dev),
+                "cand_approx": torch.empty((b, n_cand), dtype=torch.float32, device=dev),
+                "cand_thresh": torch.empty((b, self.n_lists), dtype=torch.float32, device=dev),
+                "ws": torch.empty(max(1, int(self.lib.tt_rescore_workspace_bytes(b, n_cand))), dtype=torch.uint8, device=dev),
+                "keys": torch.empty((b, k), dtype=torch.float32, device=dev),
+                "scores": torch.empty((b, k), dtype=torch.float32, device=dev),
+                "ids": torch.empty((b, k), dtype=torch.int64, device=dev),
+                "margin": torch.empty((b,), dtype=torch.float32, device=dev),
+            }
+            self._ws[key] = w
+        return w
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    def _check_queries(self, q: torch.Tensor) -> torch.Tensor:
+        if q.dim() != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"queries must be [B, {self.dim}], got {tuple(q.shape)}")
+        if q.device != self.device or q.dtype != torch.float32 or not q.is_contiguous():
+            q = q.to(self.device, torch.float32).contiguous()
+        return q
+
+    # ------------------------------------------------------------------ stage 1 + 2
+    def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None) -> SearchResult:
+        """Shortlist scan + exact re-score.  Asynchronous on the current stream; ``margin[b] > eps``
+        certifies that query b's top-k is the exact one (``search_certified`` acts on it)."""
+        q = self._check_queries(q)
+        b = int(q.shape[0])
+        w = out if out is not None else self._buffers(b, k)
+        L, st = self.lib, self._stream()
+        n_cand = self.n_lists * self.kprime
+        with torch.cuda.device(self.device):
+            check(L.tt_prepare_queries(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), st))
+            check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self.corpus.stride(0), ptr(self.inv_norm),
+                                      ptr(w["q_hi"]), ptr(w["q_lo"]), b, self.kprime, self.id_base, self.variant,
+                                      ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]), st))
+            src = self.master if self.master is not None else self.corpus
+            check(L.tt_rescore_topk(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
+                                    self.n_rows, self.dim, src.stride(0), self.id_base, ptr(q), b,
+                                    ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), self.n_lists, k, self.score_mode,
+                                    ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
+                                    ptr(w["ws"]), w["ws"].numel(), st))
+        return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"])
+
+    def search_exact(self, q: torch.Tensor, k: int) -> SearchResult:
+        """fp64 scoring of every row (CUDA cores): certificate-failure fallback and on-GPU secondary oracle."""
+        q = self._check_queries(q)
+        b = int(q.shape[0])
+        dev = self.device
+        keys = torch.empty((b, k), dtype=torch.float32, device=dev)
+        scores = torch.empty((b, k), dtype=torch.float32, device=dev)
+        ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+        src = self.master if self.master is not None else self.corpus
+        with torch.cuda.device(dev):
+            nbytes = int(self.lib.tt_scan_exact_workspace_bytes(dev.index or 0, b, k))
+            ws = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
+            check(self.lib.tt_scan_exact_f64(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
+                                             self.n_rows, self.dim, src.stride(0), self.id_base, ptr(q), b, k,
+                                             self.score_mode, ptr(keys), ptr(scores), ptr(ids), ptr(ws), ws.numel(),
+                                             self._stream()))
+        return SearchResult(keys, scores, ids, None)
+
+    def search_certified(self, q: torch.Tensor, k: int) -> SearchResult:
+        """``search`` + certificate check (one device->host read of the margins); queries that are not
+        proven exact are re-run through ``search_exact``.  Synchronises the current stream."""
+        q = self._check_queries(q)
+        r = self.search(q, k)
+        bad = torch.nonzero(~(r.margin > self.eps)).flatten()  # NaN-safe
+        if bad.numel():
+            self.fallbacks += int(bad.numel())
+            ex = self.search_exact(q.index_select(0, bad), k)
+            r.keys.index_copy_(0, bad, ex.keys)
+            r.scores.index_copy_(0, bad, ex.scores)
+            r.ids.index_copy_(0, bad, ex.ids)
+        return r
+
+    # ------------------------------------------------------------------ stage 3
+    def automerge(self, ids: torch.Tensor, scores: torch.Tensor, ratio_thresh: float = 0.5, max_rounds: int = 64,
+                  out: Optional[MergeResult] = None) -> MergeResult:
+        if self.tree is None:
+            raise RuntimeError("this index has no node tree: auto-merge is not available")
+        b, k = int(ids.shape[0]), int(ids.shape[1])
+        max_out = max(2 * k, 1)
+        if out is None:
+            out = MergeResult(torch.empty((b, max_out), dtype=torch.int64, device=self.device),
+                              torch.empty((b, max_out), dtype=torch.float64, device=self.device),
+                              torch.empty((b,), dtype=torch.int32, device=self.device))
+        with torch.cuda.device(self.device):
+            check(self.lib.tt_automerge(ptr(ids), ptr(scores), b, k, ptr(self.parent_of), ptr(self.child_count),
+                                        ptr(self.prev_id), ptr(self.next_id), self.n_nodes, float(ratio_thresh),
+                                        int(max_rounds), ptr(out.ids), ptr(out.scores), ptr(out.lens),
+                                        int(out.ids.shape[1]), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ whole path, host in / host out
+    def retrieve_host(self, q_host: torch.Tensor, k: int, ratio_thresh: float = 0.5, merge: bool = True):
+        """Query embeddings in host memory -> merged ``(ids, scores, lens)`` in host memory (numpy).
+        The H2D copy of the queries and the D2H read of the result are part of the call."""
+        with self._lock:
+            q = q_host.to(self.device, torch.float32, non_blocking=True)
+            r = self.search_certified(q, k)
+            if merge and self.tree is not None:
+                m = self.automerge(r.ids, r.scores, ratio_thresh)
+                ids, scores, lens = m.ids.cpu(), m.scores.cpu(), m.lens.cpu()
+            else:
+                ids, scores = r.ids.cpu(), r.scores.double().cpu()
+                lens = (ids >= 0).sum(dim=1).to(torch.int32)
+            return ids.numpy(), scores.numpy(), lens.numpy()
+
+    def close(self) -> None:
+        """Drop device memory (``RAGService.clear`` -> ``MultiIndexRetriever.clear_cache`` path, rag_service.py:720)."""
+        self._ws.clear()
+        self.corpus = self.master = self.inv_norm = None
+        self.parent_of = self.child_count = self.prev_id = self.next_id = None
