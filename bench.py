@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""Benchmark of the retrieval hot path (scan -> exact top-k -> auto-merge) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (oracle port, all host threads)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # N > 1: one rank per GPU, corpus row-sharded
+
+Workload (BASELINE.json configs[1]): exact cosine top-10 + auto-merge over 10,000,000 x 1024 bf16 leaf
+embeddings with a 3-level node tree, batch-1 queries (the headline, HBM-bound); batch-64 is reported in
+`batch64`.  A step = one query batch through the whole device pipeline.  N > 1 shards the SAME corpus
+by rows over the ranks ("scaling": "strong"): local exact top-k -> one NCCL all-gather -> k-way merge
+-> auto-merge on the merged list.  The corpus streamed per step (20.5 GB / N per GPU) is far larger than
+the 126 MB L2, so no explicit flush is needed between steps.
+
+Prints ONE JSON line (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "queries/sec exact top-10 (+auto-merge) over 10M x 1024 chunks, batch-1"
+UNIT = "queries/s"
+N_ROWS = 10_000_000
+DIM = 1024
+TOP_K = 10
+LEVELS = 3
+SEED = 1234
+QUERY_POOL = 64
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clocks and throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    _NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+              0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+              0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self._NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- workload
+def physical_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def build_shard(n_rows, rank, world, device, levels=LEVELS):
+    from tensor_truth_b200.sharded import shard_bounds
+    from tensor_truth_b200.synth import SynthCorpus
+
+    sc = SynthCorpus(n_rows, DIM, levels, SEED, device=device)
+    lo, hi = shard_bounds(n_rows, world, rank)
+    corpus, inv = sc.rows(lo, hi)
+    return sc, corpus, inv, lo, hi
+
+
+def make_queries(sc, corpus, lo, hi, n_q, world):
+    import torch.distributed as dist
+
+    def lookup(t):
+        return corpus[t - lo] if lo <= t < hi else None
+
+    q = sc.queries(n_q, lookup=lookup)
+    if world > 1:
+        qd = q.cuda()
+        dist.all_reduce(qd)  # every target row is owned by exactly one rank; the other ranks contribute zeros
+        q = qd.cpu()
+    return sc.finish_queries(q)
+
+
+def cpu_arm(bits, inv_norm, tree, queries, k, n_steps, n_warm, budget_s=25.0):
+    """The CPU restatement in its fast mode on every host thread (oracle/c/oracle_fast.c + oracle/automerge.py):
+    one step = one batch-1 query over the sample rows + auto-merge.  Returns (seconds per step, steps run)."""
+    import oracle
+    from oracle import cport
+
+    def step(i):
+        q = queries[i % len(queries)][None, :]
+        ids, sc = cport.fast_scan_topk(bits, inv_norm, q, k)
+        pairs = [(int(o), float(s)) for o, s in zip(ids[0], sc[0]) if o >= 0]
+        return oracle.auto_merge(pairs, tree.parent_of, tree.child_count, tree.prev_id, tree.next_id)
+
+    for i in range(n_warm):
+        step(i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(n_steps):
+        step(n_warm + i)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return (time.perf_counter() - t0) / done, done
+
+
+# --------------------------------------------------------------------------- this repo's arm
+def run_b200(args):
+    import torch.distributed as dist
+
+    from tensor_truth_b200 import _lib
+    from tensor_truth_b200.index import DeviceIndex
+    from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200VectorIndexRetriever
+    from tensor_truth_b200.schema import QueryBundle
+    from tensor_truth_b200.sharded import ShardedIndex
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    device = torch.device(f"cuda:{local_rank}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _lib.lib()  # fail loudly if the CUDA library is missing
+
+    n_rows = args.rows
+    sc, corpus, inv, lo, hi = build_shard(n_rows, rank, world, device)
+    queries = make_queries(sc, corpus, lo, hi, QUERY_POOL, world).to(device)
+    variant = {"auto": _lib.SCAN_AUTO, "simt": _lib.SCAN_SIMT, "tcgen05": _lib.SCAN_TCGEN05}[args.variant]
+    idx = DeviceIndex(corpus, sc.tree, inv_norm=inv, id_base=lo, device=device, kprime=args.kprime, variant=variant)
+    sharded = ShardedIndex(idx) if world > 1 else None
+    peak, peak_src = measured_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(batch: int, steps: int, warm: int, sample_clocks: bool):
+        margins = torch.full((steps + warm, batch), float("inf"), dtype=torch.float32, device=device)
+        base = idx._buffers(batch, TOP_K)
+        n_pool = QUERY_POOL // batch if batch <= QUERY_POOL else 1
+
+        def one(i):
+            q = queries[(i % n_pool) * batch:(i % n_pool) * batch + batch]
+            if sharded is None:
+                w = dict(base)
+                w["margin"] = margins[i]
+                r = idx.search(q, TOP_K, out=w)
+                return idx.automerge(r.ids, r.scores)
+            scores, ids = sharded.search(q, TOP_K, margins=margins[i])
+            return idx.automerge(ids, scores)
+
+        for i in range(warm):
+            one(i)
+        barrier()
+        idx.scan_events = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(physical_index(local_rank)) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
+        e0.record()
+        for i in range(steps):
+            last = one(warm + i)
+        e1.record()
+        barrier()
+        if sampler:
+            sampler.__exit__()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        ev = idx.scan_events
+        idx.scan_events = None
+        scan_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])))
+        n_scan_launches = len(ev) // steps
+        bad = int((~(margins > idx.eps)).sum().item())
+        return ms, scan_ms, n_scan_launches, bad, last, (sampler.summary() if sampler else None)
+
+    # ---- headline: batch-1
+    ms1, scan1_ms, nl1, bad1, last, clocks = timed(1, args.steps, args.warmup, True)
+    value = args.steps * 1 / (ms1 / 1e3)
+    local_bytes = float(hi - lo) * DIM * 2
+    achieved = local_bytes / (scan1_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("rows") == hi - lo and tj.get("batch") == 1:
+            traffic = tj.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+
+    # ---- batch-64 (same corpus; tensor work rises, HBM bytes per pass do not)
+    steps64 = max(3, min(args.steps, 40))
+    ms64, scan64_ms, nl64, bad64, _, _ = timed(64, steps64, 3, False)
+    value64 = steps64 * 64 / (ms64 / 1e3)
+
+    # ---- parity spot check inside the bench: the timed path vs the on-GPU exact fp64 scan of the same shard(s)
+    qs = queries[:4]
+    if sharded is None:
+        r = idx.search(qs, TOP_K)
+        got_ids, got_sc = r.ids.clone(), r.scores.clone()
+        ex = idx.search_exact(qs, TOP_K)
+        parity_ok = bool(torch.equal(got_ids, ex.ids) and torch.equal(got_sc, ex.scores))
+    else:
+        scores, ids = sharded.search(qs, TOP_K)
+        got_ids, got_sc = ids.clone(), scores.clone()
+        ex = idx.search_exact(qs, TOP_K)
+        sharded.plumbing.local_search = lambda q, k, ko, io: (ko.copy_(ex.keys), io.copy_(ex.ids))
+        s2, i2 = sharded.plumbing.search(qs, TOP_K)
+        parity_ok = bool(torch.equal(got_ids, i2) and torch.equal(got_sc, s2))
+        sharded.plumbing.local_search = sharded._local_search
+    torch.cuda.synchronize()
+
+    # ---- end to end through the public retriever API: host query in, NodeWithScore list out
+    e2e_steps = max(5, min(args.steps, 100))
+    q_host = queries.cpu()
+    if sharded is None:
+        base_r = B200VectorIndexRetriever(idx, similarity_top_k=TOP_K)
+        am = B200AutoMergingRetriever(base_r, None)
+        call = lambda i: am.retrieve(QueryBundle(query_str=f"q{i}", embedding=q_host[i % QUERY_POOL].tolist()))  # noqa: E731
+    else:
+        pinned = q_host.pin_memory()
+        call = lambda i: sharded.retrieve_host(pinned[i % QUERY_POOL:i % QUERY_POOL + 1], TOP_K)  # noqa: E731
+    for i in range(3):
+        out = call(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        out = call(3 + i)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    n_out = len(out) if sharded is None else int(out[2][0])
+    e2e = {"value": e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": DIM * 4,
+           "d2h_bytes_per_step": 4 + 2 * TOP_K * (8 + 8) + 4, "steps": e2e_steps,
+           "api": "B200AutoMergingRetriever.retrieve(QueryBundle)" if sharded is None else "ShardedIndex.retrieve_host",
+           "fallbacks": idx.fallbacks, "nodes_returned_last": n_out}
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same corpus bytes
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        sample = min(args.cpu_sample_rows, hi - lo)
+        bits = corpus[:sample].view(torch.int16).cpu().numpy().view(np.uint16)
+        inv_h = inv[:sample].cpu().numpy()
+        from oracle import cport
+
+        cport.build()
+        sec, done = cpu_arm(bits, inv_h, sc.tree, q_host.numpy(), TOP_K, 40, 2)
+        cpu = {"value": (1.0 / sec) * (sample / n_rows), "unit": UNIT, "cores": cport.fast_threads(), "kind": "port",
+               "sample": f"{done} batch-1 queries over the first {sample} of {n_rows} rows ({sec * 1e3:.1f} ms each), "
+                         f"q/s scaled by {sample}/{n_rows} (the scan is linear in rows); oracle/c/oracle_fast.c "
+                         f"fp32 AVX2 + OpenMP, auto-merge in oracle/automerge.py",
+               "host_cpus": os.cpu_count()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms1 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"C2: exact cosine top-{TOP_K} + auto-merge, {n_rows} x {DIM} bf16 leaf embeddings, "
+                                   f"{LEVELS}-level tree, batch-1 queries, corpus row-sharded over {world} GPU(s)",
+                       "rows_per_gpu": hi - lo, "batch": 1, "k": TOP_K, "kprime": args.kprime, "variant": args.variant,
+                       "l2": "no flush: every step streams the whole shard (>= 2.5 GB) through a 126 MB L2",
+                       "seed": SEED},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "scan_tc_kernel" if args.variant != "simt" else "scan_simt_kernel",
+                         "bytes_per_launch": local_bytes, "kernel_ms": scan1_ms, "peak_source": peak_src,
+                         "step_share": scan1_ms * nl1 / (ms1 / args.steps)},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": args.steps * (4 + nl1 + (1 if world > 1 else 0)),
+            "clocks": clocks,
+            "batch64": {"value": value64, "unit": UNIT, "ms_per_step": ms64 / steps64, "steps": steps64,
+                        "scan_launches_per_step": nl64, "scan_ms_per_launch": scan64_ms,
+                        "hbm_frac_per_launch": local_bytes / (scan64_ms / 1e3) / 1e9 / peak,
+                        "certificate_failures": bad64},
+            "certificate_failures": bad1,
+            "parity_vs_gpu_exact_scan": parity_ok,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------- the CPU arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cport
+    from tensor_truth_b200.synth import SynthCorpus
+
+    cport.build()
+    n_rows = args.rows
+    sample = min(args.cpu_sample_rows, n_rows)
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    sc = SynthCorpus(n_rows, DIM, LEVELS, SEED, device=dev)
+    corpus, inv = sc.rows(0, sample)
+    tgt = sc.query_targets(QUERY_POOL) % sample  # keep the targets inside the sample
+    q = torch.zeros((QUERY_POOL, DIM))
+    for j in range(QUERY_POOL):
+        g = torch.Generator(device="cpu")
+        g.manual_seed(SEED * 7_368_787 + 11 + j)
+        q[j] = corpus[int(tgt[j])].float().cpu() + (0.3 / DIM ** 0.5) * torch.randn(DIM, generator=g)
+    q = sc.finish_queries(q).numpy()
+    bits = corpus.view(torch.int16).cpu().numpy().view(np.uint16)
+    inv_h = inv.cpu().numpy()
+    del corpus
+    # calibrate so that warmup + steps stay within a few minutes
+    sec, _ = cpu_arm(bits, inv_h, sc.tree, q, TOP_K, 1, 1)
+    budget = 150.0
+    if sec * (args.steps + args.warmup) > budget:
+        sample = max(65536, int(sample * budget / (sec * (args.steps + args.warmup))) // 1024 * 1024)
+        bits, inv_h = bits[:sample], inv_h[:sample]
+    sec, done = cpu_arm(bits, inv_h, sc.tree, q, TOP_K, args.steps, args.warmup, budget_s=budget)
+    value = (1.0 / sec) * (sample / n_rows)
+    cores = cport.fast_threads()
+    desc = (f"{done} batch-1 queries over the first {sample} of {n_rows} rows ({sec * 1e3:.1f} ms each), q/s scaled by "
+            f"{sample}/{n_rows} (the scan is linear in rows); oracle/c/oracle_fast.c fp32 AVX2 + OpenMP on {cores} threads, "
+            f"auto-merge in oracle/automerge.py.  The reference's own stack (llama-index + chromadb) is not installable here.")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 * (n_rows / sample), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2: exact cosine top-{TOP_K} + auto-merge, {n_rows} x {DIM} bf16 leaf embeddings, "
+                                   f"{LEVELS}-level tree, batch-1 queries (CPU arm on a {sample}-row sample)",
+                       "batch": 1, "k": TOP_K, "seed": SEED},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=N_ROWS)
+    ap.add_argument("--kprime", type=int, default=32)
+    ap.add_argument("--variant", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_048_576)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -128,9 +128,12 @@ int tt_scan_exact_f64(const void* corpus, int corpus_dtype, int64_t n_rows, int 
 /*
  * k-way merge of per-shard top-k lists after the all-gather (row-sharded corpus).
  *   keys float [n_lists, n_q, k_in], ids int64 [n_lists, n_q, k_in]  (rank-major, as all_gather lays them)
+ *   keys_list_stride / ids_list_stride: elements between consecutive lists (0 = dense, n_q*k_in), so
+ *   that keys and ids can live in one all-gathered record per rank.
  *   out_scores float [n_q, k_out] (score_mode applied to the merged keys), out_ids int64 [n_q, k_out]
  */
-int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int n_q, int k_in, int k_out,
+int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
+                  int64_t ids_list_stride, int n_q, int k_in, int k_out,
                   int score_mode, float* out_scores, int64_t* out_ids, void* stream);
 
 /*

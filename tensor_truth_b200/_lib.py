@@ -30,7 +30,7 @@ SIGNATURES = {
     "tt_rescore_topk": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "tt_scan_exact_workspace_bytes": (_Z, [_I, _I, _I]),
     "tt_scan_exact_f64": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
-    "tt_merge_topk": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "tt_merge_topk": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P]),
     "tt_automerge_max_k": (_I, []),
     "tt_automerge": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _L, _D, _I, _P, _P, _P, _I, _P]),
 }

@@ -21,8 +21,8 @@ int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, 
 int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
                    const float* q, int n_q, const int64_t* cand_ids, int n_cand, int mode, uint64_t* packed,
                    cudaStream_t st);
-int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists, int n_q,
-                  int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys, float* out_scores,
+int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists,
+                  int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys, float* out_scores,
                   int64_t* out_ids, float* out_margin, cudaStream_t st);
 int launch_automerge(const int64_t* ids, const float* scores, int n_q, int k, const int32_t* parent_of,
                      const int32_t* child_count, const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
@@ -153,7 +153,7 @@ int tt_rescore_topk(const void* corpus, int corpus_dtype, int64_t n_rows, int di
     int rc = launch_rescore(corpus, corpus_dtype, n_rows, dim, row_stride_elems, id_base, q_f32, n_q, cand_ids, n_cand,
                             score_mode, packed, TT_STREAM(stream));
     if (rc) return rc;
-    return launch_select(packed, n_cand, nullptr, nullptr, 0, n_q, 0, k, score_mode, cand_thresh,
+    return launch_select(packed, n_cand, nullptr, nullptr, 0, 0, 0, n_q, 0, k, score_mode, cand_thresh,
                          cand_thresh ? n_lists : 0, out_keys, out_scores, out_ids, out_margin, TT_STREAM(stream));
 }
 
@@ -194,19 +194,21 @@ int tt_scan_exact_f64(const void* corpus, int corpus_dtype, int64_t n_rows, int 
     int rc = scan_simt_exact(corpus, corpus_dtype, n_rows, dim, row_stride_elems, q_f32, n_q, kp, id_base, score_mode,
                              packed, n_lists, TT_STREAM(stream));
     if (rc) return rc;
-    return launch_select(packed, n_lists * kp, nullptr, nullptr, 0, n_q, 0, k, score_mode, nullptr, 0, out_keys,
+    return launch_select(packed, n_lists * kp, nullptr, nullptr, 0, 0, 0, n_q, 0, k, score_mode, nullptr, 0, out_keys,
                          out_scores, out_ids, nullptr, TT_STREAM(stream));
 }
 
-int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int n_q, int k_in, int k_out, int score_mode,
-                  float* out_scores, int64_t* out_ids, void* stream) {
+int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride, int64_t ids_list_stride,
+                  int n_q, int k_in, int k_out, int score_mode, float* out_scores, int64_t* out_ids, void* stream) {
+    TT_CHECK_ARG(keys_list_stride >= 0 && ids_list_stride >= 0, "tt_merge_topk: negative list stride");
     TT_CHECK_ARG(n_lists >= 1 && n_q >= 0 && k_in >= 1 && k_out >= 1, "tt_merge_topk: n_lists=%d n_q=%d k_in=%d k_out=%d",
                  n_lists, n_q, k_in, k_out);
     TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_merge_topk: score_mode %d",
                  score_mode);
     if (n_q == 0) return TT_OK;
     TT_CHECK_ARG(keys && ids && out_ids, "tt_merge_topk: null pointer");
-    return launch_select(nullptr, 0, keys, ids, n_lists, n_q, k_in, k_out, score_mode, nullptr, 0, nullptr, out_scores,
+    return launch_select(nullptr, 0, keys, ids, n_lists, keys_list_stride, ids_list_stride, n_q, k_in, k_out, score_mode,
+                         nullptr, 0, nullptr, out_scores,
                          out_ids, nullptr, TT_STREAM(stream));
 }
 

@@ -105,6 +105,7 @@ constexpr int SEL_THREADS = 1024;
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __restrict__ packed, int n_in,
                                                              const float* __restrict__ in_keys,
                                                              const int64_t* __restrict__ in_ids, int n_lists,
+                                                             int64_t keys_stride, int64_t ids_stride,
                                                              int n_q, int k_in, int chunk /* pow2 */, int k,
                                                              int mode, const float* __restrict__ thresh,
                                                              int n_thresh, float* __restrict__ out_keys,
@@ -128,9 +129,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
                     e = packed[size_t(b) * n_in + j];
                 } else {
                     const int l = j / k_in, t = j - l * k_in;
-                    const size_t o = (size_t(l) * n_q + b) * k_in + t;
-                    const int64_t id = in_ids[o];
-                    e = id >= 0 ? pack_entry(in_keys[o], uint32_t(id)) : 0ull;
+                    const size_t o = size_t(b) * k_in + t;
+                    const int64_t id = in_ids[size_t(l) * ids_stride + o];
+                    e = id >= 0 ? pack_entry(in_keys[size_t(l) * keys_stride + o], uint32_t(id)) : 0ull;
                 }
             }
             s[carried + i] = e;
@@ -177,7 +178,7 @@ static int pow2_at_least(int n) {
 }
 
 int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists,
-                  int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys,
+                  int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys,
                   float* out_scores, int64_t* out_ids, float* out_margin, cudaStream_t st) {
     const int total = packed ? n_in : n_lists * k_in;
     constexpr int MAX_CHUNK = 8192;  // 64 KB of shared memory
@@ -193,7 +194,9 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
         attr_set = true;
     }
     if (n_q == 0) return TT_OK;
-    select_kernel<<<n_q, SEL_THREADS, smem, st>>>(packed, n_in, in_keys, in_ids, n_lists, n_q, k_in, chunk, k, mode,
+    if (keys_stride == 0) keys_stride = int64_t(n_q) * k_in;
+    if (ids_stride == 0) ids_stride = int64_t(n_q) * k_in;
+    select_kernel<<<n_q, SEL_THREADS, smem, st>>>(packed, n_in, in_keys, in_ids, n_lists, keys_stride, ids_stride, n_q, k_in, chunk, k, mode,
                                                   thresh, n_thresh, out_keys, out_scores, out_ids, out_margin);
     TT_LAUNCH_OK("select_kernel");
     return TT_OK;

@@ -100,6 +100,7 @@ class DeviceIndex:
         self._ws: dict = {}
         self._lock = threading.Lock()  # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420)
         self.fallbacks = 0             # queries whose certificate failed and were re-run through the exact scan
+        self.scan_events = None        # bench hook: a list collects (start, end) CUDA events around every stage-1 launch
 
     # ------------------------------------------------------------------ tree
     def set_tree(self, tree: Optional[NodeTree]) -> None:
@@ -157,9 +158,15 @@ class DeviceIndex:
         n_cand = self.n_lists * self.kprime
         with torch.cuda.device(self.device):
             check(L.tt_prepare_queries(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), st))
+            if self.scan_events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self.corpus.stride(0), ptr(self.inv_norm),
                                       ptr(w["q_hi"]), ptr(w["q_lo"]), b, self.kprime, self.id_base, self.variant,
                                       ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]), st))
+            if self.scan_events is not None:
+                e1.record()
+                self.scan_events.append((e0, e1))
             src = self.master if self.master is not None else self.corpus
             check(L.tt_rescore_topk(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
                                     self.n_rows, self.dim, src.stride(0), self.id_base, ptr(q), b,

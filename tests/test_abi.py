@@ -46,7 +46,7 @@ def test_argument_errors_come_back_as_codes_without_a_gpu(built):
     L = _lib.lib()
     rc = L.tt_prepare_queries(None, -1, 1024, None, None, None)
     assert rc == -1 and b"tt_prepare_queries" in L.tt_last_error()
-    rc = L.tt_merge_topk(None, None, 0, 1, 10, 10, 0, None, None, None)
+    rc = L.tt_merge_topk(None, None, 0, 0, 0, 1, 10, 10, 0, None, None, None)
     assert rc == -1
     with pytest.raises(_lib.TTError):
         _lib.check(L.tt_rescore_topk(None, 7, 0, 1024, 1024, 0, None, 0, None, 0, None, 0, 10, 0, None, None, None, None, None, 0, None))

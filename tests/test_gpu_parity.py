@@ -92,8 +92,19 @@ def test_l2_mode_falls_back_to_exact(golden_dir):
     idx = _index(g["bits"], None, score_mode=1, variant=_lib.SCAN_SIMT)
     r = idx.search_certified(torch.from_numpy(g["queries"]).cuda(), 10)
     torch.cuda.synchronize()
-    assert idx.fallbacks == g["queries"].shape[0]
+    assert idx.fallbacks == 0  # 1536 rows < n_lists * kprime: nothing was left out of the shortlist, so it is exact as is
     assert (_np(r.ids) == g["l2_k10_ids"]).all() and (_np(r.scores) == g["l2_k10_scores"]).all()
+    # a corpus larger than the shortlist: rows are dropped by approximate cosine, so the certificate must refuse
+    rng = np.random.default_rng(3)
+    c = (rng.standard_normal((20000, 64)) * rng.uniform(0.5, 2.0, (20000, 1))).astype(np.float32)  # norms vary: L2 != cosine order
+    bits = oracle.f32_to_bf16_bits(c)
+    q = rng.standard_normal((4, 64)).astype(np.float32)
+    idx = _index(bits, None, score_mode=1, variant=_lib.SCAN_SIMT)
+    r = idx.search_certified(torch.from_numpy(q).cuda(), 10)
+    torch.cuda.synchronize()
+    assert idx.fallbacks == 4
+    ids_o, sc_o, _ = oracle.exact_topk(bits, q, 10, 1)
+    assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
 
 
 # --------------------------------------------------------------------------- hand-built auto-merge cases
@@ -242,7 +253,7 @@ def test_ragged_row_counts_and_k_larger_than_n(vname, variant, n_rows):
         c[n_rows - 1] = c[1]
     bits = oracle.f32_to_bf16_bits(c)
     q = rng.standard_normal((3, dim)).astype(np.float32)
-    q[1] = oracle.bf16_bits_to_f32(bits[1])  # query equal to a stored (duplicated) row
+    q[1] = oracle.bf16_bits_to_f32(bits[min(1, n_rows - 1)])  # query equal to a stored (duplicated) row
     idx = _index(bits, None, variant=variant)
     for k in (1, 10, 32):
         ids_o, sc_o, keys_o = oracle.exact_topk(bits, q, k)
@@ -295,7 +306,7 @@ def test_merge_topk_matches_oracle(golden_dir):
         ids = torch.from_numpy(np.stack([p[0] for p in parts])).cuda()
         o_sc = torch.empty((q.shape[0], 10), dtype=torch.float32, device="cuda")
         o_ids = torch.empty((q.shape[0], 10), dtype=torch.int64, device="cuda")
-        _lib.check(L.tt_merge_topk(_lib.ptr(keys), _lib.ptr(ids), len(parts), q.shape[0], 10, 10, mode,
+        _lib.check(L.tt_merge_topk(_lib.ptr(keys), _lib.ptr(ids), len(parts), 0, 0, q.shape[0], 10, 10, mode,
                                    _lib.ptr(o_sc), _lib.ptr(o_ids), torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         assert (_np(o_ids) == g[f"{tag}_k10_ids"]).all()
@@ -367,7 +378,7 @@ def test_big_self_retrieval_and_shard_merge(big):
     keys, ids = torch.stack(keys), torch.stack(ids)
     o_sc = torch.empty((q.shape[0], 10), dtype=torch.float32, device="cuda")
     o_ids = torch.empty((q.shape[0], 10), dtype=torch.int64, device="cuda")
-    _lib.check(_lib.lib().tt_merge_topk(_lib.ptr(keys), _lib.ptr(ids), 3, q.shape[0], 10, 10, 0, _lib.ptr(o_sc),
+    _lib.check(_lib.lib().tt_merge_topk(_lib.ptr(keys), _lib.ptr(ids), 3, 0, 0, q.shape[0], 10, 10, 0, _lib.ptr(o_sc),
                                         _lib.ptr(o_ids), torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert (_np(o_ids) == w_ids).all() and (_np(o_sc) == w_sc).all()
