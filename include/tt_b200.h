@@ -82,11 +82,16 @@ int tt_prepare_queries(const float* q_f32, int n_q, int dim, void* q_hi_bf16, vo
  *                                           a(r) <= out_thresh[b,l]  (-inf: l emitted all it saw)
  * q_lo_bf16 may be NULL (hi only: half the tensor work, wider certificate).
  * variant: TT_SCAN_AUTO | TT_SCAN_SIMT | TT_SCAN_TCGEN05.
+ * ws: tt_scan_workspace_bytes() bytes of device memory, zeroed ONCE by the caller when it allocates
+ *     them; the kernel leaves them zero.  Holds the dynamic tile scheduler's counters, so one
+ *     workspace must not be shared by launches that can overlap.  NULL = static tile interleave.
  */
+size_t tt_scan_workspace_bytes(void);
 int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
                       const float* inv_norm, const void* q_hi_bf16, const void* q_lo_bf16, int n_q,
                       int kprime, int64_t id_base, int variant,
-                      int64_t* out_ids, float* out_approx, float* out_thresh, void* stream);
+                      int64_t* out_ids, float* out_approx, float* out_thresh,
+                      void* ws, size_t ws_bytes, void* stream);
 
 /*
  * Stage 2 -- exact re-score of the shortlist + exact top-k.  Together with stage 1 this is the

@@ -17,7 +17,7 @@ int scan_simt_exact(const void* corpus, int corpus_dtype, int64_t n_rows, int di
 bool scan_tc_supported(int64_t n_rows, int dim, int64_t stride, int kprime, const void* corpus);
 int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
                    const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
-                   float* out_approx, float* out_thresh, int n_lists, cudaStream_t st);
+                   float* out_approx, float* out_thresh, int n_lists, int* sched, cudaStream_t st);
 int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
                    const float* q, int n_q, const int64_t* cand_ids, int n_cand, int mode, uint64_t* packed,
                    cudaStream_t st);
@@ -85,6 +85,8 @@ int tt_scan_num_lists(int device) { return sm_count(device); }
 
 int tt_scan_max_kprime(void) { return 128; }
 
+size_t tt_scan_workspace_bytes(void) { return 256; }
+
 int tt_prepare_queries(const float* q_f32, int n_q, int dim, void* q_hi_bf16, void* q_lo_bf16, void* stream) {
     TT_CHECK_ARG(n_q >= 0 && dim > 0, "tt_prepare_queries: n_q=%d dim=%d", n_q, dim);
     TT_CHECK_ARG(n_q == 0 || (q_f32 && q_hi_bf16), "tt_prepare_queries: null pointer");
@@ -94,7 +96,9 @@ int tt_prepare_queries(const float* q_f32, int n_q, int dim, void* q_hi_bf16, vo
 int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
                       const float* inv_norm, const void* q_hi_bf16, const void* q_lo_bf16, int n_q, int kprime,
                       int64_t id_base, int variant, int64_t* out_ids, float* out_approx, float* out_thresh,
-                      void* stream) {
+                      void* ws, size_t ws_bytes, void* stream) {
+    TT_CHECK_ARG(ws == nullptr || ws_bytes >= tt_scan_workspace_bytes(), "tt_scan_topk_bf16: workspace %zu < %zu bytes",
+                 ws_bytes, tt_scan_workspace_bytes());
     TT_CHECK_ARG(n_rows >= 0 && n_q >= 0, "tt_scan_topk_bf16: n_rows=%lld n_q=%d", (long long)n_rows, n_q);
     TT_CHECK_ARG(dim > 0 && dim % 8 == 0, "tt_scan_topk_bf16: dim=%d must be a positive multiple of 8", dim);
     TT_CHECK_ARG(row_stride_elems >= dim && row_stride_elems % 8 == 0, "tt_scan_topk_bf16: row stride %lld",
@@ -118,7 +122,8 @@ int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t 
             return TT_ERR_UNSUPPORTED;
         }
         return scan_tc_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, q_lo_bf16, n_q, kprime,
-                              id_base, out_ids, out_approx, out_thresh, n_lists, TT_STREAM(stream));
+                              id_base, out_ids, out_approx, out_thresh, n_lists, reinterpret_cast<int*>(ws),
+                              TT_STREAM(stream));
     }
     if (variant == TT_SCAN_SIMT)
         return scan_simt_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, q_lo_bf16, n_q, kprime,

@@ -171,6 +171,93 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
     }
 }
 
+// ------------------------------------------------------------------ select, small k: k rounds of block-wide max
+// For k <= SMALL_K and <= 8 entries per thread the k best are pulled out one at a time (register-resident
+// entries, warp shuffles, one __syncthreads per round) instead of sorting everything: ~1 us for k = 10.
+constexpr int SMALL_K = 32;
+constexpr int SMALL_EPT = 8;
+
+__device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        uint64_t o = shfl_xor_u64(v, m);
+        v = o > v ? o : v;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) select_small_kernel(
+    const uint64_t* __restrict__ packed, int n_in, const float* __restrict__ in_keys, const int64_t* __restrict__ in_ids,
+    int n_lists, int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode,
+    const float* __restrict__ thresh, int n_thresh, float* __restrict__ out_keys, float* __restrict__ out_scores,
+    int64_t* __restrict__ out_ids, float* __restrict__ out_margin) {
+    __shared__ uint64_t part[2][32];
+    __shared__ uint64_t win[SMALL_K];
+    __shared__ float red[32];
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int total = packed ? n_in : n_lists * k_in;
+    uint64_t e[SMALL_EPT];
+#pragma unroll
+    for (int i = 0; i < SMALL_EPT; ++i) {
+        const int j = t + i * SEL_THREADS;
+        uint64_t v = 0ull;
+        if (j < total) {
+            if (packed) {
+                v = packed[size_t(b) * n_in + j];
+            } else {
+                const int l = j / k_in, c = j - l * k_in;
+                const size_t o = size_t(b) * k_in + c;
+                const int64_t id = in_ids[size_t(l) * ids_stride + o];
+                v = id >= 0 ? pack_entry(in_keys[size_t(l) * keys_stride + o], uint32_t(id)) : 0ull;
+            }
+        }
+        e[i] = v;
+    }
+    for (int r = 0; r < k; ++r) {
+        uint64_t m = e[0];
+#pragma unroll
+        for (int i = 1; i < SMALL_EPT; ++i) m = e[i] > m ? e[i] : m;
+        m = warp_max_u64(m);
+        if (lane == 0) part[r & 1][warp] = m;
+        __syncthreads();
+        uint64_t w = warp_max_u64(part[r & 1][lane]);  // every warp reduces the 32 partials: no second barrier
+        if (t == 0) win[r] = w;
+        if (w != 0ull) {
+#pragma unroll
+            for (int i = 0; i < SMALL_EPT; ++i)
+                if (e[i] == w) e[i] = 0ull;  // entries are unique (the id is part of the word)
+        }
+    }
+    __syncthreads();
+    if (t < k) {
+        const uint64_t w = win[t];
+        const size_t o = size_t(b) * k + t;
+        const float key = w ? entry_key(w) : -INFINITY;
+        if (out_keys) out_keys[o] = key;
+        if (out_scores) out_scores[o] = w ? score_of_key(key, mode) : -INFINITY;
+        out_ids[o] = w ? int64_t(entry_id(w)) : int64_t(-1);
+    }
+    if (out_margin) {
+        float m = -INFINITY;
+        if (thresh)
+            for (int i = t; i < n_thresh; i += SEL_THREADS) m = fmaxf(m, thresh[size_t(b) * n_thresh + i]);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+        if (lane == 0) red[warp] = m;
+        __syncthreads();
+        if (t == 0) {
+            for (int w = 1; w < SEL_THREADS / 32; ++w) m = fmaxf(m, red[w]);
+            const uint64_t ek = win[k - 1];
+            float margin;
+            if (m == -INFINITY) margin = INFINITY;
+            else if (mode != TT_SCORE_COSINE) margin = -INFINITY;
+            else if (!ek) margin = -INFINITY;
+            else margin = entry_key(ek) - m;
+            out_margin[b] = margin;
+        }
+    }
+}
+
 static int pow2_at_least(int n) {
     int p = 32;
     while (p < n) p <<= 1;
@@ -181,6 +268,16 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
                   int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys,
                   float* out_scores, int64_t* out_ids, float* out_margin, cudaStream_t st) {
     const int total = packed ? n_in : n_lists * k_in;
+    if (keys_stride == 0) keys_stride = int64_t(n_q) * k_in;
+    if (ids_stride == 0) ids_stride = int64_t(n_q) * k_in;
+    if (k <= SMALL_K && total <= SMALL_EPT * SEL_THREADS) {
+        if (n_q == 0) return TT_OK;
+        select_small_kernel<<<n_q, SEL_THREADS, 0, st>>>(packed, n_in, in_keys, in_ids, n_lists, keys_stride, ids_stride, n_q,
+                                                         k_in, k, mode, thresh, n_thresh, out_keys, out_scores, out_ids,
+                                                         out_margin);
+        TT_LAUNCH_OK("select_small_kernel");
+        return TT_OK;
+    }
     constexpr int MAX_CHUNK = 8192;  // 64 KB of shared memory
     TT_CHECK_ARG(k >= 1 && k <= MAX_CHUNK / 2, "k=%d out of range [1, %d]", k, MAX_CHUNK / 2);
     int chunk = pow2_at_least(total > k ? total : k);
@@ -194,8 +291,6 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
         attr_set = true;
     }
     if (n_q == 0) return TT_OK;
-    if (keys_stride == 0) keys_stride = int64_t(n_q) * k_in;
-    if (ids_stride == 0) ids_stride = int64_t(n_q) * k_in;
     select_kernel<<<n_q, SEL_THREADS, smem, st>>>(packed, n_in, in_keys, in_ids, n_lists, keys_stride, ids_stride, n_q, k_in, chunk, k, mode,
                                                   thresh, n_thresh, out_keys, out_scores, out_ids, out_margin);
     TT_LAUNCH_OK("select_kernel");

@@ -17,6 +17,7 @@
 //   warp  4    TMA producer: corpus tile ring (STAGES x CH x 16 KB) + the query block once
 //   warp  5    TMEM allocation + single-thread tcgen05.mma issue, double-buffered accumulators
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tt_common.cuh"
 
@@ -155,11 +156,17 @@ struct Params {
     int64_t* out_ids;
     float* out_approx;
     float* out_thresh;
+    int* sched;      // {next-tile counter, finished-CTA counter}, both zero between launches; NULL = static interleave
 };
+
+constexpr int SCHED_SLOTS = 4;  // tile-id ring between the producer and the MMA / epilogue roles
 
 // Dynamic shared memory (base rounded up to 1024 B):
 //   [ Q: n_chunks x N x 128 B ][ ring: stages x CH x 16 KB ][ lists: NQ x cap x 8 B ][ thresh NQ f32 ][ cnt NQ i32 ]
-//   [ barriers: full[stages], empty[stages], q_full, tmem_full[2], tmem_empty[2] ][ tmem base ]
+//   [ barriers: full[stages], empty[stages], q_full, tmem_full[2], tmem_empty[2], sched_full[4], sched_empty[4] ]
+//   [ tmem base ][ tile ring int[4] ]
+// Tiles are handed out by the producer: tile = blockIdx.x first, then (dynamic) gridDim.x + atomicAdd(counter) or
+// (static) +gridDim.x; the id travels to the other roles through a 4-slot ring, -1 ends the stream.
 template <int N, int CH>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_qhi,
@@ -181,10 +188,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
     uint64_t* q_full = bars + 2 * p.stages;
     uint64_t* tmem_full = q_full + 1;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* sched_full = tmem_empty + 2;
+    uint64_t* sched_empty = sched_full + SCHED_SLOTS;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sched_empty + SCHED_SLOTS);
+    volatile int* tile_ring = reinterpret_cast<volatile int*>(tmem_base_s + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_my_tiles = (p.n_tiles > int(blockIdx.x)) ? (p.n_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
     const int steps_per_tile = p.n_chunks / CH;
     constexpr int TMEM_COLS = (2 * N < 32) ? 32 : 2 * N;  // power of two for N in {16, 32, 64}
 
@@ -197,6 +206,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(tmem_full + a), 1);
             mbar_init(smem_u32(tmem_empty + a), EPI_THREADS);
+        }
+        for (int r = 0; r < SCHED_SLOTS; ++r) {
+            mbar_init(smem_u32(sched_full + r), 1);
+            mbar_init(smem_u32(sched_empty + r), 1 + EPI_THREADS / 32);  // MMA thread + one lane per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -225,7 +238,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
 
     if (warp == 4) {
         // ===================================================== TMA producer
-        if (lane == 0 && n_my_tiles > 0) {
+        if (lane == 0) {
             mbar_expect_tx(smem_u32(q_full), uint32_t(p.n_chunks * (p.has_lo ? N : NQ) * 128));
             for (int c = 0; c < p.n_chunks; ++c) {
                 tma_load_3d(smem_u32(q_s + size_t(c) * N * 128), &map_qhi, 0, p.q0, c, smem_u32(q_full), POLICY_EVICT_LAST);
@@ -235,8 +248,16 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int i = 0; i < n_my_tiles; ++i) {
-                const int tile = int(blockIdx.x) + i * int(gridDim.x);
+            int tile = int(blockIdx.x);
+            for (int it = 0;; ++it) {
+                if (tile >= p.n_tiles) tile = -1;
+                const int slot = it & (SCHED_SLOTS - 1);
+                mbar_wait(smem_u32(sched_empty + slot), (uint32_t(it / SCHED_SLOTS) & 1u) ^ 1u);
+                tile_ring[slot] = tile;
+                mbar_arrive(smem_u32(sched_full + slot));  // release: publishes the tile id
+                if (tile < 0) break;
+                // claim the next tile now; the atomic's latency hides behind this tile's loads
+                const int next = p.sched ? int(gridDim.x) + atomicAdd(p.sched, 1) : tile + int(gridDim.x);
                 for (int s = 0; s < steps_per_tile; ++s) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
                     mbar_expect_tx(smem_u32(full_bar + stage), STAGE_BYTES);
@@ -244,16 +265,30 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
                                 smem_u32(full_bar + stage), POLICY_EVICT_FIRST);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
+                tile = next;
+            }
+            if (p.sched) {  // the last CTA to get here re-arms the counters for the next launch
+                __threadfence();
+                if (atomicAdd(p.sched + 1, 1) == int(gridDim.x) - 1) {
+                    p.sched[0] = 0;
+                    p.sched[1] = 0;
+                    __threadfence();
+                }
             }
         }
     } else if (warp == 5) {
         // ===================================================== MMA issuer (one thread)
-        if (lane == 0 && n_my_tiles > 0) {
+        if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_bf16(N);
             mbar_wait(smem_u32(q_full), 0);
             int stage = 0;
             uint32_t phase = 0;
-            for (int i = 0; i < n_my_tiles; ++i) {
+            for (int i = 0;; ++i) {
+                const int slot = i & (SCHED_SLOTS - 1);
+                mbar_wait(smem_u32(sched_full + slot), uint32_t(i / SCHED_SLOTS) & 1u);
+                const int tile_id = tile_ring[slot];
+                mbar_arrive(smem_u32(sched_empty + slot));
+                if (tile_id < 0) break;
                 const int a = i & 1;
                 mbar_wait(smem_u32(tmem_empty + a), (uint32_t(i >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
@@ -283,9 +318,14 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
         const int t = threadIdx.x;
         const int nq = p.nq_here;
         const int kp = p.kprime, cap = p.cap;
-        for (int i = 0; i < n_my_tiles; ++i) {
+        for (int i = 0;; ++i) {
+            const int slot = i & (SCHED_SLOTS - 1);
+            mbar_wait(smem_u32(sched_full + slot), uint32_t(i / SCHED_SLOTS) & 1u);
+            const int tile = tile_ring[slot];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(sched_empty + slot));
+            if (tile < 0) break;
             const int a = i & 1;
-            const int tile = int(blockIdx.x) + i * int(gridDim.x);
             const int64_t row = int64_t(tile) * TILE_ROWS + t;
             const bool row_ok = row < p.n_rows;
             float inv = 1.f;
@@ -406,9 +446,10 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int dim, int
 template <int N, int CH>
 static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
                   const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
-                  float* out_thresh, int n_lists, cudaStream_t st) {
+                  float* out_thresh, int n_lists, int* sched, cudaStream_t st) {
     constexpr int NQ = N / 2;
     Params p;
+    p.sched = sched;
     p.inv_norm = inv_norm;
     p.n_rows = n_rows;
     p.id_base = id_base;
@@ -423,14 +464,18 @@ static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, c
     p.out_thresh = out_thresh;
 
     const size_t q_bytes = size_t(p.n_chunks) * N * 128;
-    const size_t fixed = 1024 /*align slack*/ + q_bytes + size_t(NQ) * p.cap * 8 + size_t(NQ) * 8 + 64;
+    const size_t fixed = 1024 /*align slack*/ + q_bytes + size_t(NQ) * p.cap * 8 + size_t(NQ) * 8 + 160;
     const size_t per_stage = size_t(CH) * CHUNK_BYTES + 16;
     if (fixed + 2 * per_stage > size_t(SMEM_LIMIT)) {
         set_error("scan_tc: dim=%d kprime=%d does not fit shared memory with N=%d", dim, kprime, N);
         return TT_ERR_UNSUPPORTED;
     }
     int stages = int((size_t(SMEM_LIMIT) - fixed) / per_stage);
-    if (stages > 16) stages = 16;
+    if (stages > 24) stages = 24;
+    if (const char* e = getenv("TT_SCAN_STAGES")) {  // tuning knob
+        const int want = atoi(e);
+        if (want >= 2 && want < stages) stages = want;
+    }
     p.stages = stages;
     const size_t smem = fixed + size_t(stages) * per_stage;
 
@@ -462,17 +507,26 @@ bool scan_tc_supported(int64_t n_rows, int dim, int64_t stride, int kprime, cons
 
 int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
                    const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
-                   float* out_approx, float* out_thresh, int n_lists, cudaStream_t st) {
+                   float* out_approx, float* out_thresh, int n_lists, int* sched, cudaStream_t st) {
     if (!scan_tc_supported(n_rows, dim, stride, kprime, corpus)) {
         set_error("scan_tc: unsupported shape (n_rows=%lld dim=%d stride=%lld kprime=%d)", (long long)n_rows, dim,
                   (long long)stride, kprime);
         return TT_ERR_UNSUPPORTED;
     }
-    if (n_q <= 8)
-        return tc::launch<16, 2>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids,
-                                 out_approx, out_thresh, n_lists, st);
-    return tc::launch<32, 2>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids,
-                             out_approx, out_thresh, n_lists, st);
+    int ch = 2;
+    if (const char* e = getenv("TT_SCAN_CH")) ch = atoi(e);  // tuning knob: 64-column chunks per ring stage
+    if (const char* e = getenv("TT_SCAN_STATIC")) { if (atoi(e)) sched = nullptr; }
+#define TT_TC(NN, CC)                                                                                              \
+    return tc::launch<NN, CC>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids, \
+                              out_approx, out_thresh, n_lists, sched, st)
+    if (n_q <= 8) {
+        if (ch == 1) TT_TC(16, 1);
+        if (ch == 4 && dim % 256 == 0) TT_TC(16, 4);
+        TT_TC(16, 2);
+    }
+    if (ch == 1) TT_TC(32, 1);
+    TT_TC(32, 2);
+#undef TT_TC
 }
 
 }  // namespace tt

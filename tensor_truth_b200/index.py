@@ -132,6 +132,7 @@ class DeviceIndex:
                 "scores": torch.empty((b, k), dtype=torch.float32, device=dev),
                 "ids": torch.empty((b, k), dtype=torch.int64, device=dev),
                 "margin": torch.empty((b,), dtype=torch.float32, device=dev),
+                "scan_ws": torch.zeros(int(self.lib.tt_scan_workspace_bytes()), dtype=torch.uint8, device=dev),
             }
             self._ws[key] = w
         return w
@@ -163,7 +164,8 @@ class DeviceIndex:
                 e0.record()
             check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self.corpus.stride(0), ptr(self.inv_norm),
                                       ptr(w["q_hi"]), ptr(w["q_lo"]), b, self.kprime, self.id_base, self.variant,
-                                      ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]), st))
+                                      ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]),
+                                      ptr(w["scan_ws"]), w["scan_ws"].numel(), st))
             if self.scan_events is not None:
                 e1.record()
                 self.scan_events.append((e0, e1))
@@ -226,19 +228,67 @@ class DeviceIndex:
         return out
 
     # ------------------------------------------------------------------ whole path, host in / host out
+    def _record(self, b: int, k: int, merged: bool):
+        """One contiguous result record per query batch, so the whole answer (and the certificate margins)
+        comes back in ONE device->host copy into pinned memory:
+        ``[ lens i32 B | margin f32 B | ids i64 B*w | scores (f64 merged / f32 leaves) B*w ]``."""
+        key = ("rec", b, k, merged)
+        r = self._ws.get(key)
+        if r is None:
+            w = max(2 * k, 1) if merged else k
+            ssz = 8 if merged else 4
+            off_ids = 8 * b
+            off_sc = off_ids + 8 * b * w
+            total = off_sc + ssz * b * w
+
+            def views(base):
+                return {"lens": base[0:4 * b].view(torch.int32), "margin": base[4 * b:8 * b].view(torch.float32),
+                        "ids": base[off_ids:off_sc].view(torch.int64).view(b, w),
+                        "scores": base[off_sc:total].view(torch.float64 if merged else torch.float32).view(b, w)}
+
+            dev = torch.zeros(total, dtype=torch.uint8, device=self.device)
+            host = torch.zeros(total, dtype=torch.uint8).pin_memory()
+            r = self._ws[key] = {"dev": dev, "host": host, "d": views(dev), "h": views(host), "bytes": total,
+                                 "event": torch.cuda.Event()}
+        return r
+
     def retrieve_host(self, q_host: torch.Tensor, k: int, ratio_thresh: float = 0.5, merge: bool = True):
         """Query embeddings in host memory -> merged ``(ids, scores, lens)`` in host memory (numpy).
-        The H2D copy of the queries and the D2H read of the result are part of the call."""
+        The H2D copy of the queries and the single D2H read of the result record are part of the call;
+        the certificate is checked on the host from the margins in that record."""
+        merged = bool(merge and self.tree is not None)
         with self._lock:
             q = q_host.to(self.device, torch.float32, non_blocking=True)
-            r = self.search_certified(q, k)
-            if merge and self.tree is not None:
-                m = self.automerge(r.ids, r.scores, ratio_thresh)
-                ids, scores, lens = m.ids.cpu(), m.scores.cpu(), m.lens.cpu()
-            else:
-                ids, scores = r.ids.cpu(), r.scores.double().cpu()
-                lens = (ids >= 0).sum(dim=1).to(torch.int32)
-            return ids.numpy(), scores.numpy(), lens.numpy()
+            q = self._check_queries(q)
+            b = int(q.shape[0])
+            rec = self._record(b, k, merged)
+            d, h = rec["d"], rec["h"]
+            w = dict(self._buffers(b, k))
+            w["margin"] = d["margin"]
+            if not merged:
+                w["ids"], w["scores"] = d["ids"], d["scores"]
+            r = self.search(q, k, out=w)
+            if merged:
+                self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+            rec["host"].copy_(rec["dev"], non_blocking=True)
+            rec["event"].record()
+            rec["event"].synchronize()
+            bad = np.nonzero(~(h["margin"].numpy() > self.eps))[0]
+            if bad.size:  # not proven exact: answer those queries with the exact fp64 scan instead
+                self.fallbacks += int(bad.size)
+                sel = torch.from_numpy(bad).to(self.device)
+                ex = self.search_exact(q.index_select(0, sel), k)
+                r.keys.index_copy_(0, sel, ex.keys)
+                r.scores.index_copy_(0, sel, ex.scores)
+                r.ids.index_copy_(0, sel, ex.ids)
+                if merged:
+                    self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+                rec["host"].copy_(rec["dev"], non_blocking=True)
+                rec["event"].record()
+                rec["event"].synchronize()
+            ids, scores = h["ids"].numpy().copy(), h["scores"].numpy().astype(np.float64)
+            lens = h["lens"].numpy().copy() if merged else (ids >= 0).sum(axis=1).astype(np.int32)
+            return ids, scores, lens
 
     def close(self) -> None:
         """Drop device memory (``RAGService.clear`` -> ``MultiIndexRetriever.clear_cache`` path, rag_service.py:720)."""

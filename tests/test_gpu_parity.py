@@ -316,7 +316,7 @@ def test_merge_topk_matches_oracle(golden_dir):
 def test_bad_arguments_raise_not_abort():
     L = _lib.lib()
     with pytest.raises(_lib.TTError) as e:
-        _lib.check(L.tt_scan_topk_bf16(None, 10, 1000, 1000, None, None, None, 1, 32, 0, 0, None, None, None, None))
+        _lib.check(L.tt_scan_topk_bf16(None, 10, 1000, 1000, None, None, None, 1, 32, 0, 0, None, None, None, None, 0, None))
     assert e.value.code == -1
     with pytest.raises(_lib.TTError):
         _lib.check(L.tt_automerge(None, None, 1, 100000, None, None, None, None, 0, 0.5, 8, None, None, None, 4, None))
