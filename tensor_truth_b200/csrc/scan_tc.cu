@@ -151,7 +151,7 @@ struct Params {
     int nq_here;     // queries in this pass (<= N/2)
     int n_q;         // total queries (output row count)
     int kprime;
-    int cap;         // candidate list capacity per query: kprime + 128, <= 256
+    int cap;         // candidate list capacity per query: kprime + spare, <= 256
     int has_lo;
     int64_t* out_ids;
     float* out_approx;
@@ -167,11 +167,11 @@ constexpr int SCHED_SLOTS = 4;  // tile-id ring between the producer and the MMA
 //   [ tmem base ][ tile ring int[4] ]
 // Tiles are handed out by the producer: tile = blockIdx.x first, then (dynamic) gridDim.x + atomicAdd(counter) or
 // (static) +gridDim.x; the id travels to the other roles through a 4-slot ring, -1 ends the stream.
-template <int N, int CH>
+template <int N, int CH, bool HILO>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_qhi,
                const __grid_constant__ CUtensorMap map_qlo, const Params p) {
-    constexpr int NQ = N / 2;
+    constexpr int NQ = HILO ? N / 2 : N;  // queries per pass: two MMA columns each (hi, lo) or one (hi only)
     constexpr int STAGE_BYTES = CH * CHUNK_BYTES;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -217,14 +217,6 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
         thresh_s[threadIdx.x] = -INFINITY;
         cnt_s[threadIdx.x] = 0;
     }
-    if (!p.has_lo) {
-        // zero the lo halves of the query block (rows [NQ, N) of every chunk)
-        for (int i = threadIdx.x; i < p.n_chunks * NQ * 32; i += THREADS) {
-            const int c = i / (NQ * 32), r = i - c * (NQ * 32);
-            reinterpret_cast<uint32_t*>(q_s + size_t(c) * N * 128 + NQ * 128)[r] = 0u;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
     if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
                      "r"(uint32_t(TMEM_COLS))
@@ -239,10 +231,10 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
     if (warp == 4) {
         // ===================================================== TMA producer
         if (lane == 0) {
-            mbar_expect_tx(smem_u32(q_full), uint32_t(p.n_chunks * (p.has_lo ? N : NQ) * 128));
+            mbar_expect_tx(smem_u32(q_full), uint32_t(p.n_chunks * N * 128));
             for (int c = 0; c < p.n_chunks; ++c) {
                 tma_load_3d(smem_u32(q_s + size_t(c) * N * 128), &map_qhi, 0, p.q0, c, smem_u32(q_full), POLICY_EVICT_LAST);
-                if (p.has_lo)
+                if (HILO)
                     tma_load_3d(smem_u32(q_s + size_t(c) * N * 128 + NQ * 128), &map_qlo, 0, p.q0, c, smem_u32(q_full),
                                 POLICY_EVICT_LAST);
             }
@@ -341,43 +333,60 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
             tcgen05_fence_before();
             mbar_arrive(smem_u32(tmem_empty + a));  // accumulator is in registers: hand TMEM back
 
-            bool pushed = false;
+            // approximate scores of this row, one per query
+            float sc[NQ];
 #pragma unroll
-            for (int j = 0; j < NQ; ++j) {
-                if (j < nq) {
-                    const float s = (acc[j] + acc[NQ + j]) * inv;
-                    if (row_ok && s > thresh_s[j]) {
-                        const int slot = atomicAdd(cnt_s + j, 1);  // slot < cap: <= kprime before the tile, +128 at most
-                        lists[size_t(j) * cap + slot] = pack_entry(s, uint32_t(row));
-                        pushed = true;
+            for (int j = 0; j < NQ; ++j) sc[j] = (HILO ? acc[j] + acc[NQ + j] : acc[j]) * inv;
+
+            // Push survivors into the per-query lists.  A list holds cap = K' + spare entries; a push that finds it
+            // full stays pending, the list is cut back to its K' best (raising the threshold) and the push is
+            // retried -- so every row ever dropped, here or by the cut, scored <= the final threshold.
+            uint64_t pending = 0ull;
+            for (bool first = true;; first = false) {
+                bool did = false;
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    if (j < nq && (first ? row_ok : bool((pending >> j) & 1ull))) {
+                        pending &= ~(1ull << j);
+                        if (sc[j] > thresh_s[j]) {
+                            const int slot = atomicAdd(cnt_s + j, 1);
+                            if (slot < cap) lists[size_t(j) * cap + slot] = pack_entry(sc[j], uint32_t(row));
+                            else pending |= 1ull << j;
+                            did = true;
+                        }
                     }
                 }
-            }
-            if (!epi_bar_or(pushed)) continue;
-
-            // ---- some list grew: rank-select every list longer than K' back to its K' best
-            bool any = false;
-            for (int j = 0; j < nq; ++j) {
-                const int n = cnt_s[j];
-                if (n <= kp) continue;
-                any = true;
-                uint64_t* L = lists + size_t(j) * cap;
-                uint64_t e0 = t < n ? L[t] : 0ull, e1 = (t + EPI_THREADS) < n ? L[t + EPI_THREADS] : 0ull;
-                int r0 = 0, r1 = 0;
-                for (int m = 0; m < n; ++m) {
-                    const uint64_t x = L[m];
-                    r0 += x > e0 ? 1 : 0;
-                    r1 += x > e1 ? 1 : 0;
+                if (!epi_bar_or(did)) break;  // nobody pushed or is pending: the tile is done (one barrier per tile)
+                // cut every list longer than K' back to its K' best: one warp per query, rank by counting
+                for (int j = warp; j < nq; j += EPI_THREADS / 32) {
+                    const int n = min(cnt_s[j], cap);
+                    if (n <= kp) continue;
+                    uint64_t* L = lists + size_t(j) * cap;
+                    uint64_t e[8];
+                    int r[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int x = lane + 32 * u;
+                        e[u] = x < n ? L[x] : 0ull;
+                        r[u] = 0;
+                    }
+                    for (int m = 0; m < n; ++m) {
+                        const uint64_t x = L[m];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) r[u] += x > e[u] ? 1 : 0;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (lane + 32 * u < n && r[u] < kp) {
+                            L[r[u]] = e[u];
+                            if (r[u] == kp - 1) thresh_s[j] = entry_key(e[u]);
+                        }
+                    }
+                    if (lane == 0) cnt_s[j] = kp;
                 }
                 epi_bar_sync();
-                if (t < n && r0 < kp) L[r0] = e0;
-                if (t + EPI_THREADS < n && r1 < kp) L[r1] = e1;
-                if (t < n && r0 == kp - 1) thresh_s[j] = entry_key(e0);
-                if (t + EPI_THREADS < n && r1 == kp - 1) thresh_s[j] = entry_key(e1);
-                if (t == 0) cnt_s[j] = kp;
             }
-            (void)any;
-            epi_bar_sync();  // unconditional: nobody may push for the next tile while others still read the counts
         }
 
         // ---- emit this CTA's shortlist
@@ -443,11 +452,11 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int dim, int
     return TT_OK;
 }
 
-template <int N, int CH>
+template <int N, int CH, bool HILO>
 static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
                   const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
                   float* out_thresh, int n_lists, int* sched, cudaStream_t st) {
-    constexpr int NQ = N / 2;
+    constexpr int NQ = HILO ? N / 2 : N;
     Params p;
     p.sched = sched;
     p.inv_norm = inv_norm;
@@ -457,37 +466,53 @@ static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, c
     p.n_chunks = dim / CHUNK_COLS;
     p.n_q = n_q;
     p.kprime = kprime;
-    p.cap = kprime + TILE_ROWS;
-    p.has_lo = q_lo != nullptr;
+    p.has_lo = HILO;
     p.out_ids = out_ids;
     p.out_approx = out_approx;
     p.out_thresh = out_thresh;
 
+    // Shared-memory budget: the resident query block, then the candidate lists, the rest is the TMA ring.
+    // Lists hold K' + spare entries; spare = 128 never needs a retry (a tile pushes at most 128 rows per query);
+    // with many queries per pass the spare shrinks so that the ring keeps enough bytes in flight.
     const size_t q_bytes = size_t(p.n_chunks) * N * 128;
-    const size_t fixed = 1024 /*align slack*/ + q_bytes + size_t(NQ) * p.cap * 8 + size_t(NQ) * 8 + 160;
+    const size_t base = 1024 /*align slack*/ + q_bytes + size_t(NQ) * 8 + 160;
     const size_t per_stage = size_t(CH) * CHUNK_BYTES + 16;
-    if (fixed + 2 * per_stage > size_t(SMEM_LIMIT)) {
+    int spare = 0, stages = 0;
+    auto try_spare = [&](int sp, size_t want_ring) {
+        if (kprime + sp > 256) return false;
+        const size_t fixed = base + size_t(NQ) * (kprime + sp) * 8;
+        if (fixed + 2 * per_stage > size_t(SMEM_LIMIT)) return false;
+        const int st_n = int((size_t(SMEM_LIMIT) - fixed) / per_stage);
+        if (size_t(st_n) * CH * CHUNK_BYTES < want_ring) return false;
+        spare = sp;
+        stages = st_n;
+        return true;
+    };
+    // first choice: the largest spare that still leaves >= 96 KB of ring; else a small spare and whatever ring is left
+    if (!try_spare(128, 96 * 1024) && !try_spare(64, 96 * 1024) && !try_spare(32, 96 * 1024) && !try_spare(32, 0))
+        try_spare(16, 0);
+    if (!spare) {
         set_error("scan_tc: dim=%d kprime=%d does not fit shared memory with N=%d", dim, kprime, N);
         return TT_ERR_UNSUPPORTED;
     }
-    int stages = int((size_t(SMEM_LIMIT) - fixed) / per_stage);
     if (stages > 24) stages = 24;
     if (const char* e = getenv("TT_SCAN_STAGES")) {  // tuning knob
         const int want = atoi(e);
         if (want >= 2 && want < stages) stages = want;
     }
+    p.cap = kprime + spare;
     p.stages = stages;
-    const size_t smem = fixed + size_t(stages) * per_stage;
+    const size_t smem = base + size_t(NQ) * p.cap * 8 + size_t(stages) * per_stage;
 
     CUtensorMap map_c, map_qhi, map_qlo;
     int rc = make_map(&map_c, corpus, n_rows, dim, stride, TILE_ROWS, CH);
     if (rc) return rc;
     rc = make_map(&map_qhi, q_hi, n_q, dim, dim, NQ, 1);
     if (rc) return rc;
-    rc = make_map(&map_qlo, q_lo ? q_lo : q_hi, n_q, dim, dim, NQ, 1);
+    rc = make_map(&map_qlo, HILO ? q_lo : q_hi, n_q, dim, dim, NQ, 1);
     if (rc) return rc;
 
-    auto kern = scan_tc_kernel<N, CH>;
+    auto kern = scan_tc_kernel<N, CH, HILO>;
     TT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     for (int q0 = 0; q0 < n_q; q0 += NQ) {
         p.q0 = q0;
@@ -513,19 +538,19 @@ int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, 
                   (long long)stride, kprime);
         return TT_ERR_UNSUPPORTED;
     }
-    int ch = 2;
-    if (const char* e = getenv("TT_SCAN_CH")) ch = atoi(e);  // tuning knob: 64-column chunks per ring stage
-    if (const char* e = getenv("TT_SCAN_STATIC")) { if (atoi(e)) sched = nullptr; }
-#define TT_TC(NN, CC)                                                                                              \
-    return tc::launch<NN, CC>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids, \
-                              out_approx, out_thresh, n_lists, sched, st)
-    if (n_q <= 8) {
-        if (ch == 1) TT_TC(16, 1);
-        if (ch == 4 && dim % 256 == 0) TT_TC(16, 4);
-        TT_TC(16, 2);
+    if (const char* e = getenv("TT_SCAN_STATIC")) { if (atoi(e)) sched = nullptr; }  // tuning knob
+#define TT_TC(NN, CC, HL)                                                                                              \
+    return tc::launch<NN, CC, HL>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids, \
+                                  out_approx, out_thresh, n_lists, sched, st)
+    if (q_lo) {  // two MMA columns per query: 8 / 16 / 32 queries per pass
+        if (n_q <= 8) TT_TC(16, 2, true);
+        if (n_q <= 16) TT_TC(32, 2, true);
+        TT_TC(64, 1, true);
     }
-    if (ch == 1) TT_TC(32, 1);
-    TT_TC(32, 2);
+    // hi only: 16 / 32 / 64 queries per pass, wider certificate
+    if (n_q <= 16) TT_TC(16, 2, false);
+    if (n_q <= 32) TT_TC(32, 2, false);
+    TT_TC(64, 1, false);
 #undef TT_TC
 }
 

@@ -27,8 +27,10 @@ from ._lib import SCAN_AUTO, SCORE_COSINE, check, ptr
 from .tree import NodeTree
 
 # Certificate bounds on |approximate stage-1 score - exact cosine| ("Exactness"):
-EPS_BF16_CORPUS = 2.5e-4   # corpus stored in bf16: split residual + fp32 accumulation + inv_norm rounding
-EPS_F32_CORPUS = 2.3e-3    # fp32 master scanned through a bf16 shadow: + 2^-9 corpus rounding
+EPS_BF16_CORPUS = 2.5e-4   # corpus stored in bf16: hi/lo split residual + fp32 accumulation + inv_norm rounding
+EPS_F32_CORPUS = 4.2e-3    # fp32 master scanned through a bf16 shadow: + 2^-8 corpus rounding
+EPS_HI_ONLY = 3.95e-3      # added when the query travels as bf16 hi only (|q - bf16(q)| <= 2^-8 |q|)
+HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first (64 queries per corpus pass)
 
 
 @dataclass
@@ -37,6 +39,7 @@ class SearchResult:
     scores: torch.Tensor    # float32 [B, k] reported scores (cosine, or exp(-squared-L2))
     ids: torch.Tensor       # int64   [B, k] global row ordinals, -1 padding
     margin: Optional[torch.Tensor]  # float32 [B] certificate margin (None for the exact scan)
+    eps: float = 0.0        # the top-k of query b is proven exact iff margin[b] > eps
 
 
 @dataclass
@@ -100,6 +103,7 @@ class DeviceIndex:
         self._ws: dict = {}
         self._lock = threading.Lock()  # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420)
         self.fallbacks = 0             # queries whose certificate failed and were re-run through the exact scan
+        self.retries = 0               # queries of a hi-only batch re-run through the hi+lo scan
         self.scan_events = None        # bench hook: a list collects (start, end) CUDA events around every stage-1 launch
 
     # ------------------------------------------------------------------ tree
@@ -116,8 +120,9 @@ class DeviceIndex:
         self.n_nodes = tree.n_nodes
 
     # ------------------------------------------------------------------ workspaces
-    def _buffers(self, b: int, k: int):
-        key = (b, k)
+    def _buffers(self, b: int, k: int, slot: int = 0):
+        """Workspace set for a (batch, k) shape; ``slot`` separates sets used concurrently on different streams."""
+        key = (b, k, slot)
         w = self._ws.get(key)
         if w is None:
             dev, n_cand = self.device, self.n_lists * self.kprime
@@ -149,11 +154,15 @@ class DeviceIndex:
         return q
 
     # ------------------------------------------------------------------ stage 1 + 2
-    def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None) -> SearchResult:
-        """Shortlist scan + exact re-score.  Asynchronous on the current stream; ``margin[b] > eps``
-        certifies that query b's top-k is the exact one (``search_certified`` acts on it)."""
+    def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None, hi_only: Optional[bool] = None) -> SearchResult:
+        """Shortlist scan + exact re-score.  Asynchronous on the current stream; ``margin[b] > result.eps``
+        certifies that query b's top-k is the exact one (``search_certified`` acts on it).
+        ``hi_only``: send the queries through the tensor cores as bf16 hi halves only (twice the queries per
+        corpus pass, wider certificate); default: batches above ``HI_ONLY_ABOVE``."""
         q = self._check_queries(q)
         b = int(q.shape[0])
+        if hi_only is None:
+            hi_only = b > HI_ONLY_ABOVE
         w = out if out is not None else self._buffers(b, k)
         L, st = self.lib, self._stream()
         n_cand = self.n_lists * self.kprime
@@ -163,7 +172,8 @@ class DeviceIndex:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self.corpus.stride(0), ptr(self.inv_norm),
-                                      ptr(w["q_hi"]), ptr(w["q_lo"]), b, self.kprime, self.id_base, self.variant,
+                                      ptr(w["q_hi"]), None if hi_only else ptr(w["q_lo"]), b, self.kprime, self.id_base,
+                                      self.variant,
                                       ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]),
                                       ptr(w["scan_ws"]), w["scan_ws"].numel(), st))
             if self.scan_events is not None:
@@ -175,7 +185,7 @@ class DeviceIndex:
                                     ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), self.n_lists, k, self.score_mode,
                                     ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
                                     ptr(w["ws"]), w["ws"].numel(), st))
-        return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"])
+        return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], self.eps + (EPS_HI_ONLY if hi_only else 0.0))
 
     def search_exact(self, q: torch.Tensor, k: int) -> SearchResult:
         """fp64 scoring of every row (CUDA cores): certificate-failure fallback and on-GPU secondary oracle."""
@@ -200,14 +210,30 @@ class DeviceIndex:
         proven exact are re-run through ``search_exact``.  Synchronises the current stream."""
         q = self._check_queries(q)
         r = self.search(q, k)
-        bad = torch.nonzero(~(r.margin > self.eps)).flatten()  # NaN-safe
+        bad = torch.nonzero(~(r.margin > r.eps)).flatten()  # NaN-safe
+        if bad.numel():
+            self._repair(q, k, r, bad, hi_lo_first=r.eps > self.eps)
+        return r
+
+    def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool) -> None:
+        """Queries whose certificate failed: (a hi-only batch first gets the tighter hi+lo scan,) then the exact fp64 scan."""
+        if hi_lo_first:
+            sub = q.index_select(0, bad)
+            r2 = self.search(sub, k, out=dict(self._buffers(int(sub.shape[0]), k, slot=-1)), hi_only=False)
+            ok = r2.margin > r2.eps
+            good = bad[ok]
+            if good.numel():
+                r.keys.index_copy_(0, good, r2.keys[ok])
+                r.scores.index_copy_(0, good, r2.scores[ok])
+                r.ids.index_copy_(0, good, r2.ids[ok])
+            self.retries += int(bad.numel())
+            bad = bad[~ok]
         if bad.numel():
             self.fallbacks += int(bad.numel())
             ex = self.search_exact(q.index_select(0, bad), k)
             r.keys.index_copy_(0, bad, ex.keys)
             r.scores.index_copy_(0, bad, ex.scores)
             r.ids.index_copy_(0, bad, ex.ids)
-        return r
 
     # ------------------------------------------------------------------ stage 3
     def automerge(self, ids: torch.Tensor, scores: torch.Tensor, ratio_thresh: float = 0.5, max_rounds: int = 64,
@@ -273,14 +299,9 @@ class DeviceIndex:
             rec["host"].copy_(rec["dev"], non_blocking=True)
             rec["event"].record()
             rec["event"].synchronize()
-            bad = np.nonzero(~(h["margin"].numpy() > self.eps))[0]
-            if bad.size:  # not proven exact: answer those queries with the exact fp64 scan instead
-                self.fallbacks += int(bad.size)
-                sel = torch.from_numpy(bad).to(self.device)
-                ex = self.search_exact(q.index_select(0, sel), k)
-                r.keys.index_copy_(0, sel, ex.keys)
-                r.scores.index_copy_(0, sel, ex.scores)
-                r.ids.index_copy_(0, sel, ex.ids)
+            bad = np.nonzero(~(h["margin"].numpy() > r.eps))[0]
+            if bad.size:  # not proven exact: re-run those queries (tighter scan, then the exact fp64 scan)
+                self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.eps > self.eps)
                 if merged:
                     self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
                 rec["host"].copy_(rec["dev"], non_blocking=True)

@@ -34,9 +34,10 @@ def shard_bounds(n_rows: int, world: int, rank: int, align: int = 128) -> Tuple[
 class ShardedSearch:
     """Gather + merge plumbing, independent of where the local top-k comes from.
 
-    ``local_search(q, k, keys_out, ids_out)`` fills this rank's exact top-k (keys float32 [B,k], ids int64
-    [B,k], global ids) into the given views of the send record; ``merge(recv, world, b, k, k_out)`` returns
-    ``(scores float32 [B,k_out], ids int64 [B,k_out])`` from the gathered records ``recv`` (uint8 [world, rec])."""
+    ``local_search(q, k, keys_out, ids_out, slot)`` fills this rank's exact top-k (keys float32 [B,k], ids int64
+    [B,k], global ids) into the given views of the send record; ``merge(recv, world, b, k, k_out, slot)`` returns
+    ``(scores float32 [B,k_out], ids int64 [B,k_out])`` from the gathered records ``recv`` (uint8 [world, rec]).
+    ``slot`` selects one of several independent buffer sets (one per CUDA stream in a pipelined caller)."""
 
     def __init__(self, local_search: Callable, merge: Callable, device: torch.device, group=None):
         self.local_search, self.merge, self.device, self.group = local_search, merge, device, group
@@ -44,26 +45,29 @@ class ShardedSearch:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._bufs: dict = {}
 
-    def buffers(self, b: int, k: int):
-        w = self._bufs.get((b, k))
+    def buffers(self, b: int, k: int, slot: int = 0):
+        w = self._bufs.get((b, k, slot))
         if w is None:
             rec, ids_off, _ = record_layout(b, k)
             send = torch.zeros(rec, dtype=torch.uint8, device=self.device)
             recv = torch.zeros((self.world, rec), dtype=torch.uint8, device=self.device)
             keys = send[: b * k * 4].view(torch.float32).view(b, k)
             ids = send[ids_off: ids_off + b * k * 8].view(torch.int64).view(b, k)
-            w = self._bufs[(b, k)] = (send, recv, keys, ids)
+            w = self._bufs[(b, k, slot)] = (send, recv, keys, ids)
         return w
 
-    def search(self, q: torch.Tensor, k: int, k_out: Optional[int] = None):
-        b = int(q.shape[0])
-        send, recv, keys, ids = self.buffers(b, k)
-        self.local_search(q, k, keys, ids)
+    def exchange(self, send: torch.Tensor, recv: torch.Tensor) -> None:
         if self.world > 1:
             dist.all_gather_into_tensor(recv.view(-1), send, group=self.group)
         else:
             recv[0].copy_(send)
-        return self.merge(recv, self.world, b, k, k_out or k)
+
+    def search(self, q: torch.Tensor, k: int, k_out: Optional[int] = None, slot: int = 0):
+        b = int(q.shape[0])
+        send, recv, keys, ids = self.buffers(b, k, slot)
+        self.local_search(q, k, keys, ids, slot)
+        self.exchange(send, recv)
+        return self.merge(recv, self.world, b, k, k_out or k, slot)
 
 
 class ShardedIndex:
@@ -79,20 +83,21 @@ class ShardedIndex:
         self.plumbing = ShardedSearch(self._local_search, self._merge, self.device, group)
         self._out: dict = {}
 
-    def _local_search(self, q, k, keys_out, ids_out):
-        w = dict(self.local._buffers(int(q.shape[0]), k))
+    def _local_search(self, q, k, keys_out, ids_out, slot=0):
+        w = dict(self.local._buffers(int(q.shape[0]), k, slot))
         w["keys"], w["ids"] = keys_out, ids_out
         if self._margins is not None:
             w["margin"] = self._margins
-        self.local.search(q, k, out=w)
+        self.last = self.local.search(q, k, out=w)
+        return self.last
 
-    def _merge(self, recv, world, b, k, k_out):
+    def _merge(self, recv, world, b, k, k_out, slot=0):
         L, ptr, check = self._lib.lib(), self._lib.ptr, self._lib.check
         rec, ids_off, _ = record_layout(b, k)
-        o = self._out.get((b, k_out))
+        o = self._out.get((b, k_out, slot))
         if o is None:
-            o = self._out[(b, k_out)] = (torch.empty((b, k_out), dtype=torch.float32, device=self.device),
-                                         torch.empty((b, k_out), dtype=torch.int64, device=self.device))
+            o = self._out[(b, k_out, slot)] = (torch.empty((b, k_out), dtype=torch.float32, device=self.device),
+                                               torch.empty((b, k_out), dtype=torch.int64, device=self.device))
         import ctypes as C
 
         base = recv.data_ptr()
@@ -101,34 +106,40 @@ class ShardedIndex:
                                   self.local.score_mode, ptr(o[0]), ptr(o[1]), torch.cuda.current_stream().cuda_stream))
         return o
 
-    def search(self, q, k, margins: Optional[torch.Tensor] = None):
+    def search(self, q, k, margins: Optional[torch.Tensor] = None, slot: int = 0):
         """Merged exact top-k, identical on every rank: ``(scores [B,k], ids [B,k])``.  ``margins`` (float32 [B])
-        receives this rank's certificate margins."""
+        receives this rank's certificate margins (compare with ``self.last.eps``)."""
         self._margins = margins
         q = self.local._check_queries(q)
-        return self.plumbing.search(q, k)
+        return self.plumbing.search(q, k, slot=slot)
 
     def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5):
         """Host queries in, merged + auto-merged lists out (numpy), with the certificate enforced per rank."""
-        q = q_host.to(self.device, torch.float32, non_blocking=True)
+        local = self.local
+        q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
         b = int(q.shape[0])
         margins = torch.empty((b,), dtype=torch.float32, device=self.device)
         send, recv, keys, ids = self.plumbing.buffers(b, k)
         self._margins = margins
-        self._local_search(q, k, keys, ids)
-        bad = torch.nonzero(~(margins > self.local.eps)).flatten()
-        if bad.numel():  # rank-local repair; the collective below is reached by every rank either way
-            self.local.fallbacks += int(bad.numel())
-            ex = self.local.search_exact(q.index_select(0, bad), k)
-            keys.index_copy_(0, bad, ex.keys)
-            ids.index_copy_(0, bad, ex.ids)
-        if self.plumbing.world > 1:
-            dist.all_gather_into_tensor(recv.view(-1), send, group=self.plumbing.group)
-        else:
-            recv[0].copy_(send)
+        r = self._local_search(q, k, keys, ids)
+        bad = torch.nonzero(~(margins > r.eps)).flatten()
+        if bad.numel():  # rank-local repair (writes into the send record); the collective below is reached by every rank
+            local._repair(q, k, r, bad, hi_lo_first=r.eps > local.eps)
+        self.plumbing.exchange(send, recv)
         scores, mids = self._merge(recv, self.plumbing.world, b, k, k)
-        if self.local.tree is not None:
-            m = self.local.automerge(mids, scores, ratio_thresh)
-            return m.ids.cpu().numpy(), m.scores.cpu().numpy(), m.lens.cpu().numpy()
-        ids_h = mids.cpu()
-        return ids_h.numpy(), scores.double().cpu().numpy(), (ids_h >= 0).sum(dim=1).to(torch.int32).numpy()
+        merged = local.tree is not None
+        rec = local._record(b, k, merged)
+        d, h = rec["d"], rec["h"]
+        if merged:
+            from .index import MergeResult
+
+            local.automerge(mids, scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+        else:
+            d["ids"].copy_(mids)
+            d["scores"].copy_(scores)
+        rec["host"].copy_(rec["dev"], non_blocking=True)
+        rec["event"].record()
+        rec["event"].synchronize()
+        ids_h, scores_h = h["ids"].numpy().copy(), h["scores"].numpy().astype("float64")
+        lens = h["lens"].numpy().copy() if merged else (ids_h >= 0).sum(axis=1).astype("int32")
+        return ids_h, scores_h, lens

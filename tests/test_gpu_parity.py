@@ -63,7 +63,7 @@ def test_mini_scan_golden_cosine(golden_dir, vname, variant, k, kprime):
     assert (_np(r.ids) == g[f"cos_k{k}_ids"]).all()
     assert (_np(r.keys) == g[f"cos_k{k}_keys"]).all()
     assert (_np(r.scores) == g[f"cos_k{k}_scores"]).all()
-    assert (_np(r.margin) > idx.eps).all()
+    assert (_np(r.margin) > r.eps).all()
     m = idx.automerge(r.ids, r.scores)
     got = _merged_lists(m)
     mi, ms = g[f"cos_k{k}_merged_ids"], g[f"cos_k{k}_merged_scores"]
@@ -156,12 +156,12 @@ def test_c1_config_golden(golden_dir, c1, vname, variant):
     if hashlib.sha256(bits.tobytes()).hexdigest() != str(g["corpus_sha256"]):
         pytest.skip("torch CPU RNG stream differs from the one the fixture was generated with")
     idx = _index(bits, tree, variant=variant)
-    r = idx.search(torch.from_numpy(q).cuda(), 10)
+    r = idx.search(torch.from_numpy(q).cuda(), 10, hi_only=False)
     torch.cuda.synchronize()
     assert (_np(r.ids) == g["ids"]).all()
     assert (_np(r.scores) == g["scores"]).all()
     margin = _np(r.margin)
-    assert (margin > idx.eps).all(), margin.min()
+    assert (margin > r.eps).all(), margin.min()
     assert idx.fallbacks == 0
     got = _merged_lists(idx.automerge(r.ids, r.scores))
     for b, lst in enumerate(got):
@@ -178,7 +178,7 @@ def test_c1_oracle_live_and_error_bound(c1, vname, variant):
     ids_o, sc_o, keys_o = cport.scan_topk(bits, q, 10)
     idx = _index(bits, tree, variant=variant)
     qd = torch.from_numpy(q).cuda()
-    r = idx.search(qd, 10)
+    r = idx.search(qd, 10, hi_only=False)
     torch.cuda.synchronize()
     assert (_np(r.ids) == ids_o).all() and (_np(r.keys) == keys_o).all()
     for b in (0, 17, 63):  # batch-1 launches give the same answer as the batch
@@ -187,7 +187,7 @@ def test_c1_oracle_live_and_error_bound(c1, vname, variant):
         assert (_np(r1.ids)[0] == ids_o[b]).all() and (_np(r1.scores)[0] == sc_o[b]).all()
     # stage-1 approximate scores vs exact fp64 cosine of the same rows
     w = idx._buffers(64, 10)
-    idx.search(qd, 10)
+    idx.search(qd, 10, hi_only=False)
     torch.cuda.synchronize()
     cand, approx = _np(w["cand_ids"]), _np(w["cand_approx"])
     c64 = oracle.bf16_bits_to_f32(bits).astype(np.float64)
@@ -199,6 +199,37 @@ def test_c1_oracle_live_and_error_bound(c1, vname, variant):
         exact = rows @ qq / (np.linalg.norm(rows, axis=1) * np.linalg.norm(qq))
         worst = max(worst, float(np.abs(exact - approx[b][ok]).max()))
     assert worst < idx.eps / 4, worst
+
+
+def test_c1_batch64_hi_only_single_pass(c1):
+    """64 queries in ONE corpus pass (bf16 hi halves only, N = 64 MMA columns): same exact answer, wider certificate,
+    and the repair ladder (hi+lo re-scan, then exact scan) for queries the hi-only certificate cannot prove."""
+    tree, bits, inv, q = c1
+    ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
+    idx = _index(bits, tree, variant=_lib.SCAN_TCGEN05)
+    qd = torch.from_numpy(q).cuda()
+    r = idx.search(qd, 10)  # 64 > HI_ONLY_ABOVE -> hi only
+    torch.cuda.synchronize()
+    assert r.eps > idx.eps
+    proven = _np(r.margin) > r.eps
+    assert proven.mean() > 0.5, _np(r.margin)
+    assert (_np(r.ids)[proven] == ids_o[proven]).all() and (_np(r.scores)[proven] == sc_o[proven]).all()
+    r = idx.search_certified(qd, 10)
+    torch.cuda.synchronize()
+    assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
+    assert idx.retries == int((~proven).sum())
+    # 20 and 32 queries: hi+lo with N = 64 columns
+    for b in (20, 32):
+        r = idx.search(qd[:b], 10)
+        torch.cuda.synchronize()
+        assert r.eps == idx.eps and (_np(r.margin) > r.eps).all()
+        assert (_np(r.ids) == ids_o[:b]).all() and (_np(r.scores) == sc_o[:b]).all()
+    # explicit hi-only on small batches exercises the N = 16 / 32 hi-only kernels
+    for b in (5, 30):
+        r = idx.search(qd[:b], 10, hi_only=True)
+        torch.cuda.synchronize()
+        ok = _np(r.margin) > r.eps
+        assert (_np(r.ids)[ok] == ids_o[:b][ok]).all()
 
 
 def test_retriever_surface(c1):
@@ -342,7 +373,7 @@ def test_big_matches_gpu_exact_scan_and_cpu_spot_check(big, vname, variant):
     r = idx.search(q, 10)
     ex = idx.search_exact(q, 10)
     torch.cuda.synchronize()
-    assert (_np(r.margin) > idx.eps).all()
+    assert (_np(r.margin) > r.eps).all()
     assert torch.equal(r.ids, ex.ids) and torch.equal(r.scores, ex.scores)
     # CPU oracle on the rows around the hits (stream a slab back to the host): exact scores of the winners
     ids = _np(r.ids)

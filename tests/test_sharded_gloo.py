@@ -35,12 +35,12 @@ def _worker(rank, world, port, out_dir):
     lo, hi = shard_bounds(n, world, rank, align=128)
     assert shard_bounds(n, world, 0)[0] == 0 and shard_bounds(n, world, world - 1)[1] == n
 
-    def local_search(qt, k, keys_out, ids_out):
+    def local_search(qt, k, keys_out, ids_out, slot=0):
         ids, _sc, keys = oracle.exact_topk(bits[lo:hi], qt.numpy(), k, 0, id_base=lo)
         keys_out.copy_(torch.from_numpy(keys))
         ids_out.copy_(torch.from_numpy(ids))
 
-    def merge(recv, w, b, k, k_out):
+    def merge(recv, w, b, k, k_out, slot=0):
         rec, ids_off, _ = record_layout(b, k)
         assert recv.shape == (w, rec)
         keys = [recv[r, : b * k * 4].view(torch.float32).view(b, k).numpy() for r in range(w)]
