@@ -161,6 +161,41 @@ struct Params {
 
 constexpr int SCHED_SLOTS = 4;  // tile-id ring between the producer and the MMA / epilogue roles
 
+// Cut candidate lists back to their K' best (rank by counting, one warp per query, warps stride over the queries).
+// all = false: only lists that are full (count >= cap);  all = true: every list longer than K'.
+// Sets thresh[q] to the K'-th key kept.  Callers put a barrier of the epilogue threads on both sides.
+__device__ __forceinline__ void cut_lists(uint64_t* lists, int* cnt_s, float* thresh_s, int nq, int kp, int cap,
+                                          int warp, int lane, bool all) {
+    for (int j = warp; j < nq; j += EPI_THREADS / 32) {
+        const int raw = cnt_s[j];
+        const int n = min(raw, cap);
+        if (all ? n <= kp : raw < cap) continue;
+        uint64_t* L = lists + size_t(j) * cap;
+        uint64_t e[8];
+        int r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int x = lane + 32 * u;
+            e[u] = x < n ? L[x] : 0ull;
+            r[u] = 0;
+        }
+        for (int m = 0; m < n; ++m) {
+            const uint64_t x = L[m];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] += x > e[u] ? 1 : 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (lane + 32 * u < n && r[u] < kp) {
+                L[r[u]] = e[u];
+                if (r[u] == kp - 1) thresh_s[j] = entry_key(e[u]);
+            }
+        }
+        if (lane == 0) cnt_s[j] = kp;
+    }
+}
+
 // Dynamic shared memory (base rounded up to 1024 B):
 //   [ Q: n_chunks x N x 128 B ][ ring: stages x CH x 16 KB ][ lists: NQ x cap x 8 B ][ thresh NQ f32 ][ cnt NQ i32 ]
 //   [ barriers: full[stages], empty[stages], q_full, tmem_full[2], tmem_empty[2], sched_full[4], sched_empty[4] ]
@@ -338,12 +373,12 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < NQ; ++j) sc[j] = (HILO ? acc[j] + acc[NQ + j] : acc[j]) * inv;
 
-            // Push survivors into the per-query lists.  A list holds cap = K' + spare entries; a push that finds it
-            // full stays pending, the list is cut back to its K' best (raising the threshold) and the push is
-            // retried -- so every row ever dropped, here or by the cut, scored <= the final threshold.
+            // Push survivors into the per-query lists.  A list holds cap = K' + spare entries and is only cut back
+            // to its K' best (raising the threshold) when it is full; a push that finds it full stays pending and is
+            // retried after the cut.  Every row ever dropped -- by the filter or by a cut -- scored <= the final threshold.
             uint64_t pending = 0ull;
             for (bool first = true;; first = false) {
-                bool did = false;
+                bool full = false;
 #pragma unroll
                 for (int j = 0; j < NQ; ++j) {
                     if (j < nq && (first ? row_ok : bool((pending >> j) & 1ull))) {
@@ -352,44 +387,19 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
                             const int slot = atomicAdd(cnt_s + j, 1);
                             if (slot < cap) lists[size_t(j) * cap + slot] = pack_entry(sc[j], uint32_t(row));
                             else pending |= 1ull << j;
-                            did = true;
+                            full |= slot >= cap - 1;
                         }
                     }
                 }
-                if (!epi_bar_or(did)) break;  // nobody pushed or is pending: the tile is done (one barrier per tile)
-                // cut every list longer than K' back to its K' best: one warp per query, rank by counting
-                for (int j = warp; j < nq; j += EPI_THREADS / 32) {
-                    const int n = min(cnt_s[j], cap);
-                    if (n <= kp) continue;
-                    uint64_t* L = lists + size_t(j) * cap;
-                    uint64_t e[8];
-                    int r[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int x = lane + 32 * u;
-                        e[u] = x < n ? L[x] : 0ull;
-                        r[u] = 0;
-                    }
-                    for (int m = 0; m < n; ++m) {
-                        const uint64_t x = L[m];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) r[u] += x > e[u] ? 1 : 0;
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (lane + 32 * u < n && r[u] < kp) {
-                            L[r[u]] = e[u];
-                            if (r[u] == kp - 1) thresh_s[j] = entry_key(e[u]);
-                        }
-                    }
-                    if (lane == 0) cnt_s[j] = kp;
-                }
+                if (!epi_bar_or(full)) break;  // no list filled up: the tile is done (one barrier per tile)
+                cut_lists(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, false);
                 epi_bar_sync();
             }
         }
 
-        // ---- emit this CTA's shortlist
+        // ---- final cut of every list to its K' best, then emit this CTA's shortlist
+        epi_bar_sync();
+        cut_lists(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, true);
         epi_bar_sync();
         for (int j = 0; j < nq; ++j) {
             const int n = cnt_s[j];
@@ -452,29 +462,13 @@ static int make_map(CUtensorMap* m, const void* base, int64_t rows, int dim, int
     return TT_OK;
 }
 
+// Shared-memory budget: the resident query block, then the candidate lists, the rest is the TMA ring.
+// Lists hold K' + spare entries; spare = 128 never needs a retry (a tile pushes at most 128 rows per query);
+// with many queries per pass the spare shrinks so that the ring keeps enough bytes in flight.
 template <int N, int CH, bool HILO>
-static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
-                  const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
-                  float* out_thresh, int n_lists, int* sched, cudaStream_t st) {
+static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* smem_out) {
     constexpr int NQ = HILO ? N / 2 : N;
-    Params p;
-    p.sched = sched;
-    p.inv_norm = inv_norm;
-    p.n_rows = n_rows;
-    p.id_base = id_base;
-    p.n_tiles = int((n_rows + TILE_ROWS - 1) / TILE_ROWS);
-    p.n_chunks = dim / CHUNK_COLS;
-    p.n_q = n_q;
-    p.kprime = kprime;
-    p.has_lo = HILO;
-    p.out_ids = out_ids;
-    p.out_approx = out_approx;
-    p.out_thresh = out_thresh;
-
-    // Shared-memory budget: the resident query block, then the candidate lists, the rest is the TMA ring.
-    // Lists hold K' + spare entries; spare = 128 never needs a retry (a tile pushes at most 128 rows per query);
-    // with many queries per pass the spare shrinks so that the ring keeps enough bytes in flight.
-    const size_t q_bytes = size_t(p.n_chunks) * N * 128;
+    const size_t q_bytes = size_t(dim / CHUNK_COLS) * N * 128;
     const size_t base = 1024 /*align slack*/ + q_bytes + size_t(NQ) * 8 + 160;
     const size_t per_stage = size_t(CH) * CHUNK_BYTES + 16;
     int spare = 0, stages = 0;
@@ -489,20 +483,46 @@ static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, c
         return true;
     };
     // first choice: the largest spare that still leaves >= 96 KB of ring; else a small spare and whatever ring is left
-    if (!try_spare(128, 96 * 1024) && !try_spare(64, 96 * 1024) && !try_spare(32, 96 * 1024) && !try_spare(32, 0))
-        try_spare(16, 0);
-    if (!spare) {
-        set_error("scan_tc: dim=%d kprime=%d does not fit shared memory with N=%d", dim, kprime, N);
-        return TT_ERR_UNSUPPORTED;
-    }
+    if (!try_spare(128, 96 * 1024) && !try_spare(64, 96 * 1024) && !try_spare(32, 96 * 1024) && !try_spare(32, 0) &&
+        !try_spare(16, 0))
+        return false;
     if (stages > 24) stages = 24;
     if (const char* e = getenv("TT_SCAN_STAGES")) {  // tuning knob
         const int want = atoi(e);
         if (want >= 2 && want < stages) stages = want;
     }
+    *spare_out = spare;
+    *stages_out = stages;
+    *smem_out = base + size_t(NQ) * (kprime + spare) * 8 + size_t(stages) * per_stage;
+    return true;
+}
+
+template <int N, int CH, bool HILO>
+static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
+                  const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
+                  float* out_thresh, int n_lists, int* sched, cudaStream_t st) {
+    constexpr int NQ = HILO ? N / 2 : N;
+    int spare = 0, stages = 0;
+    size_t smem = 0;
+    if (!plan<N, CH, HILO>(dim, kprime, &spare, &stages, &smem)) {
+        set_error("scan_tc: dim=%d kprime=%d does not fit shared memory with N=%d", dim, kprime, N);
+        return TT_ERR_UNSUPPORTED;
+    }
+    Params p;
+    p.sched = sched;
+    p.inv_norm = inv_norm;
+    p.n_rows = n_rows;
+    p.id_base = id_base;
+    p.n_tiles = int((n_rows + TILE_ROWS - 1) / TILE_ROWS);
+    p.n_chunks = dim / CHUNK_COLS;
+    p.n_q = n_q;
+    p.kprime = kprime;
+    p.has_lo = HILO;
+    p.out_ids = out_ids;
+    p.out_approx = out_approx;
+    p.out_thresh = out_thresh;
     p.cap = kprime + spare;
     p.stages = stages;
-    const size_t smem = base + size_t(NQ) * p.cap * 8 + size_t(stages) * per_stage;
 
     CUtensorMap map_c, map_qhi, map_qlo;
     int rc = make_map(&map_c, corpus, n_rows, dim, stride, TILE_ROWS, CH);
@@ -542,14 +562,16 @@ int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, 
 #define TT_TC(NN, CC, HL)                                                                                              \
     return tc::launch<NN, CC, HL>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids, \
                                   out_approx, out_thresh, n_lists, sched, st)
-    if (q_lo) {  // two MMA columns per query: 8 / 16 / 32 queries per pass
+    int sp, sg;
+    size_t sm;
+    if (q_lo) {  // two MMA columns per query: 8 / 16 / 32 queries per pass (the widest pass that fits shared memory)
         if (n_q <= 8) TT_TC(16, 2, true);
-        if (n_q <= 16) TT_TC(32, 2, true);
+        if (n_q <= 16 || !tc::plan<64, 1, true>(dim, kprime, &sp, &sg, &sm)) TT_TC(32, 2, true);
         TT_TC(64, 1, true);
     }
     // hi only: 16 / 32 / 64 queries per pass, wider certificate
     if (n_q <= 16) TT_TC(16, 2, false);
-    if (n_q <= 32) TT_TC(32, 2, false);
+    if (n_q <= 32 || !tc::plan<64, 1, false>(dim, kprime, &sp, &sg, &sm)) TT_TC(32, 2, false);
     TT_TC(64, 1, false);
 #undef TT_TC
 }

@@ -429,3 +429,71 @@ def test_big_automerge_matches_oracle_on_gpu_topk(big):
         pairs = [(int(o), float(s)) for o, s in zip(ids[b], scores[b]) if o >= 0]
         exp = oracle.auto_merge(pairs, t.parent_of, t.child_count, t.prev_id, t.next_id)
         assert got[b] == exp
+
+
+# --------------------------------------------------------------------------- the caller: MultiIndexRetriever over real indexes
+def test_multi_index_retriever_thread_pool_over_b200_retrievers(c1):
+    """rag_engine.py:416-455: one QueryBundle (no embedding) fanned out over per-index retrievers on a thread pool;
+    each embeds the string itself, results are tagged, balanced and re-sorted.  Three indexes = three row ranges."""
+    from oracle.multi_index import MultiIndexRetriever
+    from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200VectorIndexRetriever, NodeTable
+    from tensor_truth_b200.schema import TextNode
+
+    tree, bits, inv, q = c1
+    cuts = [(0, 30_000), (30_000, 70_016), (70_016, 100_000)]
+
+    class Embedder:
+        def get_agg_embedding_from_queries(self, strs):
+            return q[int(strs[0].split("#")[1])].tolist()
+
+    retrievers, expected_ids = [], {}
+    for i, (a, b) in enumerate(cuts):
+        idx = _index(bits[a:b], None)  # plain vector retrievers (a sub-range has no consistent tree)
+        table = NodeTable(factory=lambda o, i=i: TextNode(id_=f"idx{i}-row{o}"))
+        retrievers.append(B200VectorIndexRetriever(idx, similarity_top_k=10, embed_model=Embedder(), node_table=table))
+    multi = MultiIndexRetriever(retrievers)
+    for qi in (0, 9, 33):
+        out = multi.retrieve(f"query #{qi}")
+        per_index = []
+        for i, (a, b) in enumerate(cuts):
+            ids_o, sc_o, _ = cport.scan_topk(bits[a:b], q[qi:qi + 1], 10)
+            per_index.append([(f"idx{i}-row{o}", float(s), i) for o, s in zip(ids_o[0], sc_o[0])])
+        limit = max(1, 30 // 3)
+        exp = sorted([x for lst in per_index for x in lst[:limit]], key=lambda x: -x[1])
+        assert sorted((n.node.id_, n.score) for n in out) == sorted((a, s) for a, s, _ in exp)
+        assert [n.score for n in out] == [s for _, s, _ in exp]
+        assert all(n.node.metadata["_source_index"] == int(n.node.id_[3]) for n in out)
+    # hammer one retriever from many threads: per-instance lock + workspaces keep it correct
+    from concurrent.futures import ThreadPoolExecutor
+
+    am_idx = _index(bits, tree)
+    am = B200AutoMergingRetriever(B200VectorIndexRetriever(am_idx, 10, Embedder(), NodeTable()), None)
+    want = {qi: [(f"node-{o}", s) for o, s in oracle.retrieve(bits, q[qi], 10, tree)] for qi in range(16)}
+    with ThreadPoolExecutor(max_workers=8) as pool:
+        got = list(pool.map(lambda qi: (qi, am.retrieve(f"query #{qi}")), list(range(16)) * 3))
+    for qi, out in got:
+        assert [(n.node.id_, n.score) for n in out] == want[qi]
+
+
+# --------------------------------------------------------------------------- BASELINE configs[3] / [4] shapes at test size
+def test_c4_shape_large_batch_top100():
+    """configs[3] (50M rows, 16k queries, top-100) at test size: 256 queries, k = 100, K' = 128 -- many passes of the
+    widest tile that fits, bitonic selection for k > 32."""
+    tree, bits, inv, q = make_small(60_000, 256, dim=1024, levels=3, seed=4)
+    ids_o, sc_o, _ = cport.scan_topk(bits, q, 100)
+    idx = _index(bits, tree, kprime=128)
+    r = idx.search_certified(torch.from_numpy(q).cuda(), 100)
+    torch.cuda.synchronize()
+    assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
+
+
+def test_c5_shape_four_levels_top200():
+    """configs[4] (20M leaves, 4-level tree, top-200 feeding the merge) at test size, against the oracle end to end."""
+    tree, bits, inv, q = make_small(150_000, 6, dim=1024, levels=4, seed=8)
+    idx = _index(bits, tree, kprime=128)
+    ids, scores, lens = idx.retrieve_host(torch.from_numpy(q), 200)
+    for b in range(q.shape[0]):
+        exp = oracle.retrieve(bits, q[b], 200, tree)
+        got = [(int(o), float(s)) for o, s in zip(ids[b, :lens[b]], scores[b, :lens[b]])]
+        assert got == exp
+        assert any(o >= tree.level_offsets[2] for o, _ in got)  # merges cascade at least two levels up

@@ -1,0 +1,125 @@
+"""Host-side logic on CPU: the caller restatement (MultiIndexRetriever plumbing, mirroring the reference's own
+tests/unit/test_rag_engine.py:17-245), the docstore -> flat-array importer core, carrier types."""
+
+from types import SimpleNamespace
+from unittest.mock import MagicMock
+
+import numpy as np
+import pytest
+
+from oracle.multi_index import MultiIndexRetriever
+from tensor_truth_b200.schema import NodeWithScore, QueryBundle, TextNode
+from tensor_truth_b200.tree import build_uniform_tree, tree_from_relations
+
+
+def _mock_retriever(nodes):
+    r = MagicMock()
+    r.retrieve.return_value = nodes
+    return r
+
+
+def test_multi_index_combines_and_skips_empty_and_failing():
+    n1, n2 = MagicMock(score=0.9), MagicMock(score=0.8)
+    m = MultiIndexRetriever([_mock_retriever([n1]), _mock_retriever([n2])])
+    out = m._retrieve(QueryBundle(query_str="q"))
+    assert len(out) == 2 and n1 in out and n2 in out
+    m = MultiIndexRetriever([_mock_retriever([n1]), _mock_retriever([])])
+    assert m._retrieve(QueryBundle(query_str="q")) == [n1]
+    bad = MagicMock()
+    bad.retrieve.side_effect = RuntimeError("libtt_b200 error -2: boom")
+    m = MultiIndexRetriever([_mock_retriever([n1]), bad])
+    assert m._retrieve(QueryBundle(query_str="q")) == [n1]
+
+
+def test_multi_index_order_without_balancing_and_cache():
+    nodes = [MagicMock() for _ in range(5)]
+    m = MultiIndexRetriever([_mock_retriever(nodes[:3]), _mock_retriever(nodes[3:])], balance_strategy="none")
+    out = m._retrieve(QueryBundle(query_str="q"))
+    assert sorted(map(id, out)) == sorted(map(id, nodes)) and len(out) == 5
+    r = _mock_retriever([MagicMock()])
+    m = MultiIndexRetriever([r], enable_cache=True)
+    m._retrieve(QueryBundle(query_str="q"))
+    m._retrieve(QueryBundle(query_str="q"))
+    assert r.retrieve.call_count == 1 and m._retrieve_cached.cache_info().currsize == 1
+    m.clear_cache()
+    assert m._retrieve_cached.cache_info().currsize == 0
+    m2 = MultiIndexRetriever([r], enable_cache=False)
+    m2.clear_cache()
+    m2.clear_cache()
+
+
+def test_multi_index_balancing_tags_and_truncates():
+    a = [NodeWithScore(TextNode(id_=f"a{i}"), s) for i, s in enumerate((0.9, 0.8, 0.7, 0.65))]
+    b = [NodeWithScore(TextNode(id_=f"b{i}"), s) for i, s in enumerate((0.6, 0.5))]
+    m = MultiIndexRetriever([_mock_retriever(a), _mock_retriever(b)])
+    out = m._retrieve(QueryBundle(query_str="q"))
+    # 6 nodes / 2 indexes -> 3 per index at most; index 1 only has 2
+    assert [n.node.id_ for n in out] == ["a0", "a1", "a2", "b0", "b1"]
+    assert [n.node.metadata["_source_index"] for n in out] == [0, 0, 0, 1, 1]
+    assert [n.score for n in out] == sorted((n.score for n in out), reverse=True)
+
+
+def test_multi_index_passes_a_bundle_without_embedding():
+    seen = []
+
+    class R:
+        def retrieve(self, qb):
+            seen.append((qb.query_str, qb.embedding))
+            return []
+
+    MultiIndexRetriever([R(), R()]).retrieve("what is a tensor")
+    assert seen == [("what is a tensor", None)] * 2
+
+
+# --------------------------------------------------------------------------- importer core
+def _as_docstore(tree):
+    """What docstore.json holds for a tree (ids are strings, relations by id), leaves in corpus-row order."""
+    nid = lambda o: f"n{o:06d}"  # noqa: E731
+    parent, prev, nxt, children = {}, {}, {}, {}
+    for o in range(tree.n_nodes):
+        parent[nid(o)] = nid(tree.parent_of[o]) if tree.parent_of[o] >= 0 else None
+        prev[nid(o)] = nid(tree.prev_id[o]) if tree.prev_id[o] >= 0 else None
+        nxt[nid(o)] = nid(tree.next_id[o]) if tree.next_id[o] >= 0 else None
+        children[nid(o)] = []
+    for o in range(tree.n_nodes):
+        if tree.parent_of[o] >= 0:
+            children[nid(tree.parent_of[o])].append(nid(o))
+    return [nid(o) for o in range(tree.n_nodes)], parent, children, prev, nxt, [nid(o) for o in range(tree.n_leaf)]
+
+
+@pytest.mark.parametrize("levels", [1, 3, 4])
+def test_tree_from_relations_round_trip(levels):
+    t = build_uniform_tree(500, levels=levels, seed=5)
+    ids, parent, children, prev, nxt, leaf_order = _as_docstore(t)
+    rng = np.random.default_rng(0)
+    shuffled = [ids[i] for i in rng.permutation(len(ids))]  # docstore order is arbitrary
+    t2 = tree_from_relations(shuffled, parent, children, prev, nxt, leaf_order)
+    t2.validate()
+    assert t2.n_leaf == 500 and t2.node_ids[:500] == leaf_order
+    pos = {nid: o for o, nid in enumerate(t2.node_ids)}
+    for o in range(t.n_nodes):
+        o2 = pos[f"n{o:06d}"]
+        assert t2.child_count[o2] == t.child_count[o]
+        for a, b in ((t.parent_of, t2.parent_of), (t.prev_id, t2.prev_id), (t.next_id, t2.next_id)):
+            assert (b[o2] == -1) == (a[o] == -1)
+            if a[o] >= 0:
+                assert t2.node_ids[b[o2]] == f"n{a[o]:06d}"
+    # leaves come first, then deeper internal levels before shallower ones
+    depth = lambda o: 0 if t2.parent_of[o] < 0 else 1 + depth(t2.parent_of[o])  # noqa: E731
+    d = [depth(o) for o in range(t2.n_leaf, t2.n_nodes)]
+    assert d == sorted(d, reverse=True)
+
+
+def test_carrier_types_expose_what_consumers_read():
+    n = TextNode(id_="abc", text="hello", metadata={"file_name": "x.md"}, parent_id="p", prev_id=None, next_id="nx", child_ids=[])
+    ns = NodeWithScore(node=n, score=0.5)
+    assert ns.node.id_ == ns.node.node_id == ns.node_id == "abc"
+    assert ns.get_score() == 0.5 and NodeWithScore(node=n).get_score() == 0.0
+    assert ns.get_content() == ns.text == "hello"
+    ns.node.metadata["_source_index"] = 3
+    assert ns.metadata["_source_index"] == 3
+    assert n.parent_node.node_id == "p" and n.prev_node is None and n.next_node.node_id == "nx" and n.child_nodes is None
+    with pytest.raises(ValueError):
+        NodeWithScore(node=n).get_score(raise_error=True)
+    qb = QueryBundle(query_str="q")
+    assert qb.embedding is None and qb.embedding_strs == ["q"]
