@@ -497,3 +497,31 @@ def test_c5_shape_four_levels_top200():
         got = [(int(o), float(s)) for o, s in zip(ids[b, :lens[b]], scores[b, :lens[b]])]
         assert got == exp
         assert any(o >= tree.level_offsets[2] for o, _ in got)  # merges cascade at least two levels up
+
+
+def test_importer_end_to_end_fp32_store():
+    """a (duck-typed) Chroma collection + docstore snapshot -> DeviceIndex -> retriever; the stored
+    embeddings are fp32, so the scan runs on the bf16 shadow and the exact answer comes from the fp32 master."""
+    from tensor_truth_b200.importer import load_device_index
+    from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200VectorIndexRetriever, NodeTable
+    from tensor_truth_b200.schema import QueryBundle
+    from test_host_logic import _fake_docstore
+
+    tree, bits, inv, q = make_small(20_000, 6, dim=256, levels=3, seed=21)
+    emb = oracle.bf16_bits_to_f32(bits) * (1.0 + 1e-3 * np.random.default_rng(0).standard_normal(bits.shape).astype(np.float32))
+    docs = _fake_docstore(tree)
+    order = np.random.default_rng(1).permutation(tree.n_leaf)
+
+    class Collection:
+        def get(self, include):
+            assert include == ["embeddings"]
+            return {"ids": [f"uuid-{o:05d}" for o in order], "embeddings": emb[order]}
+
+    idx, nodes = load_device_index(Collection(), type("DS", (), {"docs": docs})(), device=torch.device("cuda:0"))
+    am = B200AutoMergingRetriever(B200VectorIndexRetriever(idx, 10, None, NodeTable(nodes=nodes)), None)
+    for b in range(q.shape[0]):
+        out = am.retrieve(QueryBundle(query_str="x", embedding=q[b].tolist()))
+        # oracle on the same fp32 values in the ORIGINAL leaf order, ids compared through the node ids
+        exp = oracle.retrieve(emb, q[b], 10, tree)
+        assert [n.node.id_ for n in out] == [f"uuid-{o:05d}" for o, _ in exp]
+        assert [n.score for n in out] == [s for _, s in exp]

@@ -123,3 +123,49 @@ def test_carrier_types_expose_what_consumers_read():
         NodeWithScore(node=n).get_score(raise_error=True)
     qb = QueryBundle(query_str="q")
     assert qb.embedding is None and qb.embedding_strs == ["q"]
+
+
+# --------------------------------------------------------------------------- importer (duck-typed docstore / collection)
+def _fake_docstore(tree):
+    from tensor_truth_b200.schema import TextNode
+
+    nid = lambda o: f"uuid-{o:05d}"  # noqa: E731
+    docs = {}
+    kids = {o: [] for o in range(tree.n_nodes)}
+    for o in range(tree.n_nodes):
+        if tree.parent_of[o] >= 0:
+            kids[int(tree.parent_of[o])].append(o)
+    for o in range(tree.n_nodes):
+        docs[nid(o)] = TextNode(id_=nid(o), text=f"text {o}", metadata={},
+                                parent_id=nid(tree.parent_of[o]) if tree.parent_of[o] >= 0 else None,
+                                prev_id=nid(tree.prev_id[o]) if tree.prev_id[o] >= 0 else None,
+                                next_id=nid(tree.next_id[o]) if tree.next_id[o] >= 0 else None,
+                                child_ids=[nid(c) for c in kids[o]])
+    return docs
+
+
+def test_importer_flattens_docstore_and_collection():
+    from tensor_truth_b200.importer import flatten_index
+
+    t = build_uniform_tree(300, levels=3, seed=2)
+    docs = _fake_docstore(t)
+    rng = np.random.default_rng(1)
+    order = rng.permutation(300)  # the vector store returns leaves in its own order
+    leaf_ids = [f"uuid-{o:05d}" for o in order]
+    emb = rng.standard_normal((300, 16)).astype(np.float32)
+    corpus, tree, nodes = flatten_index(leaf_ids, emb.tolist(), docs)
+    assert corpus.dtype == np.float32 and (corpus == emb).all()
+    assert [n.id_ for n in nodes[:300]] == leaf_ids and len(nodes) == t.n_nodes
+    # relations survive the re-ordering: check through ids
+    for o2 in range(tree.n_nodes):
+        n = nodes[o2]
+        assert (tree.parent_of[o2] < 0) == (n.parent_id is None)
+        if n.parent_id is not None:
+            assert nodes[tree.parent_of[o2]].id_ == n.parent_id
+        if n.next_id is not None:
+            assert nodes[tree.next_id[o2]].id_ == n.next_id
+        assert tree.child_count[o2] == len(n.child_ids)
+    with pytest.raises(ValueError):
+        flatten_index(leaf_ids + ["ghost"], emb.tolist() + [[0.0] * 16], docs)
+    with pytest.raises(ValueError):
+        flatten_index(leaf_ids[:-1], emb[:-1].tolist(), docs)
