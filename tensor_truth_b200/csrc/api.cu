@@ -1,6 +1,7 @@
 // C ABI of libtt_b200.so (include/tt_b200.h): argument checking, variant dispatch, error plumbing.
 // No kernels here; no CPU implementation of anything behind these entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tt_common.cuh"
@@ -18,6 +19,10 @@ bool scan_tc_supported(int64_t n_rows, int dim, int64_t stride, int kprime, cons
 int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
                    const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
                    float* out_approx, float* out_thresh, int n_lists, int* sched, cudaStream_t st);
+bool scan_tc2_supported(int dim, int kprime, int n_lists);
+int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
+                    const void* q_hi, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
+                    float* out_thresh, int n_lists, cudaStream_t st);
 int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
                    const float* q, int n_q, const int64_t* cand_ids, int n_cand, int mode, uint64_t* packed,
                    cudaStream_t st);
@@ -121,6 +126,10 @@ int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t 
             set_error("tt_scan_topk_bf16: the tcgen05 variant needs dim %% 128 == 0, 128 <= dim <= 2048, n_rows > 0");
             return TT_ERR_UNSUPPORTED;
         }
+        // wide hi-only batches: CTA pairs (cta_group::2) hold half of the query block each -> 64 queries per pass
+        if (!q_lo_bf16 && n_q > 32 && scan_tc2_supported(dim, kprime, n_lists) && !getenv("TT_SCAN_NO_PAIR"))
+            return scan_tc2_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, n_q, kprime, id_base,
+                                   out_ids, out_approx, out_thresh, n_lists, TT_STREAM(stream));
         return scan_tc_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, q_lo_bf16, n_q, kprime,
                               id_base, out_ids, out_approx, out_thresh, n_lists, reinterpret_cast<int*>(ws),
                               TT_STREAM(stream));

@@ -290,8 +290,10 @@ static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* s
         stages = st_n;
         return true;
     };
-    // first choice: the largest spare that still leaves >= 96 KB of ring; else a small spare and whatever ring is left
-    if (!try_spare(128, 96 * 1024) && !try_spare(64, 96 * 1024) && !try_spare(32, 96 * 1024) && !try_spare(32, 0) &&
+    // bytes in flight are what buys HBM bandwidth: the largest spare that still leaves >= 128 KB of ring, then
+    // >= 96 KB, else a small spare and whatever ring is left
+    if (!try_spare(128, 128 * 1024) && !try_spare(64, 128 * 1024) && !try_spare(32, 128 * 1024) &&
+        !try_spare(128, 96 * 1024) && !try_spare(64, 96 * 1024) && !try_spare(32, 96 * 1024) && !try_spare(32, 0) &&
         !try_spare(16, 0))
         return false;
     if (stages > 24) stages = 24;
