@@ -96,7 +96,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < NQ) {
-        thresh_s[threadIdx.x] = -INFINITY;
+        thresh_s[threadIdx.x] = int(threadIdx.x) < p.nq_here ? -INFINITY : INFINITY;  // unused columns never pass
         cnt_s[threadIdx.x] = 0;
     }
     if (warp == 5) {
@@ -215,33 +215,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
             tcgen05_fence_before();
             mbar_arrive(smem_u32(tmem_empty + a));  // accumulator is in registers: hand TMEM back
 
-            // approximate scores of this row, one per query
-            float sc[NQ];
-#pragma unroll
-            for (int j = 0; j < NQ; ++j) sc[j] = (HILO ? acc[j] + acc[NQ + j] : acc[j]) * inv;
-
-            // Push survivors into the per-query lists.  A list holds cap = K' + spare entries and is only cut back
-            // to its K' best (raising the threshold) when it is full; a push that finds it full stays pending and is
-            // retried after the cut.  Every row ever dropped -- by the filter or by a cut -- scored <= the final threshold.
-            uint64_t pending = 0ull;
-            for (bool first = true;; first = false) {
-                bool full = false;
-#pragma unroll
-                for (int j = 0; j < NQ; ++j) {
-                    if (j < nq && (first ? row_ok : bool((pending >> j) & 1ull))) {
-                        pending &= ~(1ull << j);
-                        if (sc[j] > thresh_s[j]) {
-                            const int slot = atomicAdd(cnt_s + j, 1);
-                            if (slot < cap) lists[size_t(j) * cap + slot] = pack_entry(sc[j], uint32_t(row));
-                            else pending |= 1ull << j;
-                            full |= slot >= cap - 1;
-                        }
-                    }
-                }
-                if (!epi_bar_or(full)) break;  // no list filled up: the tile is done (one barrier per tile)
-                cut_lists(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, false);
-                epi_bar_sync();
-            }
+            filter_and_push<NQ, HILO, N>(acc, inv, row_ok, uint32_t(row), nq, lists, cnt_s, thresh_s, kp, cap, warp, lane);
         }
 
         // ---- final cut of every list to its K' best, then emit this CTA's shortlist

@@ -129,7 +129,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < NQ) {
-        thresh_s[threadIdx.x] = -INFINITY;
+        thresh_s[threadIdx.x] = int(threadIdx.x) < p.nq_here ? -INFINITY : INFINITY;  // unused columns never pass
         cnt_s[threadIdx.x] = 0;
     }
     if (warp == 5) {
@@ -221,28 +221,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(a ? te1 : te0);  // accumulator is in registers: hand TMEM back (leader's barrier)
-#pragma unroll
-            for (int j = 0; j < NQ; ++j) sc[j] *= inv;
-
-            uint64_t pending = 0ull;
-            for (bool first = true;; first = false) {
-                bool full = false;
-#pragma unroll
-                for (int j = 0; j < NQ; ++j) {
-                    if (j < nq && (first ? row_ok : bool((pending >> j) & 1ull))) {
-                        pending &= ~(1ull << j);
-                        if (sc[j] > thresh_s[j]) {
-                            const int slot = atomicAdd(cnt_s + j, 1);
-                            if (slot < cap) lists[size_t(j) * cap + slot] = pack_entry(sc[j], uint32_t(row));
-                            else pending |= 1ull << j;
-                            full |= slot >= cap - 1;
-                        }
-                    }
-                }
-                if (!epi_bar_or(full)) break;
-                cut_lists(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, false);
-                epi_bar_sync();
-            }
+            filter_and_push<NQ, false, NQ>(sc, inv, row_ok, uint32_t(row), nq, lists, cnt_s, thresh_s, kp, cap, warp, lane);
         }
 
         // ---- final cut of every list to its K' best, then emit this CTA's shortlist

@@ -161,6 +161,81 @@ __device__ __forceinline__ void cut_lists(uint64_t* lists, int* cnt_s, float* th
 }
 
 
+// Epilogue core shared by both stage-1 tensor-core kernels: filter one corpus row's NQ approximate scores against
+// the per-query thresholds and push the survivors into the shared-memory candidate lists.
+//
+// The common case (nothing passes) costs ~3 instructions per query: thresholds come in as float4, the comparison
+// results are collected in compile-time-indexed bit masks, and only rows with a set bit enter the push path.
+// A list holds cap = K' + spare entries and is only cut back to its K' best (raising the threshold) when it is
+// full; a push that finds it full stays pending and is retried after the cut.  Every row ever dropped -- by the
+// filter or by a cut -- scored <= the final threshold.  thresh_s[j] must be +inf for unused queries j >= nq.
+// Executed by all EPI_THREADS threads (contains barriers of the epilogue group).
+// The rare path, kept out of line so that the compiler does not speculate its arithmetic into the filter loop.
+// Returns true when the list was full (the candidate stays pending).
+static __device__ __noinline__ bool push_candidate(uint64_t* list, int* cnt, float s, uint32_t row, int cap, int* full) {
+    const int slot = atomicAdd(cnt, 1);
+    if (slot >= cap - 1) *full = 1;
+    if (slot < cap) {
+        list[slot] = pack_entry(s, row);
+        return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+template <int NQ, bool HILO, int NACC>
+__device__ __forceinline__ void filter_and_push(const float (&acc)[NACC], float inv, bool row_ok, uint32_t row, int nq,
+                                                uint64_t* lists, int* cnt_s, float* thresh_s, int kp, int cap, int warp,
+                                                int lane) {
+    static_assert(NQ % 4 == 0 && NQ <= 64, "NQ");
+    constexpr int NW = (NQ + 31) / 32;
+    uint32_t hit[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) hit[w] = 0u;
+    const uint32_t th_addr = smem_u32(thresh_s);
+#pragma unroll
+    for (int j4 = 0; j4 < NQ / 4; ++j4) {
+        const float4 th = lds_f4(th_addr + j4 * 16);
+        const float tv[4] = {th.x, th.y, th.z, th.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j4 * 4 + u;
+            const float s = (HILO ? acc[j] + acc[NQ + j] : acc[j]) * inv;
+            if (s > tv[u]) hit[j >> 5] |= 1u << (j & 31);
+        }
+    }
+    if (!row_ok) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) hit[w] = 0u;
+    }
+    for (;;) {
+        int full = 0;
+        bool any = false;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) any |= hit[w] != 0u;
+        if (any) {
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+                if (hit[j >> 5] & (1u << (j & 31))) {
+                    const float s = (HILO ? acc[j] + acc[NQ + j] : acc[j]) * inv;
+                    bool keep = false;
+                    if (s > thresh_s[j])  // re-check: the threshold may have risen since the bit was set
+                        keep = push_candidate(lists + size_t(j) * cap, cnt_s + j, s, row, cap, &full);
+                    if (!keep) hit[j >> 5] &= ~(1u << (j & 31));
+                }
+            }
+        }
+        if (!epi_bar_or(full != 0)) break;  // no list filled up: the tile is done (one barrier per tile)
+        cut_lists(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, false);
+        epi_bar_sync();
+    }
+}
+
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
