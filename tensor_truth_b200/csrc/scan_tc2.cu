@@ -38,8 +38,11 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// Remote arrive with the default (.release.cta) semantics: a cluster-scope release would put a GPU-wide MEMBAR on
+// the producer's / epilogue's critical path.  No generic-proxy data is published through these barriers (TMA bytes
+// are tracked by complete_tx, TMEM reads are ordered by tcgen05.wait::ld + tcgen05.fence).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion is signalled on a barrier that may live in the peer CTA (cta_group::2)
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
