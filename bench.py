@@ -312,10 +312,11 @@ def run_b200(args):
     # ---- end to end through the public retriever API: host query in, NodeWithScore list out
     e2e_steps = max(5, min(args.steps, 100))
     q_host = queries.cpu()
+    q_lists = [row.tolist() for row in q_host]  # host input as an embed model hands it over: a Python list of floats
     if sharded is None:
         base_r = B200VectorIndexRetriever(idx, similarity_top_k=TOP_K)
         am = B200AutoMergingRetriever(base_r, None)
-        call = lambda i: am.retrieve(QueryBundle(query_str=f"q{i}", embedding=q_host[i % QUERY_POOL].tolist()))  # noqa: E731
+        call = lambda i: am.retrieve(QueryBundle(query_str=f"q{i}", embedding=q_lists[i % QUERY_POOL]))  # noqa: E731
     else:
         pinned = q_host.pin_memory()
         call = lambda i: sharded.retrieve_host(pinned[i % QUERY_POOL:i % QUERY_POOL + 1], TOP_K)  # noqa: E731

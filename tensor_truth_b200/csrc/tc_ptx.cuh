@@ -125,7 +125,34 @@ __device__ __forceinline__ bool epi_bar_or(bool pred) {
     return r != 0;
 }
 
-// Cut candidate lists back to their K' best (rank by counting, one warp per query, warps stride over the queries).
+// Cut one candidate list of n entries back to its kp best: rank by counting, each lane owns entries lane + 32u
+// (u < NE), the list is read once per rank step as a shared-memory broadcast.  Whole warp.
+template <int NE>
+__device__ __forceinline__ void cut_one(uint64_t* L, int n, int kp, float* thresh, int lane) {
+    uint64_t e[NE];
+    int r[NE];
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        const int x = lane + 32 * u;
+        e[u] = x < n ? L[x] : 0ull;
+        r[u] = 0;
+    }
+    for (int m = 0; m < n; ++m) {
+        const uint64_t x = L[m];
+#pragma unroll
+        for (int u = 0; u < NE; ++u) r[u] += x > e[u] ? 1 : 0;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < NE; ++u) {
+        if (lane + 32 * u < n && r[u] < kp) {
+            L[r[u]] = e[u];
+            if (r[u] == kp - 1) *thresh = entry_key(e[u]);
+        }
+    }
+}
+
+// Cut candidate lists back to their K' best, one warp per query, warps stride over the queries.
 // all = false: only lists that are full (count >= cap);  all = true: every list longer than K'.
 // Sets thresh[q] to the K'-th key kept.  Callers put a barrier of the epilogue threads on both sides.
 __device__ __forceinline__ void cut_lists(uint64_t* lists, int* cnt_s, float* thresh_s, int nq, int kp, int cap,
@@ -135,41 +162,13 @@ __device__ __forceinline__ void cut_lists(uint64_t* lists, int* cnt_s, float* th
         const int n = min(raw, cap);
         if (all ? n <= kp : raw < cap) continue;
         uint64_t* L = lists + size_t(j) * cap;
-        uint64_t e[8];
-        int r[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int x = lane + 32 * u;
-            e[u] = x < n ? L[x] : 0ull;
-            r[u] = 0;
-        }
-        for (int m = 0; m < n; ++m) {
-            const uint64_t x = L[m];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) r[u] += x > e[u] ? 1 : 0;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            if (lane + 32 * u < n && r[u] < kp) {
-                L[r[u]] = e[u];
-                if (r[u] == kp - 1) thresh_s[j] = entry_key(e[u]);
-            }
-        }
+        if (n <= 64) cut_one<2>(L, n, kp, thresh_s + j, lane);
+        else if (n <= 128) cut_one<4>(L, n, kp, thresh_s + j, lane);
+        else cut_one<8>(L, n, kp, thresh_s + j, lane);
         if (lane == 0) cnt_s[j] = kp;
     }
 }
 
-
-// Epilogue core shared by both stage-1 tensor-core kernels: filter one corpus row's NQ approximate scores against
-// the per-query thresholds and push the survivors into the shared-memory candidate lists.
-//
-// The common case (nothing passes) costs ~3 instructions per query: thresholds come in as float4, the comparison
-// results are collected in compile-time-indexed bit masks, and only rows with a set bit enter the push path.
-// A list holds cap = K' + spare entries and is only cut back to its K' best (raising the threshold) when it is
-// full; a push that finds it full stays pending and is retried after the cut.  Every row ever dropped -- by the
-// filter or by a cut -- scored <= the final threshold.  thresh_s[j] must be +inf for unused queries j >= nq.
-// Executed by all EPI_THREADS threads (contains barriers of the epilogue group).
 // The rare path, kept out of line so that the compiler does not speculate its arithmetic into the filter loop.
 // Returns true when the list was full (the candidate stays pending).
 static __device__ __noinline__ bool push_candidate(uint64_t* list, int* cnt, float s, uint32_t row, int cap, int* full) {

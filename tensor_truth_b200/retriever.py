@@ -18,6 +18,7 @@ fallback.
 
 from __future__ import annotations
 
+from array import array
 from typing import Any, Callable, List, Optional, Sequence, Union
 
 import numpy as np
@@ -39,14 +40,21 @@ class NodeTable:
         self._nodes = nodes
         self._ids = node_ids
         self._factory = factory
+        self._made: dict = {}  # like the docstore, hand out the SAME node object for an ordinal every time
 
     def __call__(self, ordinal: int):
         if self._nodes is not None:
             return self._nodes[ordinal]
-        if self._factory is not None:
-            return self._factory(ordinal)
-        nid = self._ids[ordinal] if self._ids is not None else f"node-{ordinal}"
-        return TextNode(id_=nid, text="", metadata={})
+        node = self._made.get(ordinal)
+        if node is None:
+            if self._factory is not None:
+                node = self._factory(ordinal)
+            else:
+                nid = self._ids[ordinal] if self._ids is not None else f"node-{ordinal}"
+                node = TextNode(id_=nid, text="", metadata={})
+            if len(self._made) < 1_000_000:
+                self._made[ordinal] = node
+        return node
 
 
 def _embed(embed_model, query_bundle: QueryBundle) -> List[float]:
@@ -86,8 +94,9 @@ class B200VectorIndexRetriever(_RetrieverBase):
                 query_bundle.embedding = emb  # upstream caches it on the bundle too
             except Exception:
                 pass
-        q = torch.as_tensor(np.asarray(emb, dtype=np.float32)).reshape(1, -1)
-        return q
+        if isinstance(emb, (list, tuple)):  # what an embed model hands over; array('f') is the fastest list -> fp32 path
+            return torch.frombuffer(array("f", emb), dtype=torch.float32).reshape(1, -1)
+        return torch.as_tensor(np.asarray(emb, dtype=np.float32)).reshape(1, -1)
 
     def _retrieve(self, query_bundle: QueryBundle) -> List[NodeWithScore]:
         ids, scores, lens = self.index.retrieve_host(self._query_tensor(query_bundle), self.similarity_top_k, merge=False)
