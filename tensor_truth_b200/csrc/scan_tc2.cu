@@ -90,8 +90,13 @@ struct Params {
 // Dynamic shared memory of each CTA (base rounded up to 1024 B):
 //   [ Q half: n_chunks x N/2 x 128 B ][ ring: stages x 16 KB ][ lists: N x cap x 8 B ][ thresh N f32 ][ cnt N i32 ]
 //   [ barriers: full[stages] (used in CTA 0), empty[stages], q_full (CTA 0), tmem_full[2], tmem_empty[2] (CTA 0) ][ tmem base ]
+// Ten warps: 0-7 epilogue (warps w and w+4 share the TMEM lane quarter w%4 and split the N query columns in
+// halves -- two warps per scheduler hide each other's latencies), 8 TMA producer, 9 TMEM alloc + MMA issue.
+constexpr int EPI2 = 256;
+constexpr int THREADS2 = EPI2 + 64;
+
 template <int N>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_q, const Params p) {
     constexpr int NQ = N;      // hi only: one MMA column per query
     constexpr int NH = N / 2;  // query rows held by each CTA
@@ -127,7 +132,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
         mbar_init(smem_u32(q_full), 2);
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(tmem_full + a), 1);
-            mbar_init(smem_u32(tmem_empty + a), 2 * (EPI_THREADS / 32));  // one lane per epilogue warp of both CTAs
+            mbar_init(smem_u32(tmem_empty + a), 2 * (EPI2 / 32));  // one lane per epilogue warp of both CTAs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -135,7 +140,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
         thresh_s[threadIdx.x] = int(threadIdx.x) < p.nq_here ? -INFINITY : INFINITY;  // unused columns never pass
         cnt_s[threadIdx.x] = 0;
     }
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
                      "r"(uint32_t(TMEM_COLS))
                      : "memory");
@@ -147,7 +152,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================================================== TMA producer (both CTAs, own rows + own query half)
         if (lane == 0 && n_my > 0) {
             const uint32_t qf = mapa(smem_u32(q_full), 0);
@@ -172,7 +177,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================================================== MMA issuer: one thread of the leader CTA
         if (lane == 0 && rank == 0 && n_my > 0) {
             constexpr uint32_t idesc = umma_idesc_bf16_m256(N);
@@ -201,7 +206,9 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
         }
         __syncwarp();
     } else {
-        // ===================================================== epilogue: 128 threads per CTA, thread = corpus row
+        // ===================================================== epilogue: 8 warps per CTA; thread = (corpus row, half of the queries)
+        const int quarter = warp & 3, half = warp >> 2;
+        constexpr int NW = N / 2;  // query columns per warp
         const int t = threadIdx.x;
         const int nq = p.nq_here;
         const int kp = p.kprime, cap = p.cap;
@@ -209,32 +216,33 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
         for (int i = 0; i < n_my; ++i) {
             const int a = i & 1;
             const int super = cluster_id + i * n_clusters;
-            const int64_t row = int64_t(super) * 256 + int64_t(rank) * TILE_ROWS + t;
+            const int64_t row = int64_t(super) * 256 + int64_t(rank) * TILE_ROWS + quarter * 32 + lane;
             const bool row_ok = row < p.n_rows;
             float inv = 1.f;
             if (p.inv_norm && row_ok) inv = __ldg(p.inv_norm + row);
 
             mbar_wait(smem_u32(tmem_full + a), uint32_t(i >> 1) & 1u);
             tcgen05_fence_after();
-            float sc[NQ];
-            const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(a * N);
+            float sc[NW];
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(a * N + half * NW);
 #pragma unroll
-            for (int c = 0; c < N; c += 16) tmem_ld_x16(taddr + c, sc + c);
+            for (int c = 0; c < NW; c += 16) tmem_ld_x16(taddr + c, sc + c);
             tmem_ld_wait();
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(a ? te1 : te0);  // accumulator is in registers: hand TMEM back (leader's barrier)
-            filter_and_push<NQ, false, NQ>(sc, inv, row_ok, uint32_t(row), nq, lists, cnt_s, thresh_s, kp, cap, warp, lane);
+            filter_and_push<NW, false, NW, EPI2>(sc, inv, row_ok, uint32_t(row), nq, lists, cnt_s, thresh_s, kp, cap, warp, lane,
+                                                 half * NW);
         }
 
         // ---- final cut of every list to its K' best, then emit this CTA's shortlist
-        epi_bar_sync();
-        cut_lists(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, true);
-        epi_bar_sync();
+        epi_bar_sync<EPI2>();
+        cut_lists<EPI2>(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, true);
+        epi_bar_sync<EPI2>();
         for (int j = 0; j < nq; ++j) {
             const int n = cnt_s[j];
             const size_t o = (size_t(p.q0 + j) * gridDim.x + blockIdx.x) * kp;
-            for (int s = t; s < kp; s += EPI_THREADS) {
+            for (int s = t; s < kp; s += EPI2) {
                 const uint64_t e = s < n ? lists[size_t(j) * cap + s] : 0ull;
                 p.out_ids[o + s] = e ? int64_t(p.id_base + entry_id(e)) : int64_t(-1);
                 p.out_approx[o + s] = e ? entry_key(e) : -INFINITY;
@@ -246,7 +254,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
     tcgen05_fence_before();
     __syncthreads();
     cluster_sync_all();  // nobody frees TMEM or exits while the peer may still signal / read
-    if (warp == 5) {
+    if (warp == 9) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS))
                      : "memory");
@@ -326,7 +334,7 @@ int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride,
     for (int q0 = 0; q0 < n_q; q0 += N) {
         p.q0 = q0;
         p.nq_here = (n_q - q0 < N) ? n_q - q0 : N;
-        kern<<<n_lists, tc::THREADS, smem, st>>>(map_c, map_q, p);
+        kern<<<n_lists, tc2::THREADS2, smem, st>>>(map_c, map_q, p);
         TT_LAUNCH_OK("scan_tc2_kernel");
     }
     return TT_OK;

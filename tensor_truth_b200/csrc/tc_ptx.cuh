@@ -110,8 +110,11 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+// named barrier 1 over the EPI epilogue threads of the CTA
+template <int EPI = EPI_THREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI) : "memory"); }
 // barrier + OR-reduction of a predicate over the 128 epilogue threads
+template <int EPI = EPI_THREADS>
 __device__ __forceinline__ bool epi_bar_or(bool pred) {
     uint32_t r;
     asm volatile(
@@ -120,7 +123,7 @@ __device__ __forceinline__ bool epi_bar_or(bool pred) {
         "bar.red.or.pred q, 1, %2, p;\n\t"
         "selp.u32 %0, 1, 0, q;\n\t}"
         : "=r"(r)
-        : "r"(uint32_t(pred)), "n"(EPI_THREADS)
+        : "r"(uint32_t(pred)), "n"(EPI)
         : "memory");
     return r != 0;
 }
@@ -155,9 +158,10 @@ __device__ __forceinline__ void cut_one(uint64_t* L, int n, int kp, float* thres
 // Cut candidate lists back to their K' best, one warp per query, warps stride over the queries.
 // all = false: only lists that are full (count >= cap);  all = true: every list longer than K'.
 // Sets thresh[q] to the K'-th key kept.  Callers put a barrier of the epilogue threads on both sides.
+template <int EPI = EPI_THREADS>
 __device__ __forceinline__ void cut_lists(uint64_t* lists, int* cnt_s, float* thresh_s, int nq, int kp, int cap,
                                           int warp, int lane, bool all) {
-    for (int j = warp; j < nq; j += EPI_THREADS / 32) {
+    for (int j = warp; j < nq; j += EPI / 32) {
         const int raw = cnt_s[j];
         const int n = min(raw, cap);
         if (all ? n <= kp : raw < cap) continue;
@@ -187,16 +191,16 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     return v;
 }
 
-template <int NQ, bool HILO, int NACC>
+template <int NQ, bool HILO, int NACC, int EPI = EPI_THREADS>
 __device__ __forceinline__ void filter_and_push(const float (&acc)[NACC], float inv, bool row_ok, uint32_t row, int nq,
-                                                uint64_t* lists, int* cnt_s, float* thresh_s, int kp, int cap, int warp,
-                                                int lane) {
+                                                uint64_t* lists, int* cnt_s, float* thresh_s, int kp, int cap,
+                                                int epi_warp, int lane, int q_off = 0) {
     static_assert(NQ % 4 == 0 && NQ <= 64, "NQ");
     constexpr int NW = (NQ + 31) / 32;
     uint32_t hit[NW];
 #pragma unroll
     for (int w = 0; w < NW; ++w) hit[w] = 0u;
-    const uint32_t th_addr = smem_u32(thresh_s);
+    const uint32_t th_addr = smem_u32(thresh_s + q_off);
 #pragma unroll
     for (int j4 = 0; j4 < NQ / 4; ++j4) {
         const float4 th = lds_f4(th_addr + j4 * 16);
@@ -223,15 +227,15 @@ __device__ __forceinline__ void filter_and_push(const float (&acc)[NACC], float 
                 if (hit[j >> 5] & (1u << (j & 31))) {
                     const float s = (HILO ? acc[j] + acc[NQ + j] : acc[j]) * inv;
                     bool keep = false;
-                    if (s > thresh_s[j])  // re-check: the threshold may have risen since the bit was set
-                        keep = push_candidate(lists + size_t(j) * cap, cnt_s + j, s, row, cap, &full);
+                    if (s > thresh_s[q_off + j])  // re-check: the threshold may have risen since the bit was set
+                        keep = push_candidate(lists + size_t(q_off + j) * cap, cnt_s + q_off + j, s, row, cap, &full);
                     if (!keep) hit[j >> 5] &= ~(1u << (j & 31));
                 }
             }
         }
-        if (!epi_bar_or(full != 0)) break;  // no list filled up: the tile is done (one barrier per tile)
-        cut_lists(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, false);
-        epi_bar_sync();
+        if (!epi_bar_or<EPI>(full != 0)) break;  // no list filled up: the tile is done (one barrier per tile)
+        cut_lists<EPI>(lists, cnt_s, thresh_s, nq, kp, cap, epi_warp, lane, false);
+        epi_bar_sync<EPI>();
     }
 }
 
