@@ -525,3 +525,41 @@ def test_importer_end_to_end_fp32_store():
         exp = oracle.retrieve(emb, q[b], 10, tree)
         assert [n.node.id_ for n in out] == [f"uuid-{o:05d}" for o, _ in exp]
         assert [n.score for n in out] == [s for _, s in exp]
+
+
+def test_near_duplicate_corpus_walks_the_repair_ladder():
+    """Rows that differ by ~1e-3 relative: approximate scores cannot separate them, every certificate must refuse and
+    the exact fp64 scan must answer -- ids still bit-exact, including the verbatim duplicates (ties -> smaller id)."""
+    rng = np.random.default_rng(17)
+    base = rng.standard_normal(1024).astype(np.float32)
+    c = base[None, :] * (1.0 + 2e-3 * rng.standard_normal((40_000, 1024)).astype(np.float32))
+    c[5000] = c[123]
+    c[39_999] = c[123]
+    bits = oracle.f32_to_bf16_bits(c)
+    q = (base[None, :] * (1.0 + 1e-3 * rng.standard_normal((40, 1024)))).astype(np.float32)
+    q[7] = oracle.bf16_bits_to_f32(bits[123])
+    ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
+    idx = _index(bits, None)
+    for b in (40, 3):  # hi-only batch (-> hi+lo retry -> exact) and a small hi+lo batch (-> exact)
+        idx.retries = idx.fallbacks = 0
+        r = idx.search_certified(torch.from_numpy(q[:b]).cuda(), 10)
+        torch.cuda.synchronize()
+        assert (_np(r.ids) == ids_o[:b]).all() and (_np(r.scores) == sc_o[:b]).all()
+        assert idx.fallbacks > 0
+        if b > 32:
+            assert idx.retries >= idx.fallbacks
+    assert _np(r.ids).shape == (3, 10)
+    r = idx.search_certified(torch.from_numpy(q[7:8]).cuda(), 3)
+    torch.cuda.synchronize()
+    assert _np(r.ids)[0].tolist() == [123, 5000, 39_999]
+
+
+def test_empty_index_and_empty_batch():
+    bits = np.zeros((0, 128), np.uint16)
+    idx = _index(bits, None)
+    q = torch.ones((2, 128), device="cuda")
+    r = idx.search_certified(q, 4)
+    torch.cuda.synchronize()
+    assert (_np(r.ids) == -1).all() and np.isneginf(_np(r.scores)).all()
+    ids, scores, lens = idx.retrieve_host(torch.ones((1, 128)), 4, merge=False)
+    assert lens.tolist() == [0]
