@@ -86,25 +86,31 @@ def test_mini_exact_scan_golden(golden_dir, tag, mode, k):
         assert (_np(r.scores) == g[f"{tag}_k{k}_scores"]).all()
 
 
-def test_l2_mode_falls_back_to_exact(golden_dir):
-    """The shortlist is ordered by cosine; in chroma_l2_exp mode the certificate refuses and the exact scan answers."""
+def test_l2_mode_is_answered_by_the_exact_scan(golden_dir):
+    """chroma_l2_exp mode (what ChromaVectorStore would report): the cosine-ordered shortlist proves nothing about
+    squared-L2 order on rows of unequal norm, so this mode goes straight to the exact fp64 scan."""
     g = np.load(os.path.join(golden_dir, "mini_scan.npz"))
-    idx = _index(g["bits"], None, score_mode=1, variant=_lib.SCAN_SIMT)
+    idx = _index(g["bits"], _Tree(g).t, score_mode=1)
     r = idx.search_certified(torch.from_numpy(g["queries"]).cuda(), 10)
     torch.cuda.synchronize()
-    assert idx.fallbacks == 0  # 1536 rows < n_lists * kprime: nothing was left out of the shortlist, so it is exact as is
+    assert idx.fallbacks == 0 and r.eps == 0.0
     assert (_np(r.ids) == g["l2_k10_ids"]).all() and (_np(r.scores) == g["l2_k10_scores"]).all()
-    # a corpus larger than the shortlist: rows are dropped by approximate cosine, so the certificate must refuse
+    got = _merged_lists(idx.automerge(r.ids, r.scores))
+    mi, ms = g["l2_k10_merged_ids"], g["l2_k10_merged_scores"]
+    for b, lst in enumerate(got):
+        n = int((mi[b] >= 0).sum())
+        assert [o for o, _ in lst] == mi[b, :n].tolist() and [s for _, s in lst] == ms[b, :n].tolist()
+    # rows of very different norms: L2 order != cosine order
     rng = np.random.default_rng(3)
-    c = (rng.standard_normal((20000, 64)) * rng.uniform(0.5, 2.0, (20000, 1))).astype(np.float32)  # norms vary: L2 != cosine order
+    c = (rng.standard_normal((20000, 64)) * rng.uniform(0.5, 2.0, (20000, 1))).astype(np.float32)
     bits = oracle.f32_to_bf16_bits(c)
     q = rng.standard_normal((4, 64)).astype(np.float32)
-    idx = _index(bits, None, score_mode=1, variant=_lib.SCAN_SIMT)
-    r = idx.search_certified(torch.from_numpy(q).cuda(), 10)
-    torch.cuda.synchronize()
-    assert idx.fallbacks == 4
+    idx = _index(bits, None, score_mode=1)
+    ids, scores, lens = idx.retrieve_host(torch.from_numpy(q), 10, merge=False)
     ids_o, sc_o, _ = oracle.exact_topk(bits, q, 10, 1)
-    assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
+    assert (ids == ids_o).all() and (scores.astype(np.float32) == sc_o).all()
+    ids_c, _, _ = oracle.exact_topk(bits, q, 10, 0)
+    assert (ids_c != ids_o).any()
 
 
 # --------------------------------------------------------------------------- hand-built auto-merge cases
