@@ -378,6 +378,7 @@ def run_b200(args):
                         "certificate_failures": ser64["bad"] + pip64["bad"], "min_margin": pip64["min_margin"],
                         "eps": pip64["eps"], "mode": "hi-only bf16 queries, 64 per corpus pass"},
             "certificate_failures": bad1, "min_margin": pip1["min_margin"], "eps": pip1["eps"],
+            "exchange": (sharded.transport + (" (fused into the select / merge kernels over peer memory)" if sharded.transport == "peer" else " all-gather")) if sharded is not None else None,
             "parity_vs_gpu_exact_scan": parity_ok,
         }
         print(json.dumps(line))

@@ -142,6 +142,42 @@ int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int64_t ke
                   int score_mode, float* out_scores, int64_t* out_ids, void* stream);
 
 /*
+ * Peer exchange for the row-sharded corpus: the all-gather fused into the kernels on either side of it.
+ * Every rank owns, per pipeline slot, a receive region [world][record] and a flag array uint32[world] in
+ * memory that all ranks have mapped (CUDA peer / symmetric memory; tensor_truth_b200/sharded.py).
+ *   tt_rescore_topk_push   = tt_rescore_topk whose selecting kernel ALSO stores this rank's (keys, ids)
+ *                            record into every peer's region (slot [rank]) and then raises flag[rank]
+ *                            = epoch on every peer with a system-scope release.
+ *   tt_exchange_push       = the same publication of an already finished record (after a host-side repair).
+ *   tt_merge_topk_pulled   = tt_merge_topk whose kernel first waits (acquire) until all `world` flags of
+ *                            this rank's slot have reached `epoch`.
+ * record layout: keys float[n_q*k] at offset 0, ids int64[n_q*k] at ids_off_bytes; records of consecutive
+ * source ranks are rec_stride_bytes apart.  A slot may be reused once every rank has merged it (sharded.py
+ * keeps a ring of 4 slots per stream pair, which the data dependencies of the pipeline make sufficient).
+ */
+#define TT_MAX_PEERS 16
+typedef struct tt_exchange {
+    int world, rank;
+    uint32_t epoch;
+    uint64_t rec_stride_bytes;
+    uint64_t ids_off_bytes;
+    void* peer_recv[TT_MAX_PEERS];      /* peer p: base of ITS receive region for this slot, as mapped here */
+    uint32_t* peer_flags[TT_MAX_PEERS]; /* peer p: ITS flag array for this slot, as mapped here             */
+    uint32_t* ticket;                   /* local device word, zero between calls (one per slot)             */
+} tt_exchange_t;
+
+int tt_rescore_topk_push(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                         int64_t id_base, const float* q_f32, int n_q,
+                         const int64_t* cand_ids, int n_cand, const float* cand_thresh, int n_lists,
+                         int k, int score_mode,
+                         float* out_keys, float* out_scores, int64_t* out_ids, float* out_margin,
+                         void* ws, size_t ws_bytes, const tt_exchange_t* xchg, void* stream);
+int tt_exchange_push(const void* record, size_t nbytes, const tt_exchange_t* xchg, void* stream);
+int tt_merge_topk_pulled(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
+                         int64_t ids_list_stride, int n_q, int k_in, int k_out, int score_mode,
+                         float* out_scores, int64_t* out_ids, const tt_exchange_t* xchg, void* stream);
+
+/*
  * Stage 3 -- auto-merge.  Replaces AutoMergingRetriever._retrieve after the base retriever
  * returned (rag_engine.py:641-643; upstream _fill_in_nodes / _get_parents_and_merge /
  * _try_merging loop, then a stable sort by score).  One CTA per query; float64 scores.

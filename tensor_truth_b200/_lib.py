@@ -32,9 +32,23 @@ SIGNATURES = {
     "tt_scan_exact_workspace_bytes": (_Z, [_I, _I, _I]),
     "tt_scan_exact_f64": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "tt_merge_topk": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P]),
+    "tt_rescore_topk_push": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P, _P]),
+    "tt_exchange_push": (_I, [_P, _Z, _P, _P]),
+    "tt_merge_topk_pulled": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tt_automerge_max_k": (_I, []),
     "tt_automerge": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _L, _D, _I, _P, _P, _P, _I, _P]),
 }
+
+
+MAX_PEERS = 16
+
+
+class Exchange(C.Structure):
+    """``tt_exchange_t`` (include/tt_b200.h): where one launch pushes its record and which flags it raises / waits on."""
+
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("epoch", C.c_uint32), ("rec_stride_bytes", C.c_uint64),
+                ("ids_off_bytes", C.c_uint64), ("peer_recv", C.c_void_p * MAX_PEERS), ("peer_flags", C.c_void_p * MAX_PEERS),
+                ("ticket", C.c_void_p)]
 
 
 class TTError(RuntimeError):
@@ -74,5 +88,5 @@ def check(rc: int) -> None:
 
 
 def ptr(t):
-    """Device (or host) pointer of a torch tensor, or None."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device (or host) pointer of a torch tensor as an int (ctypes converts it for ``c_void_p`` parameters), or None."""
+    return None if t is None else t.data_ptr()

@@ -28,7 +28,9 @@ int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64
                    cudaStream_t st);
 int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists,
                   int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys, float* out_scores,
-                  int64_t* out_ids, float* out_margin, cudaStream_t st);
+                  int64_t* out_ids, float* out_margin, cudaStream_t st, const tt_exchange_t* xh = nullptr, bool push = false,
+                  bool wait = false);
+int launch_exchange_push(const void* rec, size_t nbytes, const tt_exchange_t* h, cudaStream_t st);
 int launch_automerge(const int64_t* ids, const float* scores, int n_q, int k, const int32_t* parent_of,
                      const int32_t* child_count, const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
                      double ratio_thresh, int max_rounds, int64_t* out_ids, double* out_scores, int32_t* out_len,
@@ -150,6 +152,16 @@ int tt_rescore_topk(const void* corpus, int corpus_dtype, int64_t n_rows, int di
                     int64_t id_base, const float* q_f32, int n_q, const int64_t* cand_ids, int n_cand,
                     const float* cand_thresh, int n_lists, int k, int score_mode, float* out_keys, float* out_scores,
                     int64_t* out_ids, float* out_margin, void* ws, size_t ws_bytes, void* stream) {
+    return tt_rescore_topk_push(corpus, corpus_dtype, n_rows, dim, row_stride_elems, id_base, q_f32, n_q, cand_ids, n_cand,
+                                cand_thresh, n_lists, k, score_mode, out_keys, out_scores, out_ids, out_margin, ws, ws_bytes,
+                                nullptr, stream);
+}
+
+int tt_rescore_topk_push(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                         int64_t id_base, const float* q_f32, int n_q, const int64_t* cand_ids, int n_cand,
+                         const float* cand_thresh, int n_lists, int k, int score_mode, float* out_keys, float* out_scores,
+                         int64_t* out_ids, float* out_margin, void* ws, size_t ws_bytes, const tt_exchange_t* xchg,
+                         void* stream) {
     TT_CHECK_ARG(corpus_dtype == TT_DTYPE_BF16 || corpus_dtype == TT_DTYPE_F32, "tt_rescore_topk: dtype %d", corpus_dtype);
     TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_rescore_topk: score_mode %d",
                  score_mode);
@@ -158,7 +170,7 @@ int tt_rescore_topk(const void* corpus, int corpus_dtype, int64_t n_rows, int di
     TT_CHECK_ARG(n_q >= 0 && n_cand >= 0 && k >= 1, "tt_rescore_topk: n_q=%d n_cand=%d k=%d", n_q, n_cand, k);
     TT_CHECK_ARG(id_base >= 0 && id_base + n_rows <= (int64_t(1) << 32), "tt_rescore_topk: ids must stay below 2^32");
     if (n_q == 0) return TT_OK;
-    TT_CHECK_ARG(q_f32 && out_ids && (n_cand == 0 || cand_ids), "tt_rescore_topk: null pointer");
+    TT_CHECK_ARG(q_f32 && (out_ids || xchg) && (n_cand == 0 || cand_ids), "tt_rescore_topk: null pointer");
     if (ws_bytes < tt_rescore_workspace_bytes(n_q, n_cand) || (n_cand > 0 && !ws)) {
         set_error("tt_rescore_topk: workspace %zu < %zu bytes", ws_bytes, tt_rescore_workspace_bytes(n_q, n_cand));
         return TT_ERR_WORKSPACE;
@@ -168,7 +180,13 @@ int tt_rescore_topk(const void* corpus, int corpus_dtype, int64_t n_rows, int di
                             score_mode, packed, TT_STREAM(stream));
     if (rc) return rc;
     return launch_select(packed, n_cand, nullptr, nullptr, 0, 0, 0, n_q, 0, k, score_mode, cand_thresh,
-                         cand_thresh ? n_lists : 0, out_keys, out_scores, out_ids, out_margin, TT_STREAM(stream));
+                         cand_thresh ? n_lists : 0, out_keys, out_scores, out_ids, out_margin, TT_STREAM(stream), xchg,
+                         xchg != nullptr, false);
+}
+
+int tt_exchange_push(const void* record, size_t nbytes, const tt_exchange_t* xchg, void* stream) {
+    TT_CHECK_ARG(record && xchg, "tt_exchange_push: null pointer");
+    return launch_exchange_push(record, nbytes, xchg, TT_STREAM(stream));
 }
 
 size_t tt_scan_exact_workspace_bytes(int device, int n_q, int k) {
@@ -214,6 +232,13 @@ int tt_scan_exact_f64(const void* corpus, int corpus_dtype, int64_t n_rows, int 
 
 int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride, int64_t ids_list_stride,
                   int n_q, int k_in, int k_out, int score_mode, float* out_scores, int64_t* out_ids, void* stream) {
+    return tt_merge_topk_pulled(keys, ids, n_lists, keys_list_stride, ids_list_stride, n_q, k_in, k_out, score_mode,
+                                out_scores, out_ids, nullptr, stream);
+}
+
+int tt_merge_topk_pulled(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
+                         int64_t ids_list_stride, int n_q, int k_in, int k_out, int score_mode, float* out_scores,
+                         int64_t* out_ids, const tt_exchange_t* xchg, void* stream) {
     TT_CHECK_ARG(keys_list_stride >= 0 && ids_list_stride >= 0, "tt_merge_topk: negative list stride");
     TT_CHECK_ARG(n_lists >= 1 && n_q >= 0 && k_in >= 1 && k_out >= 1, "tt_merge_topk: n_lists=%d n_q=%d k_in=%d k_out=%d",
                  n_lists, n_q, k_in, k_out);
@@ -222,9 +247,9 @@ int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int64_t ke
     if (n_q == 0) return TT_OK;
     TT_CHECK_ARG(keys && ids && out_ids, "tt_merge_topk: null pointer");
     return launch_select(nullptr, 0, keys, ids, n_lists, keys_list_stride, ids_list_stride, n_q, k_in, k_out, score_mode,
-                         nullptr, 0, nullptr, out_scores,
-                         out_ids, nullptr, TT_STREAM(stream));
+                         nullptr, 0, nullptr, out_scores, out_ids, nullptr, TT_STREAM(stream), xchg, false, xchg != nullptr);
 }
+
 
 int tt_automerge_max_k(void) { return automerge_max_k(); }
 

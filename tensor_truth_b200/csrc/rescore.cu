@@ -3,6 +3,8 @@
 // With stage 1 this reproduces the exact brute-force target of the vector-store query the
 // reference issues at /root/reference/src/tensortruth/rag_engine.py:639 and the scoring
 // ChromaVectorStore applies to it (cosine here; exp(-squared-L2) in TT_SCORE_CHROMA_L2_EXP).
+#include <string.h>
+
 #include "tt_common.cuh"
 
 namespace tt {
@@ -96,6 +98,74 @@ __device__ __forceinline__ float score_of_key(float key, int mode) {
     return mode == TT_SCORE_COSINE ? key : float(exp(double(key)));  // key = -d
 }
 
+// ------------------------------------------------------------------ peer exchange (row-sharded corpus)
+// The per-rank exact top-k is PUSHED straight from the selecting kernel into every rank's receive region over
+// NVLink peer mappings (symmetric memory), followed by a system-scope release of a per-source flag; the merging
+// kernel on each rank spins on its own flags (acquire) before it reads.  No NCCL call, no extra kernel: the
+// collective is fused into the two kernels on either side of it.
+struct Xchg {
+    int push_world;  // > 0: push this launch's output to that many peers
+    int wait_world;  // > 0: wait for that many sources before reading the input lists
+    int rank;
+    unsigned epoch;
+    unsigned long long rec_stride, ids_off;       // layout of a receive region: [source rank][keys | ids]
+    unsigned long long recv[TT_MAX_PEERS];        // peer p: base of its receive region for this slot
+    unsigned long long flags[TT_MAX_PEERS];       // peer p: its flag array for this slot (element [rank] is ours)
+    unsigned* ticket;                             // local counter, zero between launches
+    const unsigned* wait_flags;                   // local flag array for this slot
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// all threads of all blocks of the launch call this after their peer stores
+__device__ __forceinline__ void xchg_publish(const Xchg& x) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned tk = atomicAdd(x.ticket, 1u);
+        if (tk == gridDim.x - 1) {  // last block: every block's stores are fenced; raise our flag on every peer
+            *x.ticket = 0u;
+            __threadfence_system();
+            for (int p = 0; p < x.push_world; ++p)
+                st_release_sys(reinterpret_cast<unsigned*>(x.flags[p]) + x.rank, x.epoch);
+        }
+    }
+}
+
+// all threads of a block call this before reading gathered lists
+__device__ __forceinline__ void xchg_wait(const Xchg& x) {
+    if (int(threadIdx.x) < x.wait_world) {
+        long long t0 = 0;
+        for (unsigned spins = 0;; ++spins) {
+            if (int(ld_acquire_sys(x.wait_flags + threadIdx.x) - x.epoch) >= 0) break;
+            if ((spins & 0xfffu) == 0xfffu) {
+                const long long now = clock64();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 20000000000ll) {
+                    printf("tt_b200: peer exchange timed out waiting for rank %d (epoch %u)\n", int(threadIdx.x), x.epoch);
+                    __trap();
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void xchg_store(const Xchg& x, size_t o, float key, int64_t id) {
+    for (int p = 0; p < x.push_world; ++p) {
+        const unsigned long long rec = x.recv[p] + (unsigned long long)x.rank * x.rec_stride;
+        reinterpret_cast<float*>(rec)[o] = key;
+        reinterpret_cast<int64_t*>(rec + x.ids_off)[o] = id;
+    }
+}
+
 // ------------------------------------------------------------------ select: one CTA per query
 // Sorts the query's packed candidates in chunks of SEL_CHUNK (carrying the running top-k) and
 // emits the k best.  Input either `packed` [n_q, n_in] or (keys, ids) laid out
@@ -111,11 +181,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
                                                              int n_thresh, float* __restrict__ out_keys,
                                                              float* __restrict__ out_scores,
                                                              int64_t* __restrict__ out_ids,
-                                                             float* __restrict__ out_margin) {
+                                                             float* __restrict__ out_margin, const Xchg x) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ float red[32];
     const int b = blockIdx.x;
+    if (x.wait_world) xchg_wait(x);
     const int total = packed ? n_in : n_lists * k_in;
     int carried = 0;  // entries [0, carried) of s hold the running top-k
     for (int base = 0; base < total || base == 0;) {
@@ -148,8 +219,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
         const float key = e ? entry_key(e) : -INFINITY;
         if (out_keys) out_keys[o] = key;
         if (out_scores) out_scores[o] = e ? score_of_key(key, mode) : -INFINITY;
-        out_ids[o] = e ? int64_t(entry_id(e)) : int64_t(-1);
+        if (out_ids) out_ids[o] = e ? int64_t(entry_id(e)) : int64_t(-1);
+        if (x.push_world) xchg_store(x, o, key, e ? int64_t(entry_id(e)) : int64_t(-1));
     }
+    if (x.push_world) xchg_publish(x);
     if (out_margin) {
         float m = -INFINITY;
         if (thresh)
@@ -190,11 +263,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_small_kernel(
     const uint64_t* __restrict__ packed, int n_in, const float* __restrict__ in_keys, const int64_t* __restrict__ in_ids,
     int n_lists, int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode,
     const float* __restrict__ thresh, int n_thresh, float* __restrict__ out_keys, float* __restrict__ out_scores,
-    int64_t* __restrict__ out_ids, float* __restrict__ out_margin) {
+    int64_t* __restrict__ out_ids, float* __restrict__ out_margin, const Xchg x) {
     __shared__ uint64_t part[2][32];
     __shared__ uint64_t win[SMALL_K];
     __shared__ float red[32];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (x.wait_world) xchg_wait(x);
     const int total = packed ? n_in : n_lists * k_in;
     uint64_t e[SMALL_EPT];
 #pragma unroll
@@ -235,8 +309,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_small_kernel(
         const float key = w ? entry_key(w) : -INFINITY;
         if (out_keys) out_keys[o] = key;
         if (out_scores) out_scores[o] = w ? score_of_key(key, mode) : -INFINITY;
-        out_ids[o] = w ? int64_t(entry_id(w)) : int64_t(-1);
+        if (out_ids) out_ids[o] = w ? int64_t(entry_id(w)) : int64_t(-1);
+        if (x.push_world) xchg_store(x, o, key, w ? int64_t(entry_id(w)) : int64_t(-1));
     }
+    if (x.push_world) xchg_publish(x);
     if (out_margin) {
         float m = -INFINITY;
         if (thresh)
@@ -264,9 +340,63 @@ static int pow2_at_least(int n) {
     return p;
 }
 
+static int fill_xchg(Xchg* x, const tt_exchange_t* h, bool push, bool wait) {
+    memset(x, 0, sizeof(*x));
+    if (!h) return TT_OK;
+    TT_CHECK_ARG(h->world >= 1 && h->world <= TT_MAX_PEERS && h->rank >= 0 && h->rank < h->world,
+                 "tt_exchange: world=%d rank=%d", h->world, h->rank);
+    x->rank = h->rank;
+    x->epoch = h->epoch;
+    x->rec_stride = h->rec_stride_bytes;
+    x->ids_off = h->ids_off_bytes;
+    if (push) {
+        TT_CHECK_ARG(h->ticket != nullptr, "tt_exchange: null ticket");
+        x->push_world = h->world;
+        x->ticket = h->ticket;
+        for (int p = 0; p < h->world; ++p) {
+            TT_CHECK_ARG(h->peer_recv[p] && h->peer_flags[p], "tt_exchange: null peer pointer %d", p);
+            x->recv[p] = reinterpret_cast<unsigned long long>(h->peer_recv[p]);
+            x->flags[p] = reinterpret_cast<unsigned long long>(h->peer_flags[p]);
+        }
+    }
+    if (wait) {
+        TT_CHECK_ARG(h->peer_flags[h->rank] != nullptr, "tt_exchange: null local flags");
+        x->wait_world = h->world;
+        x->wait_flags = h->peer_flags[h->rank];
+    }
+    return TT_OK;
+}
+
+// one block per peer copies the finished local record to it, then the flags are raised (exchange without compute:
+// used when the record was repaired on the host side of the certificate check)
+__global__ void __launch_bounds__(256) exchange_push_kernel(const unsigned char* __restrict__ rec, unsigned long long nbytes,
+                                                            const Xchg x) {
+    const int p = blockIdx.x;
+    unsigned char* dst = reinterpret_cast<unsigned char*>(x.recv[p] + (unsigned long long)x.rank * x.rec_stride);
+    for (unsigned long long i = threadIdx.x * 4ull; i < nbytes; i += 256 * 4ull)
+        *reinterpret_cast<unsigned*>(dst + i) = *reinterpret_cast<const unsigned*>(rec + i);
+    xchg_publish(x);
+}
+
+int launch_exchange_push(const void* rec, size_t nbytes, const tt_exchange_t* h, cudaStream_t st) {
+    Xchg x;
+    int rc = fill_xchg(&x, h, true, false);
+    if (rc) return rc;
+    TT_CHECK_ARG(h && nbytes % 4 == 0 && nbytes <= h->rec_stride_bytes, "tt_exchange_push: nbytes=%zu", nbytes);
+    exchange_push_kernel<<<h->world, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(rec), nbytes, x);
+    TT_LAUNCH_OK("exchange_push_kernel");
+    return TT_OK;
+}
+
 int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists,
                   int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys,
-                  float* out_scores, int64_t* out_ids, float* out_margin, cudaStream_t st) {
+                  float* out_scores, int64_t* out_ids, float* out_margin, cudaStream_t st,
+                  const tt_exchange_t* xh = nullptr, bool push = false, bool wait = false) {
+    Xchg x;
+    {
+        int rc = fill_xchg(&x, xh, push, wait);
+        if (rc) return rc;
+    }
     const int total = packed ? n_in : n_lists * k_in;
     if (keys_stride == 0) keys_stride = int64_t(n_q) * k_in;
     if (ids_stride == 0) ids_stride = int64_t(n_q) * k_in;
@@ -274,7 +404,7 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
         if (n_q == 0) return TT_OK;
         select_small_kernel<<<n_q, SEL_THREADS, 0, st>>>(packed, n_in, in_keys, in_ids, n_lists, keys_stride, ids_stride, n_q,
                                                          k_in, k, mode, thresh, n_thresh, out_keys, out_scores, out_ids,
-                                                         out_margin);
+                                                         out_margin, x);
         TT_LAUNCH_OK("select_small_kernel");
         return TT_OK;
     }
@@ -292,7 +422,7 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
     }
     if (n_q == 0) return TT_OK;
     select_kernel<<<n_q, SEL_THREADS, smem, st>>>(packed, n_in, in_keys, in_ids, n_lists, keys_stride, ids_stride, n_q, k_in, chunk, k, mode,
-                                                  thresh, n_thresh, out_keys, out_scores, out_ids, out_margin);
+                                                  thresh, n_thresh, out_keys, out_scores, out_ids, out_margin, x);
     TT_LAUNCH_OK("select_kernel");
     return TT_OK;
 }

@@ -15,6 +15,8 @@ HBM layout (one shard):
 
 from __future__ import annotations
 
+import contextlib
+import ctypes as C
 import threading
 from dataclasses import dataclass
 from typing import Optional
@@ -31,6 +33,9 @@ EPS_BF16_CORPUS = 2.5e-4   # corpus stored in bf16: hi/lo split residual + fp32 
 EPS_F32_CORPUS = 4.2e-3    # fp32 master scanned through a bf16 shadow: + 2^-8 corpus rounding
 EPS_HI_ONLY = 3.95e-3      # added when the query travels as bf16 hi only (|q - bf16(q)| <= 2^-8 |q|)
 HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first (64 queries per corpus pass)
+
+
+_NULL_CTX = contextlib.nullcontext()
 
 
 @dataclass
@@ -83,6 +88,7 @@ class DeviceIndex:
             self.master = None
             self.corpus = stored
             self.eps = EPS_BF16_CORPUS
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.n_rows, self.dim = int(self.corpus.shape[0]), int(self.corpus.shape[1])
         if self.dim % 8:
             raise ValueError("dim must be a multiple of 8")
@@ -142,6 +148,12 @@ class DeviceIndex:
             self._ws[key] = w
         return w
 
+    def _on_device(self):
+        """Context that makes this index's GPU current -- a no-op object when it already is (the common case)."""
+        if torch.cuda.current_device() == self._dev_index:
+            return _NULL_CTX
+        return torch.cuda.device(self.device)
+
     def _row_stride(self, t: torch.Tensor) -> int:
         return max(int(t.stride(0)), self.dim)  # an empty tensor reports stride 0
 
@@ -157,11 +169,14 @@ class DeviceIndex:
         return q
 
     # ------------------------------------------------------------------ stage 1 + 2
-    def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None, hi_only: Optional[bool] = None) -> SearchResult:
+    def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None, hi_only: Optional[bool] = None,
+               xchg=None) -> SearchResult:
         """Shortlist scan + exact re-score.  Asynchronous on the current stream; ``margin[b] > result.eps``
         certifies that query b's top-k is the exact one (``search_certified`` acts on it).
         ``hi_only``: send the queries through the tensor cores as bf16 hi halves only (twice the queries per
-        corpus pass, wider certificate); default: batches above ``HI_ONLY_ABOVE``."""
+        corpus pass, wider certificate); default: batches above ``HI_ONLY_ABOVE``.
+        ``xchg`` (``_lib.Exchange``): row-sharded corpus -- the selecting kernel also pushes this shard's top-k
+        record to every peer rank (sharded.py)."""
         q = self._check_queries(q)
         b = int(q.shape[0])
         if hi_only is None:
@@ -175,7 +190,7 @@ class DeviceIndex:
             return SearchResult(ex.keys, ex.scores, ex.ids, w["margin"], 0.0)
         L, st = self.lib, self._stream()
         n_cand = self.n_lists * self.kprime
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(L.tt_prepare_queries(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), st))
             if self.scan_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -189,11 +204,11 @@ class DeviceIndex:
                 e1.record()
                 self.scan_events.append((e0, e1))
             src = self.master if self.master is not None else self.corpus
-            check(L.tt_rescore_topk(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
-                                    self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q), b,
-                                    ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), self.n_lists, k, self.score_mode,
-                                    ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
-                                    ptr(w["ws"]), w["ws"].numel(), st))
+            check(L.tt_rescore_topk_push(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
+                                         self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q), b,
+                                         ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), self.n_lists, k, self.score_mode,
+                                         ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
+                                         ptr(w["ws"]), w["ws"].numel(), C.byref(xchg) if xchg is not None else None, st))
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], self.eps + (EPS_HI_ONLY if hi_only else 0.0))
 
     def search_exact(self, q: torch.Tensor, k: int, out: Optional[dict] = None) -> SearchResult:
@@ -259,7 +274,7 @@ class DeviceIndex:
             out = MergeResult(torch.empty((b, max_out), dtype=torch.int64, device=self.device),
                               torch.empty((b, max_out), dtype=torch.float64, device=self.device),
                               torch.empty((b,), dtype=torch.int32, device=self.device))
-        with torch.cuda.device(self.device):
+        with self._on_device():
             check(self.lib.tt_automerge(ptr(ids), ptr(scores), b, k, ptr(self.parent_of), ptr(self.child_count),
                                         ptr(self.prev_id), ptr(self.next_id), self.n_nodes, float(ratio_thresh),
                                         int(max_rounds), ptr(out.ids), ptr(out.scores), ptr(out.lens),

@@ -10,6 +10,7 @@ Record layout per rank (what travels):  ``[ keys float32 B*k | pad to 8 B | ids 
 
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -70,6 +71,49 @@ class ShardedSearch:
         return self.merge(recv, self.world, b, k, k_out or k, slot)
 
 
+class PeerBuffers:
+    """Symmetric (peer-mapped) receive regions + flags for one (batch, k) shape: what lets the selecting kernel push
+    its record straight into every rank's memory and the merging kernel wait on flags (include/tt_b200.h,
+    ``tt_exchange_t``).  A ring of ``DEPTH`` slots: with steps alternating between two streams, slot e % 4 is only
+    rewritten (epoch e+4) after this rank merged epoch e+2, which needed every peer's push of e+2, which on that peer
+    is stream-ordered after ITS merge of epoch e -- so nobody is still reading the slot."""
+
+    DEPTH = 4
+
+    def __init__(self, b: int, k: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        rec, self.ids_off, _ = record_layout(b, k)
+        self.rec_stride = (rec + 15) // 16 * 16
+        self.region = self.world * self.rec_stride
+        self.flags_off = (self.DEPTH * self.region + 127) // 128 * 128
+        total = self.flags_off + (self.DEPTH * self.world * 4 + 127) // 128 * 128
+        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.tickets = torch.zeros(self.DEPTH, dtype=torch.int32, device=device)
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's zero-fill has landed before anyone pushes
+
+    def next(self):
+        """The exchange descriptor of the next step (all ranks call this in lockstep) and the local addresses the merge reads."""
+        from ._lib import Exchange
+
+        self.epoch += 1
+        slot = (self.epoch - 1) % self.DEPTH
+        x = Exchange()
+        x.world, x.rank, x.epoch = self.world, self.rank, self.epoch
+        x.rec_stride_bytes, x.ids_off_bytes = self.rec_stride, self.ids_off
+        for p in range(self.world):
+            x.peer_recv[p] = self.ptrs[p] + slot * self.region
+            x.peer_flags[p] = self.ptrs[p] + self.flags_off + slot * self.world * 4
+        x.ticket = self.tickets.data_ptr() + 4 * slot
+        return x, self.ptrs[self.rank] + slot * self.region
+
+
 class ShardedIndex:
     """``DeviceIndex`` shards + NCCL all-gather + the CUDA merge and auto-merge kernels."""
 
@@ -82,6 +126,44 @@ class ShardedIndex:
         self._margins = None
         self.plumbing = ShardedSearch(self._local_search, self._merge, self.device, group)
         self._out: dict = {}
+        self.group = group
+        self._peers: dict = {}
+        # peer pushes need symmetric memory (NVLink peer mappings); without it the exchange is an NCCL all-gather
+        self.transport = "nccl" if os.environ.get("TT_EXCHANGE", "peer") == "nccl" or self.plumbing.world == 1 else "peer"
+
+    def peers(self, b: int, k: int) -> Optional[PeerBuffers]:
+        if self.transport != "peer":
+            return None
+        pb = self._peers.get((b, k))
+        if pb is None:
+            try:
+                pb = self._peers[(b, k)] = PeerBuffers(b, k, self.device, self.group)
+            except Exception as exc:  # every rank fails alike (same node, same driver): fall back together
+                import warnings
+
+                warnings.warn(f"symmetric memory unavailable ({exc}); exchanging with NCCL all-gather")
+                self.transport = "nccl"
+                return None
+        return pb
+
+    def _outputs(self, b, k_out, slot):
+        o = self._out.get((b, k_out, slot))
+        if o is None:
+            o = self._out[(b, k_out, slot)] = (torch.empty((b, k_out), dtype=torch.float32, device=self.device),
+                                               torch.empty((b, k_out), dtype=torch.int64, device=self.device))
+        return o
+
+    def _merge_pulled(self, x, region_ptr, b, k, k_out, slot):
+        """Merge straight out of this rank's receive region once every source's flag has reached the epoch."""
+        import ctypes as C
+
+        L, ptr, check = self._lib.lib(), self._lib.ptr, self._lib.check
+        o = self._outputs(b, k_out, slot)
+        with self.local._on_device():
+            check(L.tt_merge_topk_pulled(region_ptr, region_ptr + x.ids_off_bytes, x.world, x.rec_stride_bytes // 4,
+                                         x.rec_stride_bytes // 8, b, k, k_out, self.local.score_mode, ptr(o[0]), ptr(o[1]),
+                                         C.byref(x), torch.cuda.current_stream().cuda_stream))
+        return o
 
     def _local_search(self, q, k, keys_out, ids_out, slot=0):
         w = dict(self.local._buffers(int(q.shape[0]), k, slot))
@@ -94,15 +176,10 @@ class ShardedIndex:
     def _merge(self, recv, world, b, k, k_out, slot=0):
         L, ptr, check = self._lib.lib(), self._lib.ptr, self._lib.check
         rec, ids_off, _ = record_layout(b, k)
-        o = self._out.get((b, k_out, slot))
-        if o is None:
-            o = self._out[(b, k_out, slot)] = (torch.empty((b, k_out), dtype=torch.float32, device=self.device),
-                                               torch.empty((b, k_out), dtype=torch.int64, device=self.device))
-        import ctypes as C
-
+        o = self._outputs(b, k_out, slot)
         base = recv.data_ptr()
-        with torch.cuda.device(self.device):
-            check(L.tt_merge_topk(C.c_void_p(base), C.c_void_p(base + ids_off), world, rec // 4, rec // 8, b, k, k_out,
+        with self.local._on_device():
+            check(L.tt_merge_topk(base, base + ids_off, world, rec // 4, rec // 8, b, k, k_out,
                                   self.local.score_mode, ptr(o[0]), ptr(o[1]), torch.cuda.current_stream().cuda_stream))
         return o
 
@@ -111,7 +188,17 @@ class ShardedIndex:
         receives this rank's certificate margins (compare with ``self.last.eps``)."""
         self._margins = margins
         q = self.local._check_queries(q)
-        return self.plumbing.search(q, k, slot=slot)
+        b = int(q.shape[0])
+        pb = self.peers(b, k)
+        if pb is None:
+            return self.plumbing.search(q, k, slot=slot)
+        # fused exchange: the selecting kernel pushes to every peer, the merging kernel waits on the flags
+        x, region = pb.next()
+        w = dict(self.local._buffers(b, k, slot))
+        if margins is not None:
+            w["margin"] = margins
+        self.last = self.local.search(q, k, out=w, xchg=x)
+        return self._merge_pulled(x, region, b, k, k, slot)
 
     def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5):
         """Host queries in, merged + auto-merged lists out (numpy), with the certificate enforced per rank."""
@@ -123,10 +210,20 @@ class ShardedIndex:
         self._margins = margins
         r = self._local_search(q, k, keys, ids)
         bad = torch.nonzero(~(margins > r.eps)).flatten()
-        if bad.numel():  # rank-local repair (writes into the send record); the collective below is reached by every rank
+        if bad.numel():  # rank-local repair (writes into the send record); the exchange below is reached by every rank
             local._repair(q, k, r, bad, hi_lo_first=r.eps > local.eps)
-        self.plumbing.exchange(send, recv)
-        scores, mids = self._merge(recv, self.plumbing.world, b, k, k)
+        pb = self.peers(b, k)
+        if pb is None:
+            self.plumbing.exchange(send, recv)
+            scores, mids = self._merge(recv, self.plumbing.world, b, k, k)
+        else:
+            x, region = pb.next()
+            import ctypes as C
+
+            with local._on_device():
+                self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), send.numel() // 4 * 4, C.byref(x),
+                                                                 torch.cuda.current_stream().cuda_stream))
+            scores, mids = self._merge_pulled(x, region, b, k, k, 0)
         merged = local.tree is not None
         rec = local._record(b, k, merged)
         d, h = rec["d"], rec["h"]
