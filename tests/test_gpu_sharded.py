@@ -1,0 +1,67 @@
+"""Row-sharded path on real GPUs (needs >= 2; skipped otherwise): ShardedIndex with the fused peer exchange and
+with the NCCL all-gather transport must both reproduce the whole-corpus oracle answer bit-exactly."""
+
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, transport, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import oracle
+    from oracle import cport
+    from tensor_truth_b200.index import DeviceIndex
+    from tensor_truth_b200.sharded import ShardedIndex, shard_bounds
+    from tensor_truth_b200.synth import make_small
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TT_EXCHANGE=transport)
+    torch.cuda.set_device(rank)
+    dev = torch.device(f"cuda:{rank}")
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    tree, bits, inv, q = make_small(50_000, 12, dim=1024, levels=3, seed=31)
+    lo, hi = shard_bounds(bits.shape[0], world, rank)
+    idx = DeviceIndex(bits[lo:hi], tree, id_base=lo, device=dev)
+    sh = ShardedIndex(idx)
+    assert sh.transport == ("peer" if transport == "peer" else "nccl")
+    ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
+    qd = torch.from_numpy(q).to(dev)
+    for rep in range(6):  # several epochs through the slot ring, two batch shapes
+        for b in (1, 12):
+            scores, ids = sh.search(qd[:b], 10)
+            torch.cuda.synchronize()
+            assert (ids.cpu().numpy() == ids_o[:b]).all() and (scores.cpu().numpy() == sc_o[:b]).all(), (rep, b)
+    ids_h, sc_h, lens = sh.retrieve_host(torch.from_numpy(q[:3]), 10)
+    for b in range(3):
+        exp = oracle.retrieve(bits, q[b], 10, tree)
+        got = [(int(o), float(s)) for o, s in zip(ids_h[b, :lens[b]], sc_h[b, :lens[b]])]
+        assert got == exp
+    assert sh.transport == ("peer" if transport == "peer" else "nccl")  # no silent fallback
+    open(os.path.join(out_dir, f"ok-{transport}-{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_sharded_index_two_gpus(tmp_path, transport):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    mp.spawn(_worker, args=(2, _free_port(), transport, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(tmp_path / f"ok-{transport}-{r}") for r in range(2))
