@@ -313,13 +313,9 @@ def run_b200(args):
     e2e_steps = max(5, min(args.steps, 100))
     q_host = queries.cpu()
     q_lists = [row.tolist() for row in q_host]  # host input as an embed model hands it over: a Python list of floats
-    if sharded is None:
-        base_r = B200VectorIndexRetriever(idx, similarity_top_k=TOP_K)
-        am = B200AutoMergingRetriever(base_r, None)
-        call = lambda i: am.retrieve(QueryBundle(query_str=f"q{i}", embedding=q_lists[i % QUERY_POOL]))  # noqa: E731
-    else:
-        pinned = q_host.pin_memory()
-        call = lambda i: sharded.retrieve_host(pinned[i % QUERY_POOL:i % QUERY_POOL + 1], TOP_K)  # noqa: E731
+    base_r = B200VectorIndexRetriever(idx if sharded is None else sharded, similarity_top_k=TOP_K)
+    am = B200AutoMergingRetriever(base_r, None)  # over a ShardedIndex every rank makes the same call (SPMD)
+    call = lambda i: am.retrieve(QueryBundle(query_str=f"q{i}", embedding=q_lists[i % QUERY_POOL]))  # noqa: E731
     for i in range(3):
         out = call(i)
     barrier()
@@ -328,10 +324,10 @@ def run_b200(args):
         out = call(3 + i)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
-    n_out = len(out) if sharded is None else int(out[2][0])
+    n_out = len(out)
     e2e = {"value": e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": DIM * 4,
            "d2h_bytes_per_step": idx._record(1, TOP_K, True)["bytes"], "steps": e2e_steps,
-           "api": "B200AutoMergingRetriever.retrieve(QueryBundle)" if sharded is None else "ShardedIndex.retrieve_host",
+           "api": "B200AutoMergingRetriever.retrieve(QueryBundle)" + ("" if sharded is None else " over ShardedIndex, every rank"),
            "fallbacks": idx.fallbacks, "nodes_returned_last": n_out}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same corpus bytes

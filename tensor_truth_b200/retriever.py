@@ -79,8 +79,9 @@ class _RetrieverBase:
 class B200VectorIndexRetriever(_RetrieverBase):
     """``index.as_retriever(similarity_top_k=k)``: exact top-k leaves of the index for the query."""
 
-    def __init__(self, index: DeviceIndex, similarity_top_k: int = 10, embed_model: Any = None,
+    def __init__(self, index, similarity_top_k: int = 10, embed_model: Any = None,
                  node_table: Optional[NodeTable] = None):
+        """``index``: a ``DeviceIndex``, or a ``ShardedIndex`` (row-sharded over GPUs; every rank then makes the same calls)."""
         self.index = index
         self.similarity_top_k = int(similarity_top_k)
         self.embed_model = embed_model

@@ -95,22 +95,27 @@ class PeerBuffers:
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.tickets = torch.zeros(self.DEPTH, dtype=torch.int32, device=device)
         self.epoch = 0
+        from ._lib import Exchange
+
+        self._x = []
+        for slot in range(self.DEPTH):  # one descriptor per slot; only the epoch changes from step to step
+            x = Exchange()
+            x.world, x.rank = self.world, self.rank
+            x.rec_stride_bytes, x.ids_off_bytes = self.rec_stride, self.ids_off
+            for p in range(self.world):
+                x.peer_recv[p] = self.ptrs[p] + slot * self.region
+                x.peer_flags[p] = self.ptrs[p] + self.flags_off + slot * self.world * 4
+            x.ticket = self.tickets.data_ptr() + 4 * slot
+            self._x.append(x)
         torch.cuda.synchronize(device)
         dist.barrier(group)  # every rank's zero-fill has landed before anyone pushes
 
     def next(self):
         """The exchange descriptor of the next step (all ranks call this in lockstep) and the local addresses the merge reads."""
-        from ._lib import Exchange
-
         self.epoch += 1
         slot = (self.epoch - 1) % self.DEPTH
-        x = Exchange()
-        x.world, x.rank, x.epoch = self.world, self.rank, self.epoch
-        x.rec_stride_bytes, x.ids_off_bytes = self.rec_stride, self.ids_off
-        for p in range(self.world):
-            x.peer_recv[p] = self.ptrs[p] + slot * self.region
-            x.peer_flags[p] = self.ptrs[p] + self.flags_off + slot * self.world * 4
-        x.ticket = self.tickets.data_ptr() + 4 * slot
+        x = self._x[slot]  # the library copies it into the kernel parameters at launch, so reuse is safe
+        x.epoch = self.epoch
         return x, self.ptrs[self.rank] + slot * self.region
 
 
@@ -200,8 +205,13 @@ class ShardedIndex:
         self.last = self.local.search(q, k, out=w, xchg=x)
         return self._merge_pulled(x, region, b, k, k, slot)
 
-    def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5):
-        """Host queries in, merged + auto-merged lists out (numpy), with the certificate enforced per rank."""
+    @property
+    def tree(self):
+        return self.local.tree
+
+    def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True):
+        """Host queries in, merged (+ auto-merged) lists out (numpy), with the certificate enforced per rank.
+        Same contract as ``DeviceIndex.retrieve_host``, so the retriever classes take either; every rank must call it."""
         local = self.local
         q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
         b = int(q.shape[0])
@@ -224,7 +234,7 @@ class ShardedIndex:
                 self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), send.numel() // 4 * 4, C.byref(x),
                                                                  torch.cuda.current_stream().cuda_stream))
             scores, mids = self._merge_pulled(x, region, b, k, k, 0)
-        merged = local.tree is not None
+        merged = bool(merge and local.tree is not None)
         rec = local._record(b, k, merged)
         d, h = rec["d"], rec["h"]
         if merged:
