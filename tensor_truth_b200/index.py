@@ -33,6 +33,7 @@ EPS_BF16_CORPUS = 2.5e-4   # corpus stored in bf16: hi/lo split residual + fp32 
 EPS_F32_CORPUS = 4.2e-3    # fp32 master scanned through a bf16 shadow: + 2^-8 corpus rounding
 EPS_HI_ONLY = 3.95e-3      # added when the query travels as bf16 hi only (|q - bf16(q)| <= 2^-8 |q|)
 HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first (64 queries per corpus pass)
+MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist workspace: 148 * K' * 12 B per query)
 
 
 _NULL_CTX = contextlib.nullcontext()
@@ -311,6 +312,10 @@ class DeviceIndex:
         The H2D copy of the queries and the single D2H read of the result record are part of the call;
         the certificate is checked on the host from the margins in that record."""
         merged = bool(merge and self.tree is not None)
+        if int(q_host.shape[0]) > MAX_HOST_BATCH:  # bound the workspaces: large batches go through in slices
+            parts = [self.retrieve_host(q_host[i:i + MAX_HOST_BATCH], k, ratio_thresh, merge)
+                     for i in range(0, int(q_host.shape[0]), MAX_HOST_BATCH)]
+            return tuple(np.concatenate([p[j] for p in parts], axis=0) for j in range(3))
         with self._lock:
             q = q_host.to(self.device, torch.float32, non_blocking=True)
             q = self._check_queries(q)

@@ -493,6 +493,18 @@ def test_c4_shape_large_batch_top100():
     assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
 
 
+def test_retrieve_host_slices_large_batches(c1, monkeypatch):
+    from tensor_truth_b200 import index as index_mod
+
+    tree, bits, inv, q = c1
+    idx = _index(bits, tree)
+    whole = idx.retrieve_host(torch.from_numpy(q[:40]), 10)
+    monkeypatch.setattr(index_mod, "MAX_HOST_BATCH", 16)
+    sliced = idx.retrieve_host(torch.from_numpy(q[:40]), 10)
+    for a, b in zip(whole, sliced):
+        assert a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
 def test_c5_shape_four_levels_top200():
     """configs[4] (20M leaves, 4-level tree, top-200 feeding the merge) at test size, against the oracle end to end."""
     tree, bits, inv, q = make_small(150_000, 6, dim=1024, levels=4, seed=8)
