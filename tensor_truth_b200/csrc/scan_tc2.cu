@@ -95,12 +95,12 @@ struct Params {
 constexpr int EPI2 = 256;
 constexpr int THREADS2 = EPI2 + 64;
 
-template <int N>
+template <int N, int CH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
 scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_q, const Params p) {
     constexpr int NQ = N;      // hi only: one MMA column per query
     constexpr int NH = N / 2;  // query rows held by each CTA
-    constexpr int STAGE_BYTES = CHUNK_BYTES;
+    constexpr int STAGE_BYTES = CH * CHUNK_BYTES;  // CH 64-column chunks per ring stage (256 B contiguous per row at CH = 2)
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
 
@@ -122,6 +122,7 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = int(blockIdx.x) >> 1, n_clusters = int(gridDim.x) >> 1;
     const int n_my = (p.n_super > cluster_id) ? (p.n_super - 1 - cluster_id) / n_clusters + 1 : 0;
+    const int steps_per_tile = p.n_chunks / CH;
     constexpr int TMEM_COLS = (2 * N < 32) ? 32 : 2 * N;
 
     if (threadIdx.x == 0) {
@@ -166,12 +167,12 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
             for (int i = 0; i < n_my; ++i) {
                 const int super = cluster_id + i * n_clusters;
                 const int row0 = super * 256 + int(rank) * TILE_ROWS;
-                for (int s = 0; s < p.n_chunks; ++s) {
+                for (int s = 0; s < steps_per_tile; ++s) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
                     const uint32_t fb = mapa(smem_u32(full_bar + stage), 0);
                     if (rank == 0) mbar_expect_tx(smem_u32(full_bar + stage), 2 * STAGE_BYTES);
                     else mbar_arrive_cluster(fb);
-                    tma_load_3d_pair(smem_u32(ring + size_t(stage) * STAGE_BYTES), &map_c, 0, row0, s, fb,
+                    tma_load_3d_pair(smem_u32(ring + size_t(stage) * STAGE_BYTES), &map_c, 0, row0, s * CH, fb,
                                      POLICY_EVICT_FIRST);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -189,15 +190,18 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
                 mbar_wait(smem_u32(tmem_empty + a), (uint32_t(i >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + uint32_t(a * N);
-                for (int s = 0; s < p.n_chunks; ++s) {
+                for (int s = 0; s < steps_per_tile; ++s) {
                     mbar_wait(smem_u32(full_bar + stage), phase);
                     tcgen05_fence_after();
                     const uint32_t a_base = smem_u32(ring + size_t(stage) * STAGE_BYTES);
-                    const uint32_t b_base = smem_u32(q_s + size_t(s) * NH * 128);
 #pragma unroll
-                    for (int k = 0; k < CHUNK_COLS / 16; ++k)
-                        umma_bf16_pair(d_tmem, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
-                                       uint32_t((s | k) != 0));
+                    for (int c = 0; c < CH; ++c) {
+                        const uint32_t b_base = smem_u32(q_s + size_t(s * CH + c) * NH * 128);
+#pragma unroll
+                        for (int k = 0; k < CHUNK_COLS / 16; ++k)
+                            umma_bf16_pair(d_tmem, umma_desc_sw128(a_base + c * CHUNK_BYTES + k * 32),
+                                           umma_desc_sw128(b_base + k * 32), idesc, uint32_t((s | c | k) != 0));
+                    }
                     umma_commit_pair(smem_u32(empty_bar + stage));  // frees this ring slot in both CTAs
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
@@ -261,11 +265,11 @@ scan_tc2_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant
     }
 }
 
-template <int N>
+template <int N, int CH>
 static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* smem_out) {
     const size_t q_bytes = size_t(dim / CHUNK_COLS) * (N / 2) * 128;
     const size_t base = 1024 + q_bytes + size_t(N) * 8 + 160;
-    const size_t per_stage = size_t(CHUNK_BYTES) + 16;
+    const size_t per_stage = size_t(CH) * CHUNK_BYTES + 16;
     const int spares[4] = {128, 64, 32, 16};
     // prefer >= 128 KB of ring (bytes in flight are what buys HBM bandwidth), then >= 96 KB, then whatever fits
     for (int pass = 0; pass < 3; ++pass) {
@@ -274,8 +278,8 @@ static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* s
             const size_t fixed = base + size_t(N) * (kprime + spares[i]) * 8;
             if (fixed + 2 * per_stage > size_t(SMEM_LIMIT)) continue;
             int st_n = int((size_t(SMEM_LIMIT) - fixed) / per_stage);
-            if (pass == 0 && size_t(st_n) * CHUNK_BYTES < 128 * 1024) continue;
-            if (pass == 1 && size_t(st_n) * CHUNK_BYTES < 96 * 1024) continue;
+            if (pass == 0 && size_t(st_n) * CH * CHUNK_BYTES < 128 * 1024) continue;
+            if (pass == 1 && size_t(st_n) * CH * CHUNK_BYTES < 96 * 1024) continue;
             if (st_n > 24) st_n = 24;
             if (const char* e = getenv("TT_SCAN_STAGES")) {
                 const int want = atoi(e);
@@ -292,20 +296,13 @@ static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* s
 
 }  // namespace tc2
 
-bool scan_tc2_supported(int dim, int kprime, int n_lists) {
-    int sp, sg;
-    size_t sm;
-    return n_lists % 2 == 0 && tc2::plan<64>(dim, kprime, &sp, &sg, &sm);
-}
-
-// hi-only scan of n_q queries in passes of 64 with CTA pairs
-int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
-                    const void* q_hi, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
-                    float* out_thresh, int n_lists, cudaStream_t st) {
-    constexpr int N = 64;
+template <int N, int CH>
+static int launch2(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
+                   int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx, float* out_thresh,
+                   int n_lists, cudaStream_t st) {
     int spare = 0, stages = 0;
     size_t smem = 0;
-    if (n_lists % 2 != 0 || !tc2::plan<N>(dim, kprime, &spare, &stages, &smem)) {
+    if (n_lists % 2 != 0 || !tc2::plan<N, CH>(dim, kprime, &spare, &stages, &smem)) {
         set_error("scan_tc2: dim=%d kprime=%d n_lists=%d unsupported", dim, kprime, n_lists);
         return TT_ERR_UNSUPPORTED;
     }
@@ -324,12 +321,12 @@ int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride,
     p.out_thresh = out_thresh;
 
     CUtensorMap map_c, map_q;
-    int rc = tc::make_map(&map_c, corpus, n_rows, dim, stride, tc::TILE_ROWS, 1);
+    int rc = tc::make_map(&map_c, corpus, n_rows, dim, stride, tc::TILE_ROWS, CH);
     if (rc) return rc;
     rc = tc::make_map(&map_q, q_hi, n_q, dim, dim, N / 2, 1);
     if (rc) return rc;
 
-    auto kern = tc2::scan_tc2_kernel<N>;
+    auto kern = tc2::scan_tc2_kernel<N, CH>;
     TT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
     for (int q0 = 0; q0 < n_q; q0 += N) {
         p.q0 = q0;
@@ -338,6 +335,25 @@ int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride,
         TT_LAUNCH_OK("scan_tc2_kernel");
     }
     return TT_OK;
+}
+
+bool scan_tc2_supported(int dim, int kprime, int n_lists) {
+    int sp, sg;
+    size_t sm;
+    return n_lists % 2 == 0 && dim % 128 == 0 && tc2::plan<64, 2>(dim, kprime, &sp, &sg, &sm);
+}
+
+// hi-only scan of n_q queries in passes of 64 with CTA pairs
+int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
+                    const void* q_hi, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
+                    float* out_thresh, int n_lists, cudaStream_t st) {
+    if (const char* e = getenv("TT_SCAN_CH")) {  // tuning knob
+        if (atoi(e) == 1)
+            return launch2<64, 1>(corpus, n_rows, dim, stride, inv_norm, q_hi, n_q, kprime, id_base, out_ids, out_approx,
+                                  out_thresh, n_lists, st);
+    }
+    return launch2<64, 2>(corpus, n_rows, dim, stride, inv_norm, q_hi, n_q, kprime, id_base, out_ids, out_approx,
+                          out_thresh, n_lists, st);
 }
 
 }  // namespace tt
