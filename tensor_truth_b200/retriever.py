@@ -18,6 +18,8 @@ fallback.
 
 from __future__ import annotations
 
+import contextlib
+import threading
 from array import array
 from typing import Any, Callable, List, Optional, Sequence, Union
 
@@ -90,11 +92,21 @@ class B200VectorIndexRetriever(_RetrieverBase):
     def _query_tensor(self, query_bundle: QueryBundle) -> torch.Tensor:
         emb = query_bundle.embedding
         if emb is None:
-            emb = _embed(self.embed_model, query_bundle)
+            # MultiIndexRetriever hands ONE bundle without an embedding to every per-index retriever on a thread pool
+            # (rag_engine.py:416-424), and upstream embeds the same string once per index.  Embed it once: the
+            # first thread does the work under a lock that lives on the bundle, the others pick up the result.
             try:
-                query_bundle.embedding = emb  # upstream caches it on the bundle too
-            except Exception:
-                pass
+                lock = query_bundle.__dict__.setdefault("_tt_embed_lock", threading.Lock())
+            except AttributeError:  # a bundle type without __dict__
+                lock = contextlib.nullcontext()
+            with lock:
+                emb = query_bundle.embedding
+                if emb is None:
+                    emb = _embed(self.embed_model, query_bundle)
+                    try:
+                        query_bundle.embedding = emb  # upstream caches it on the bundle too
+                    except Exception:
+                        pass
         if isinstance(emb, (list, tuple)):  # what an embed model hands over; array('f') is the fastest list -> fp32 path
             return torch.frombuffer(array("f", emb), dtype=torch.float32).reshape(1, -1)
         return torch.as_tensor(np.asarray(emb, dtype=np.float32)).reshape(1, -1)

@@ -169,3 +169,29 @@ def test_importer_flattens_docstore_and_collection():
         flatten_index(leaf_ids + ["ghost"], emb.tolist() + [[0.0] * 16], docs)
     with pytest.raises(ValueError):
         flatten_index(leaf_ids[:-1], emb[:-1].tolist(), docs)
+
+
+def test_query_is_embedded_once_across_per_index_retrievers():
+    """one QueryBundle fanned out over several retrievers on a thread pool is embedded once."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    from tensor_truth_b200.retriever import B200VectorIndexRetriever, NodeTable
+
+    class Embedder:
+        calls = 0
+
+        def get_agg_embedding_from_queries(self, strs):
+            Embedder.calls += 1
+            time.sleep(0.05)  # a real embed model takes 10-30 ms
+            return [0.25] * 16
+
+    dummy_index = SimpleNamespace(tree=None)
+    emb = Embedder()
+    retrievers = [B200VectorIndexRetriever(dummy_index, 10, emb, NodeTable()) for _ in range(6)]
+    qb = QueryBundle(query_str="shared question")
+    with ThreadPoolExecutor(max_workers=6) as pool:
+        outs = list(pool.map(lambda r: r._query_tensor(qb), retrievers))
+    assert Embedder.calls == 1
+    assert all(o.shape == (1, 16) and float(o[0, 0]) == 0.25 for o in outs)
+    assert qb.embedding == [0.25] * 16
