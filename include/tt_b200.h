@@ -166,12 +166,24 @@ typedef struct tt_exchange {
     uint32_t* ticket;                   /* local device word, zero between calls (one per slot)             */
 } tt_exchange_t;
 
+/*
+ * Certificate for TT_SCORE_CHROMA_L2_EXP.  Stage 1 orders rows by cosine; when every row norm of the shard lies
+ * in [row_norm_min, row_norm_max] (unit-norm embeddings: both ~1) a dropped row's squared-L2 key is bounded from
+ * above through its cosine bound, and out_margin becomes (k-th exact key) - (that bound, eps included):
+ * the top-k is proven exact iff out_margin > 0.  Without it (NULL) L2-mode margins are -inf unless nothing was dropped.
+ */
+typedef struct tt_l2_cert {
+    float row_norm_min, row_norm_max; /* bounds on |c_r| over the rows of this shard, as stored */
+    float eps;                        /* bound on |stage-1 score - exact cosine| (what cosine mode compares its margin to) */
+} tt_l2_cert_t;
+
 int tt_rescore_topk_push(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
                          int64_t id_base, const float* q_f32, int n_q,
                          const int64_t* cand_ids, int n_cand, const float* cand_thresh, int n_lists,
                          int k, int score_mode,
                          float* out_keys, float* out_scores, int64_t* out_ids, float* out_margin,
-                         void* ws, size_t ws_bytes, const tt_exchange_t* xchg, void* stream);
+                         void* ws, size_t ws_bytes, const tt_exchange_t* xchg, const tt_l2_cert_t* l2_cert,
+                         void* stream);
 int tt_exchange_push(const void* record, size_t nbytes, const tt_exchange_t* xchg, void* stream);
 int tt_merge_topk_pulled(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
                          int64_t ids_list_stride, int n_q, int k_in, int k_out, int score_mode,

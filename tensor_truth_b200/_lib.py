@@ -32,7 +32,7 @@ SIGNATURES = {
     "tt_scan_exact_workspace_bytes": (_Z, [_I, _I, _I]),
     "tt_scan_exact_f64": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
     "tt_merge_topk": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P]),
-    "tt_rescore_topk_push": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P, _P]),
+    "tt_rescore_topk_push": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P, _P, _P]),
     "tt_exchange_push": (_I, [_P, _Z, _P, _P]),
     "tt_merge_topk_pulled": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tt_automerge_max_k": (_I, []),
@@ -49,6 +49,12 @@ class Exchange(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("epoch", C.c_uint32), ("rec_stride_bytes", C.c_uint64),
                 ("ids_off_bytes", C.c_uint64), ("peer_recv", C.c_void_p * MAX_PEERS), ("peer_flags", C.c_void_p * MAX_PEERS),
                 ("ticket", C.c_void_p)]
+
+
+class L2Cert(C.Structure):
+    """``tt_l2_cert_t``: row-norm bounds that let the cosine-ordered shortlist certify a squared-L2 top-k."""
+
+    _fields_ = [("row_norm_min", C.c_float), ("row_norm_max", C.c_float), ("eps", C.c_float)]
 
 
 class TTError(RuntimeError):

@@ -29,7 +29,7 @@ int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64
 int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists,
                   int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys, float* out_scores,
                   int64_t* out_ids, float* out_margin, cudaStream_t st, const tt_exchange_t* xh = nullptr, bool push = false,
-                  bool wait = false);
+                  bool wait = false, const tt_l2_cert_t* l2 = nullptr, const float* q_f32 = nullptr, int dim = 0);
 int launch_exchange_push(const void* rec, size_t nbytes, const tt_exchange_t* h, cudaStream_t st);
 int launch_automerge(const int64_t* ids, const float* scores, int n_q, int k, const int32_t* parent_of,
                      const int32_t* child_count, const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
@@ -154,14 +154,17 @@ int tt_rescore_topk(const void* corpus, int corpus_dtype, int64_t n_rows, int di
                     int64_t* out_ids, float* out_margin, void* ws, size_t ws_bytes, void* stream) {
     return tt_rescore_topk_push(corpus, corpus_dtype, n_rows, dim, row_stride_elems, id_base, q_f32, n_q, cand_ids, n_cand,
                                 cand_thresh, n_lists, k, score_mode, out_keys, out_scores, out_ids, out_margin, ws, ws_bytes,
-                                nullptr, stream);
+                                nullptr, nullptr, stream);
 }
 
 int tt_rescore_topk_push(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
                          int64_t id_base, const float* q_f32, int n_q, const int64_t* cand_ids, int n_cand,
                          const float* cand_thresh, int n_lists, int k, int score_mode, float* out_keys, float* out_scores,
                          int64_t* out_ids, float* out_margin, void* ws, size_t ws_bytes, const tt_exchange_t* xchg,
-                         void* stream) {
+                         const tt_l2_cert_t* l2_cert, void* stream) {
+    TT_CHECK_ARG(!l2_cert || (l2_cert->row_norm_min >= 0.f && l2_cert->row_norm_max >= l2_cert->row_norm_min &&
+                              l2_cert->eps >= 0.f),
+                 "tt_rescore_topk: bad L2 certificate bounds");
     TT_CHECK_ARG(corpus_dtype == TT_DTYPE_BF16 || corpus_dtype == TT_DTYPE_F32, "tt_rescore_topk: dtype %d", corpus_dtype);
     TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_rescore_topk: score_mode %d",
                  score_mode);
@@ -181,7 +184,7 @@ int tt_rescore_topk_push(const void* corpus, int corpus_dtype, int64_t n_rows, i
     if (rc) return rc;
     return launch_select(packed, n_cand, nullptr, nullptr, 0, 0, 0, n_q, 0, k, score_mode, cand_thresh,
                          cand_thresh ? n_lists : 0, out_keys, out_scores, out_ids, out_margin, TT_STREAM(stream), xchg,
-                         xchg != nullptr, false);
+                         xchg != nullptr, false, l2_cert, q_f32, dim);
 }
 
 int tt_exchange_push(const void* record, size_t nbytes, const tt_exchange_t* xchg, void* stream) {

@@ -115,6 +115,36 @@ struct Xchg {
     const unsigned* wait_flags;                   // local flag array for this slot
 };
 
+// Certificate inputs for TT_SCORE_CHROMA_L2_EXP: the shortlist is ordered by cosine, so a dropped row r is only
+// known to have cos(r) <= t (t = threshold + eps).  With every row norm in [nlo, nhi] that bounds its squared-L2
+// key from above:  -(|q|^2 + |c|^2 - 2 cos |q||c|)  <=  U(t),  U maximised over |c| in [nlo, nhi] (a concave
+// parabola in |c| with vertex at t|q|).  The top-k is proven exact iff its k-th key exceeds U.
+struct L2Cert {
+    const float* q;  // [n_q, dim]; NULL = no L2 certificate
+    int dim;
+    float nlo, nhi, eps;
+};
+
+__device__ __forceinline__ float l2_upper_bound(float t, double qq, float nlo, float nhi) {
+    const double qn = sqrt(qq);
+    double n = double(t) * qn;  // unconstrained maximiser of -(n^2 - 2 t qn n)
+    n = n < double(nlo) ? double(nlo) : (n > double(nhi) ? double(nhi) : n);
+    return float(-(qq + n * n - 2.0 * double(t) * qn * n));
+}
+
+// block-wide |q_b|^2 in fp64 (all threads call; result valid in thread 0)
+__device__ __forceinline__ double block_sqnorm(const float* q, int dim, double* red /* [32] shared */) {
+    double a = 0.0;
+    for (int d = threadIdx.x; d < dim; d += blockDim.x) { const double v = q[d]; a += v * v; }
+    a = warp_sum_f64(a);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    double tot = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < int(blockDim.x >> 5); ++w) tot += red[w];
+    return tot;
+}
+
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -181,10 +211,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
                                                              int n_thresh, float* __restrict__ out_keys,
                                                              float* __restrict__ out_scores,
                                                              int64_t* __restrict__ out_ids,
-                                                             float* __restrict__ out_margin, const Xchg x) {
+                                                             float* __restrict__ out_margin, const Xchg x,
+                                                             const L2Cert cert) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
     __shared__ float red[32];
+    __shared__ double red64[32];
     const int b = blockIdx.x;
     if (x.wait_world) xchg_wait(x);
     const int total = packed ? n_in : n_lists * k_in;
@@ -231,14 +263,18 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
         for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
         if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
         __syncthreads();
+        const bool l2c = mode != TT_SCORE_COSINE && cert.q != nullptr;
+        double qq = 0.0;
+        if (l2c) qq = block_sqnorm(cert.q + size_t(b) * cert.dim, cert.dim, red64);
         if (threadIdx.x == 0) {
             for (int w = 1; w < SEL_THREADS / 32; ++w) m = fmaxf(m, red[w]);
             const uint64_t ek = (k - 1 < chunk) ? s[k - 1] : 0ull;
             float margin;
             if (m == -INFINITY) margin = INFINITY;            // nothing was left out of any shortlist
-            else if (mode != TT_SCORE_COSINE) margin = -INFINITY;  // the shortlist is ordered by cosine only
             else if (!ek) margin = -INFINITY;                 // fewer than k candidates although rows were dropped
-            else margin = entry_key(ek) - m;
+            else if (mode == TT_SCORE_COSINE) margin = entry_key(ek) - m;
+            else if (l2c) margin = entry_key(ek) - l2_upper_bound(m + cert.eps, qq, cert.nlo, cert.nhi);  // > 0 proves it
+            else margin = -INFINITY;                          // cosine-ordered shortlist, no norm bounds given
             out_margin[b] = margin;
         }
     }
@@ -263,10 +299,11 @@ __global__ void __launch_bounds__(SEL_THREADS) select_small_kernel(
     const uint64_t* __restrict__ packed, int n_in, const float* __restrict__ in_keys, const int64_t* __restrict__ in_ids,
     int n_lists, int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode,
     const float* __restrict__ thresh, int n_thresh, float* __restrict__ out_keys, float* __restrict__ out_scores,
-    int64_t* __restrict__ out_ids, float* __restrict__ out_margin, const Xchg x) {
+    int64_t* __restrict__ out_ids, float* __restrict__ out_margin, const Xchg x, const L2Cert cert) {
     __shared__ uint64_t part[2][32];
     __shared__ uint64_t win[SMALL_K];
     __shared__ float red[32];
+    __shared__ double red64[32];
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (x.wait_world) xchg_wait(x);
     const int total = packed ? n_in : n_lists * k_in;
@@ -321,14 +358,18 @@ __global__ void __launch_bounds__(SEL_THREADS) select_small_kernel(
         for (int d = 16; d >= 1; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
         if (lane == 0) red[warp] = m;
         __syncthreads();
+        const bool l2c = mode != TT_SCORE_COSINE && cert.q != nullptr;
+        double qq = 0.0;
+        if (l2c) qq = block_sqnorm(cert.q + size_t(b) * cert.dim, cert.dim, red64);
         if (t == 0) {
             for (int w = 1; w < SEL_THREADS / 32; ++w) m = fmaxf(m, red[w]);
             const uint64_t ek = win[k - 1];
             float margin;
             if (m == -INFINITY) margin = INFINITY;
-            else if (mode != TT_SCORE_COSINE) margin = -INFINITY;
             else if (!ek) margin = -INFINITY;
-            else margin = entry_key(ek) - m;
+            else if (mode == TT_SCORE_COSINE) margin = entry_key(ek) - m;
+            else if (l2c) margin = entry_key(ek) - l2_upper_bound(m + cert.eps, qq, cert.nlo, cert.nhi);
+            else margin = -INFINITY;
             out_margin[b] = margin;
         }
     }
@@ -391,7 +432,14 @@ int launch_exchange_push(const void* rec, size_t nbytes, const tt_exchange_t* h,
 int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists,
                   int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys,
                   float* out_scores, int64_t* out_ids, float* out_margin, cudaStream_t st,
-                  const tt_exchange_t* xh = nullptr, bool push = false, bool wait = false) {
+                  const tt_exchange_t* xh = nullptr, bool push = false, bool wait = false,
+                  const tt_l2_cert_t* l2 = nullptr, const float* q_f32 = nullptr, int dim = 0) {
+    L2Cert cert;
+    cert.q = (l2 && q_f32) ? q_f32 : nullptr;
+    cert.dim = dim;
+    cert.nlo = l2 ? l2->row_norm_min : 0.f;
+    cert.nhi = l2 ? l2->row_norm_max : 0.f;
+    cert.eps = l2 ? l2->eps : 0.f;
     Xchg x;
     {
         int rc = fill_xchg(&x, xh, push, wait);
@@ -404,7 +452,7 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
         if (n_q == 0) return TT_OK;
         select_small_kernel<<<n_q, SEL_THREADS, 0, st>>>(packed, n_in, in_keys, in_ids, n_lists, keys_stride, ids_stride, n_q,
                                                          k_in, k, mode, thresh, n_thresh, out_keys, out_scores, out_ids,
-                                                         out_margin, x);
+                                                         out_margin, x, cert);
         TT_LAUNCH_OK("select_small_kernel");
         return TT_OK;
     }
@@ -422,7 +470,7 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
     }
     if (n_q == 0) return TT_OK;
     select_kernel<<<n_q, SEL_THREADS, smem, st>>>(packed, n_in, in_keys, in_ids, n_lists, keys_stride, ids_stride, n_q, k_in, chunk, k, mode,
-                                                  thresh, n_thresh, out_keys, out_scores, out_ids, out_margin, x);
+                                                  thresh, n_thresh, out_keys, out_scores, out_ids, out_margin, x, cert);
     TT_LAUNCH_OK("select_kernel");
     return TT_OK;
 }

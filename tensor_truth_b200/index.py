@@ -46,6 +46,7 @@ class SearchResult:
     ids: torch.Tensor       # int64   [B, k] global row ordinals, -1 padding
     margin: Optional[torch.Tensor]  # float32 [B] certificate margin (None for the exact scan)
     eps: float = 0.0        # the top-k of query b is proven exact iff margin[b] > eps
+    hi_only: bool = False   # the scan saw bf16 hi halves of the queries only (the repair ladder starts with hi+lo)
 
 
 @dataclass
@@ -106,6 +107,18 @@ class DeviceIndex:
                 c = self.corpus[lo:lo + step].float()
                 inv_norm[lo:lo + step] = (c * c).sum(dim=1).clamp_min(1e-30).rsqrt()
         self.inv_norm = inv_norm.to(self.device, torch.float32).contiguous()
+        # bounds on the stored rows' norms: what lets the cosine-ordered shortlist certify chroma_l2_exp mode
+        self.norm_lo, self.norm_hi = 0.0, 0.0
+        if self.n_rows:
+            if self.master is not None:
+                lo_v, hi_v = float("inf"), 0.0
+                for a in range(0, self.n_rows, 1 << 20):
+                    nrm = self.master[a:a + (1 << 20)].double().norm(dim=1)
+                    lo_v, hi_v = min(lo_v, float(nrm.min())), max(hi_v, float(nrm.max()))
+            else:
+                nrm = 1.0 / self.inv_norm.double()
+                lo_v, hi_v = float(nrm.min()), float(nrm.max())
+            self.norm_lo, self.norm_hi = max(0.0, lo_v * (1 - 1e-5)), hi_v * (1 + 1e-5)
         self.set_tree(tree)
         self._ws: dict = {}
         self._lock = threading.Lock()  # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420)
@@ -183,12 +196,17 @@ class DeviceIndex:
         if hi_only is None:
             hi_only = b > HI_ONLY_ABOVE
         w = out if out is not None else self._buffers(b, k)
-        if self.score_mode != SCORE_COSINE:
-            # The shortlist is ordered by cosine, which only orders squared-L2 on equal-norm rows: in chroma_l2_exp
-            # mode the exact fp64 scan answers directly (2.6x the time of the shortlist scan at 10M rows).
+        l2 = self.score_mode != SCORE_COSINE
+        if l2 and not (self.norm_lo > 0.0 and self.norm_hi <= 1.05 * self.norm_lo):
+            # chroma_l2_exp on rows of clearly unequal norm: cosine order says little about squared-L2 order, the
+            # certificate below would refuse every query -- let the exact fp64 scan answer directly.
             ex = self.search_exact(q, k, out=w)
             w["margin"].fill_(float("inf"))
             return SearchResult(ex.keys, ex.scores, ex.ids, w["margin"], 0.0)
+        eps = self.eps + (EPS_HI_ONLY if hi_only else 0.0)
+        cert = None
+        if l2:  # (near-)unit-norm rows: the cosine bound of a dropped row bounds its L2 key (tt_l2_cert_t)
+            cert = _lib.L2Cert(self.norm_lo, self.norm_hi, eps)
         L, st = self.lib, self._stream()
         n_cand = self.n_lists * self.kprime
         with self._on_device():
@@ -209,8 +227,10 @@ class DeviceIndex:
                                          self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q), b,
                                          ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), self.n_lists, k, self.score_mode,
                                          ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
-                                         ptr(w["ws"]), w["ws"].numel(), C.byref(xchg) if xchg is not None else None, st))
-        return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], self.eps + (EPS_HI_ONLY if hi_only else 0.0))
+                                         ptr(w["ws"]), w["ws"].numel(), C.byref(xchg) if xchg is not None else None,
+                                         C.byref(cert) if cert is not None else None, st))
+        # cosine: proven iff margin > eps;  L2: the bound already contains eps, proven iff margin > 0
+        return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if l2 else eps, bool(hi_only))
 
     def search_exact(self, q: torch.Tensor, k: int, out: Optional[dict] = None) -> SearchResult:
         """fp64 scoring of every row (CUDA cores): certificate-failure fallback, the chroma_l2_exp path and the
@@ -241,7 +261,7 @@ class DeviceIndex:
         r = self.search(q, k)
         bad = torch.nonzero(~(r.margin > r.eps)).flatten()  # NaN-safe
         if bad.numel():
-            self._repair(q, k, r, bad, hi_lo_first=r.eps > self.eps)
+            self._repair(q, k, r, bad, hi_lo_first=r.hi_only)
         return r
 
     def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool) -> None:
@@ -334,7 +354,7 @@ class DeviceIndex:
             rec["event"].synchronize()
             bad = np.nonzero(~(h["margin"].numpy() > r.eps))[0]
             if bad.size:  # not proven exact: re-run those queries (tighter scan, then the exact fp64 scan)
-                self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.eps > self.eps)
+                self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only)
                 if merged:
                     self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
                 rec["host"].copy_(rec["dev"], non_blocking=True)

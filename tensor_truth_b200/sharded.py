@@ -221,7 +221,7 @@ class ShardedIndex:
         r = self._local_search(q, k, keys, ids)
         bad = torch.nonzero(~(margins > r.eps)).flatten()
         if bad.numel():  # rank-local repair (writes into the send record); the exchange below is reached by every rank
-            local._repair(q, k, r, bad, hi_lo_first=r.eps > local.eps)
+            local._repair(q, k, r, bad, hi_lo_first=r.hi_only)
         pb = self.peers(b, k)
         if pb is None:
             self.plumbing.exchange(send, recv)

@@ -86,9 +86,10 @@ def test_mini_exact_scan_golden(golden_dir, tag, mode, k):
         assert (_np(r.scores) == g[f"{tag}_k{k}_scores"]).all()
 
 
-def test_l2_mode_is_answered_by_the_exact_scan(golden_dir):
-    """chroma_l2_exp mode (what ChromaVectorStore would report): the cosine-ordered shortlist proves nothing about
-    squared-L2 order on rows of unequal norm, so this mode goes straight to the exact fp64 scan."""
+def test_l2_mode_certified_through_row_norm_bounds(golden_dir, c1):
+    """chroma_l2_exp mode (what ChromaVectorStore would report).  The shortlist is ordered by cosine; with (near-)unit-norm
+    rows the cosine bound of a dropped row bounds its squared-L2 key, so the same scan certifies the L2 top-k
+    (tt_l2_cert_t).  Rows of clearly unequal norm go straight to the exact fp64 scan."""
     g = np.load(os.path.join(golden_dir, "mini_scan.npz"))
     idx = _index(g["bits"], _Tree(g).t, score_mode=1)
     r = idx.search_certified(torch.from_numpy(g["queries"]).cuda(), 10)
@@ -100,7 +101,18 @@ def test_l2_mode_is_answered_by_the_exact_scan(golden_dir):
     for b, lst in enumerate(got):
         n = int((mi[b] >= 0).sum())
         assert [o for o, _ in lst] == mi[b, :n].tolist() and [s for _, s in lst] == ms[b, :n].tolist()
-    # rows of very different norms: L2 order != cosine order
+    # C1 (100k rows > shortlist): rows are dropped, the L2 certificate must prove the result without any fallback
+    tree, bits, inv, q = c1
+    ids_o, sc_o, keys_o = cport.scan_topk(bits, q[:16], 10, 1)
+    for variant in (_lib.SCAN_TCGEN05, _lib.SCAN_SIMT):
+        idx = _index(bits, tree, score_mode=1, variant=variant)
+        assert 0.99 < idx.norm_lo <= idx.norm_hi < 1.01
+        r = idx.search(torch.from_numpy(q[:16]).cuda(), 10)
+        torch.cuda.synchronize()
+        m = _np(r.margin)
+        assert (m > 0).all() and np.isfinite(m).all(), m
+        assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all() and (_np(r.keys) == keys_o).all()
+    # rows of very different norms: L2 order != cosine order -> exact scan, no certificate attempted
     rng = np.random.default_rng(3)
     c = (rng.standard_normal((20000, 64)) * rng.uniform(0.5, 2.0, (20000, 1))).astype(np.float32)
     bits = oracle.f32_to_bf16_bits(c)
@@ -111,6 +123,16 @@ def test_l2_mode_is_answered_by_the_exact_scan(golden_dir):
     assert (ids == ids_o).all() and (scores.astype(np.float32) == sc_o).all()
     ids_c, _, _ = oracle.exact_topk(bits, q, 10, 0)
     assert (ids_c != ids_o).any()
+    # norms within 3 %: the certificate is attempted, may refuse, and the ladder still ends exact
+    c = (rng.standard_normal((30000, 128)) ).astype(np.float32)
+    c = c / np.linalg.norm(c, axis=1, keepdims=True) * rng.uniform(0.99, 1.02, (30000, 1)).astype(np.float32)
+    bits = oracle.f32_to_bf16_bits(c)
+    q = rng.standard_normal((5, 128)).astype(np.float32)
+    idx = _index(bits, None, score_mode=1)
+    r = idx.search_certified(torch.from_numpy(q).cuda(), 10)
+    torch.cuda.synchronize()
+    ids_o, sc_o, _ = oracle.exact_topk(bits, q, 10, 1)
+    assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
 
 
 # --------------------------------------------------------------------------- hand-built auto-merge cases
