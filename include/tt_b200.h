@@ -94,6 +94,30 @@ int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t 
                       void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * Stage 1 for very wide batches (hundreds to tens of thousands of concurrent queries; BASELINE config C4,
+ * the tensor-bound regime).  Same role and same output contract as tt_scan_topk_bf16 with ONE list per
+ * query (n_lists = 1), queries as bf16 hi halves only:
+ *
+ *   out_ids    int64 [n_q, kprime]   the kprime rows with the best approximate score, best first; -1 = empty
+ *   out_approx float [n_q, kprime]
+ *   out_thresh float [n_q]           every row NOT emitted has a(r) <= out_thresh[b];  -inf: nothing was
+ *                                    left out;  +inf: the query's candidate buffer overflowed (the
+ *                                    certificate of tt_rescore_topk then fails and the caller re-runs it)
+ *
+ * A GEMM-shaped tcgen05 kernel (256 x 256 output tiles per CTA pair, corpus and query tiles both TMA-
+ * streamed) visits the corpus in phases of geometrically growing size; between phases each query's
+ * candidate buffer is cut to its kprime best and the K'-th score becomes the threshold the next phase's
+ * epilogue filters with.  The score matrix never reaches HBM.
+ * kprime in {128, 256, 512}; dim % 64 == 0; ws: tt_scan_gemm_workspace_bytes(n_q, kprime) bytes
+ * (no initialisation needed; 16 * kprime * 8 B per query).
+ */
+size_t tt_scan_gemm_workspace_bytes(int n_q, int kprime);
+int tt_scan_gemm_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
+                           const float* inv_norm, const void* q_hi_bf16, int n_q, int kprime, int64_t id_base,
+                           int64_t* out_ids, float* out_approx, float* out_thresh,
+                           void* ws, size_t ws_bytes, void* stream);
+
+/*
  * Stage 2 -- exact re-score of the shortlist + exact top-k.  Together with stage 1 this is the
  * exact brute-force result the reference's (approximate, HNSW) query targets.
  *

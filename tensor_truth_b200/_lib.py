@@ -27,6 +27,8 @@ SIGNATURES = {
     "tt_prepare_queries": (_I, [_P, _I, _I, _P, _P, _P]),
     "tt_scan_workspace_bytes": (_Z, []),
     "tt_scan_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _I, _P, _P, _P, _P, _Z, _P]),
+    "tt_scan_gemm_workspace_bytes": (_Z, [_I, _I]),
+    "tt_scan_gemm_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _I, _I, _L, _P, _P, _P, _P, _Z, _P]),
     "tt_rescore_workspace_bytes": (_Z, [_I, _I]),
     "tt_rescore_topk": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "tt_scan_exact_workspace_bytes": (_Z, [_I, _I, _I]),

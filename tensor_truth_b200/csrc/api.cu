@@ -23,6 +23,11 @@ bool scan_tc2_supported(int dim, int kprime, int n_lists);
 int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
                     const void* q_hi, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
                     float* out_thresh, int n_lists, cudaStream_t st);
+size_t scan_gemm_workspace_bytes(int n_q, int kprime);
+bool scan_gemm_supported(int dim, int kprime, int n_lists);
+int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
+                     int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx, float* out_thresh,
+                     void* ws, int n_sms, cudaStream_t st);
 int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
                    const float* q, int n_q, const int64_t* cand_ids, int n_cand, int mode, uint64_t* packed,
                    cudaStream_t st);
@@ -141,6 +146,46 @@ int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t 
                                 id_base, out_ids, out_approx, out_thresh, n_lists, TT_STREAM(stream));
     set_error("tt_scan_topk_bf16: unknown variant %d", variant);
     return TT_ERR_INVALID;
+}
+
+size_t tt_scan_gemm_workspace_bytes(int n_q, int kprime) {
+    if (n_q <= 0 || kprime <= 0) return 0;
+    return scan_gemm_workspace_bytes(n_q, kprime);
+}
+
+int tt_scan_gemm_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
+                           const float* inv_norm, const void* q_hi_bf16, int n_q, int kprime, int64_t id_base,
+                           int64_t* out_ids, float* out_approx, float* out_thresh, void* ws, size_t ws_bytes,
+                           void* stream) {
+    TT_CHECK_ARG(n_rows >= 0 && n_q >= 0, "tt_scan_gemm_topk_bf16: n_rows=%lld n_q=%d", (long long)n_rows, n_q);
+    TT_CHECK_ARG(dim > 0 && dim % 64 == 0, "tt_scan_gemm_topk_bf16: dim=%d must be a positive multiple of 64", dim);
+    TT_CHECK_ARG(row_stride_elems >= dim && row_stride_elems % 8 == 0, "tt_scan_gemm_topk_bf16: row stride %lld",
+                 (long long)row_stride_elems);
+    TT_CHECK_ARG(kprime == 128 || kprime == 256 || kprime == 512, "tt_scan_gemm_topk_bf16: kprime=%d not in {128,256,512}",
+                 kprime);
+    TT_CHECK_ARG(id_base >= 0 && id_base + n_rows <= (int64_t(1) << 32) && n_rows < (int64_t(1) << 31) * 256,
+                 "tt_scan_gemm_topk_bf16: ids must stay below 2^32");
+    if (n_q == 0) return TT_OK;
+    TT_CHECK_ARG(q_hi_bf16 && out_ids && out_approx && out_thresh && (n_rows == 0 || corpus_bf16),
+                 "tt_scan_gemm_topk_bf16: null pointer");
+    TT_CHECK_ARG((reinterpret_cast<uintptr_t>(corpus_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_hi_bf16) & 15) == 0,
+                 "tt_scan_gemm_topk_bf16: corpus and queries must be 16-byte aligned");
+    const int n_sms = sm_count(current_device());
+    if (n_sms <= 0) {
+        set_error("tt_scan_gemm_topk_bf16: no CUDA device");
+        return TT_ERR_CUDA;
+    }
+    if (!scan_gemm_supported(dim, kprime, n_sms)) {
+        set_error("tt_scan_gemm_topk_bf16: dim=%d kprime=%d unsupported on this device", dim, kprime);
+        return TT_ERR_UNSUPPORTED;
+    }
+    const size_t need = tt_scan_gemm_workspace_bytes(n_q, kprime);
+    if (!ws || ws_bytes < need) {
+        set_error("tt_scan_gemm_topk_bf16: workspace %zu < %zu bytes", ws_bytes, need);
+        return TT_ERR_WORKSPACE;
+    }
+    return scan_gemm_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, n_q, kprime, id_base, out_ids,
+                            out_approx, out_thresh, ws, n_sms, TT_STREAM(stream));
 }
 
 size_t tt_rescore_workspace_bytes(int n_q, int n_cand) {

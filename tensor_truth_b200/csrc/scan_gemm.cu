@@ -1,0 +1,367 @@
+// Stage 1 for very wide query batches (hundreds to tens of thousands of concurrent queries): the
+// tensor-bound regime.  A GEMM-shaped kernel -- corpus AND query tiles both streamed through the TMA ring,
+// 256 x 256 output tiles per CTA pair (tcgen05.mma cta_group::2, M = 256, N = 256, accumulators double-buffered
+// in all 512 TMEM columns) -- whose epilogue never writes the score matrix: every accumulator element is
+// compared with its query's running threshold tau[q] and only the survivors are appended to that query's
+// candidate buffer in HBM.
+//
+// The thresholds come from the data itself.  The corpus is visited in PHASES over a pseudo-random permutation
+// of its 256-row super-tiles: phase 0 is a small sample scanned with tau = -inf (everything is kept), after each
+// phase `cut_kernel` sorts every query's buffer, keeps its K' best and sets tau[q] to the K'-th approximate score
+// seen so far.  Each phase visits `growth` times the rows seen before it, so it appends about growth x K'
+// candidates per query and the whole scan writes O(K' log(n_rows)) entries per query instead of n_rows.
+// A row that is dropped anywhere has a(r) <= tau at that moment <= the final K'-th score, which is the
+// `out_thresh` contract of tt_scan_topk_bf16 with a single list per query -- stage 2 (rescore.cu) and the
+// certificate are unchanged.  A query whose buffer overflows reports thresh = +inf (certificate fails, the caller's
+// repair ladder answers it).
+//
+// Queries travel as bf16 hi halves (one MMA column per query).
+//
+// Replaces the vector-store query behind `index.as_retriever(similarity_top_k=k)` at
+// /root/reference/src/tensortruth/rag_engine.py:639 for a large batch of concurrent queries (BASELINE config C4).
+#include "tc_ptx.cuh"
+
+namespace tt {
+namespace tc3 {
+
+using namespace tc;
+
+constexpr int NQB = 256;                       // query columns per output tile (MMA N)
+constexpr int NH = NQB / 2;                    // query rows (B operand) held by each CTA of the pair
+constexpr int STAGE_A = CHUNK_BYTES;           // 128 corpus rows x 64 columns
+constexpr int STAGE_B = NH * 128;              // 128 query rows x 64 columns
+constexpr int STAGE_BYTES = STAGE_A + STAGE_B; // 32 KB
+constexpr int EPI3 = 256;                      // 8 epilogue warps
+constexpr int THREADS3 = EPI3 + 64;
+constexpr int TMEM_COLS = 2 * NQB;
+
+struct Params {
+    const float* inv_norm;
+    int64_t n_rows;
+    int n_super;          // 256-row super-tiles in the corpus
+    int n_chunks;         // dim / 64
+    int stages;
+    int n_qb;             // 256-query blocks
+    int i0, i1;           // this phase: permuted super-tile indices [i0, i1)
+    uint32_t perm_mul;    // super = (i * perm_mul) % n_super, gcd(perm_mul, n_super) == 1
+    const float* tau;     // [n_qb * 256] running thresholds (+inf in the padding columns)
+    unsigned long long* buf;  // [n_q, cap] packed (approx key, local row) entries
+    int* cnt;             // [n_qb * 256] entries appended so far (may exceed cap: overflow)
+    int cap;
+};
+
+// Rare path, out of line: append (score, row) to query q's buffer.
+static __device__ __noinline__ void append_candidate(unsigned long long* buf, int* cnt, int cap, int q, float s, uint32_t row) {
+    const int slot = atomicAdd(cnt + q, 1);
+    if (slot < cap) buf[size_t(q) * cap + slot] = pack_entry(s, row);
+}
+
+// Dynamic shared memory of each CTA (base rounded up to 1024 B):
+//   [ ring: stages x (A 16 KB | B 16 KB) ][ tau: 2 x 256 f32 ][ barriers: full[stages] (CTA 0), empty[stages],
+//     tmem_full[2], tmem_empty[2] (CTA 0) ][ tmem base ]
+// Ten warps: 0-7 epilogue (warps w and w+4 share the TMEM lane quarter w%4 and split the 256 query columns in
+// halves), 8 TMA producer, 9 TMEM alloc + MMA issue (leader CTA).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS3, 1)
+scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_q, const Params p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+
+    unsigned char* ring = smem;
+    float* tau_s = reinterpret_cast<float*>(ring + size_t(p.stages) * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tau_s + 2 * NQB);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + p.stages;
+    uint64_t* tmem_full = bars + 2 * p.stages;
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = int(blockIdx.x) >> 1, n_clusters = int(gridDim.x) >> 1;
+    const int64_t n_work = int64_t(p.i1 - p.i0) * p.n_qb;  // (super-tile, query block) pairs, query block fastest
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(full_bar + s), 2);   // one arrive per CTA's producer; the bytes of both land here (CTA 0)
+            mbar_init(smem_u32(empty_bar + s), 1);  // multicast tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(tmem_full + a), 1);
+            mbar_init(smem_u32(tmem_empty + a), 2 * (EPI3 / 32));  // one lane per epilogue warp of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
+                     "r"(uint32_t(TMEM_COLS))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 8) {
+        // ===================================================== TMA producer (both CTAs: own corpus rows + own query half)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t w = cluster_id; w < n_work; w += n_clusters) {
+                const int qb = int(w % p.n_qb);
+                const int super = int((uint64_t(p.i0 + int(w / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
+                const int row0 = super * 256 + int(rank) * TILE_ROWS;
+                const int qrow0 = qb * NQB + int(rank) * NH;
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
+                    const uint32_t fb = mapa(smem_u32(full_bar + stage), 0);
+                    if (rank == 0) mbar_expect_tx(smem_u32(full_bar + stage), 2 * STAGE_BYTES);
+                    else mbar_arrive_cluster(fb);
+                    const uint32_t dst = smem_u32(ring + size_t(stage) * STAGE_BYTES);
+                    tma_load_3d_pair(dst, &map_c, 0, row0, c, fb, POLICY_EVICT_NORMAL);  // re-read from L2 by every query block
+                    tma_load_3d_pair(dst + STAGE_A, &map_q, 0, qrow0, c, fb, POLICY_EVICT_LAST);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================================================== MMA issuer: one thread of the leader CTA
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16_m256(NQB);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int64_t w = cluster_id; w < n_work; w += n_clusters, ++it) {
+                const int a = it & 1;
+                mbar_wait(smem_u32(tmem_empty + a), (uint32_t(it >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(a * NQB);
+                for (int c = 0; c < p.n_chunks; ++c) {
+                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    tcgen05_fence_after();
+                    const uint32_t a_base = smem_u32(ring + size_t(stage) * STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < CHUNK_COLS / 16; ++k)
+                        umma_bf16_pair(d_tmem, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(a_base + STAGE_A + k * 32),
+                                       idesc, uint32_t((c | k) != 0));
+                    umma_commit_pair(smem_u32(empty_bar + stage));  // frees this ring slot in both CTAs
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_pair(smem_u32(tmem_full + a));  // both CTAs' accumulator halves are complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================== epilogue: thread = (corpus row, 128 of the 256 query columns)
+        const int quarter = warp & 3, half = warp >> 2;
+        const uint32_t te0 = mapa(smem_u32(tmem_empty), 0), te1 = mapa(smem_u32(tmem_empty + 1), 0);
+        int it = 0;
+        for (int64_t w = cluster_id; w < n_work; w += n_clusters, ++it) {
+            const int a = it & 1;
+            const int qb = int(w % p.n_qb);
+            const int super = int((uint64_t(p.i0 + int(w / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
+            const int64_t row = int64_t(super) * 256 + int64_t(rank) * TILE_ROWS + quarter * 32 + lane;
+            const bool row_ok = row < p.n_rows;
+            float inv = 1.f;
+            if (p.inv_norm && row_ok) inv = __ldg(p.inv_norm + row);
+
+            // this tile's thresholds (double-buffered by `a`: one barrier per tile keeps readers and writers apart)
+            float* th = tau_s + a * NQB;
+            th[threadIdx.x] = __ldcg(p.tau + size_t(qb) * NQB + threadIdx.x);
+            epi_bar_sync<EPI3>();
+
+            mbar_wait(smem_u32(tmem_full + a), uint32_t(it >> 1) & 1u);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(a * NQB + half * (NQB / 2));
+            const uint32_t th_addr = smem_u32(th + half * (NQB / 2));
+#pragma unroll 1
+            for (int c32 = 0; c32 < NQB / 2; c32 += 32) {
+                float v[32];
+                tmem_ld_x32(taddr + c32, v);
+                tmem_ld_wait();
+                // fast filter: does any of the 32 columns beat its threshold?  fma(v, inv, -tau) > 0 is implied by
+                // the exact test (v * inv rounded) > tau used below, so nothing is missed.
+                float m = -INFINITY;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 t4 = lds_f4(th_addr + (c32 + j4 * 4) * 4);
+                    m = fmaxf(m, fmaf(v[j4 * 4 + 0], inv, -t4.x));
+                    m = fmaxf(m, fmaf(v[j4 * 4 + 1], inv, -t4.y));
+                    m = fmaxf(m, fmaf(v[j4 * 4 + 2], inv, -t4.z));
+                    m = fmaxf(m, fmaf(v[j4 * 4 + 3], inv, -t4.w));
+                }
+                if (__any_sync(0xffffffffu, row_ok && m > 0.f)) {
+                    const int q0 = qb * NQB + half * (NQB / 2) + c32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float s = v[j] * inv;
+                        if (row_ok && s > th[half * (NQB / 2) + c32 + j]) append_candidate(p.buf, p.cnt, p.cap, q0 + j, s, uint32_t(row));
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(a ? te1 : te0);  // this warp is done with the accumulator (leader's barrier)
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // nobody frees TMEM or exits while the peer may still signal / read
+    if (warp == 9) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS))
+                     : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ per-query cut between phases
+__global__ void gemm_init_kernel(int* cnt, float* tau, int* ovf, int n_q, int n_pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) {
+        cnt[i] = 0;
+        ovf[i] = 0;
+        tau[i] = i < n_q ? -INFINITY : INFINITY;  // padding columns never pass
+    }
+}
+
+// One block per query: sort the buffer (key desc, id asc), keep the K' best at its front, tau := K'-th key.
+// final: also emit the shortlist in the stage-1 output format (one list per query).
+constexpr int CUT_THREADS = 512;
+__global__ void __launch_bounds__(CUT_THREADS)
+gemm_cut_kernel(unsigned long long* buf, int* cnt, float* tau, int* ovf, int cap, int kp, int final_pass, int64_t id_base,
+                int64_t* out_ids, float* out_approx, float* out_thresh) {
+    extern __shared__ uint64_t sort_s[];
+    const int q = blockIdx.x;
+    const int raw = cnt[q];
+    const int n = min(raw, cap);
+    unsigned long long* B = buf + size_t(q) * cap;
+    const bool over = raw > cap || ovf[q] != 0;
+    if (n > kp || final_pass) {
+        int n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (int i = threadIdx.x; i < n2; i += CUT_THREADS) sort_s[i] = i < n ? B[i] : 0ull;
+        __syncthreads();
+        if (n2 > 1) block_bitonic_sort_desc(sort_s, n2);
+        const int keep = min(n, kp);
+        if (n > kp)
+            for (int i = threadIdx.x; i < keep; i += CUT_THREADS) B[i] = sort_s[i];
+        if (final_pass) {
+            for (int i = threadIdx.x; i < kp; i += CUT_THREADS) {
+                const uint64_t e = i < keep ? sort_s[i] : 0ull;
+                out_ids[size_t(q) * kp + i] = e ? int64_t(id_base + entry_id(e)) : int64_t(-1);
+                out_approx[size_t(q) * kp + i] = e ? entry_key(e) : -INFINITY;
+            }
+        }
+        if (threadIdx.x == 0) {
+            const float t = n > kp ? entry_key(sort_s[kp - 1]) : tau[q];  // n <= kp: nothing dropped by this cut
+            if (n > kp) {
+                cnt[q] = kp;
+                tau[q] = t;
+            }
+            if (final_pass) out_thresh[q] = over ? INFINITY : t;
+        }
+    }
+    if (threadIdx.x == 0 && over) ovf[q] = 1;
+}
+
+static uint32_t pick_perm_mul(uint32_t n) {
+    if (n <= 2) return 1;
+    uint32_t m = uint32_t(double(n) * 0.6180339887);
+    if (m < 1) m = 1;
+    auto gcd = [](uint32_t a, uint32_t b) { while (b) { uint32_t t = a % b; a = b; b = t; } return a; };
+    while (gcd(m, n) != 1) ++m;
+    return m % n ? m % n : 1;
+}
+
+}  // namespace tc3
+
+size_t scan_gemm_workspace_bytes(int n_q, int kprime) {
+    const size_t n_pad = size_t((n_q + tc3::NQB - 1) / tc3::NQB) * tc3::NQB;
+    return 3 * n_pad * 4 + size_t(n_q) * size_t(16 * kprime) * 8;
+}
+
+bool scan_gemm_supported(int dim, int kprime, int n_lists) {
+    return n_lists >= 2 && dim % 64 == 0 && dim >= 64 && (kprime == 128 || kprime == 256 || kprime == 512);
+}
+
+int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
+                     int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx, float* out_thresh,
+                     void* ws, int n_sms, cudaStream_t st) {
+    using namespace tc3;
+    const int n_qb = (n_q + NQB - 1) / NQB;
+    const int n_pad = n_qb * NQB;
+    const int cap = 16 * kprime;
+    int* cnt = reinterpret_cast<int*>(ws);
+    float* tau = reinterpret_cast<float*>(cnt + n_pad);
+    int* ovf = reinterpret_cast<int*>(tau + n_pad);
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(ovf + n_pad);
+
+    gemm_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(cnt, tau, ovf, n_q, n_pad);
+    TT_LAUNCH_OK("gemm_init_kernel");
+
+    int stages = (tc::SMEM_LIMIT - 1024 - 2 * NQB * 4 - 256) / (STAGE_BYTES + 16);
+    if (stages > 8) stages = 8;
+    if (const char* e = getenv("TT_GEMM_STAGES")) {
+        const int want = atoi(e);
+        if (want >= 2 && want < stages) stages = want;
+    }
+    const size_t smem = 1024 + size_t(stages) * STAGE_BYTES + 2 * NQB * 4 + (2 * size_t(stages) + 4) * 8 + 16;
+
+    Params p;
+    p.inv_norm = inv_norm;
+    p.n_rows = n_rows;
+    p.n_super = int((n_rows + 255) / 256);
+    p.n_chunks = dim / tc::CHUNK_COLS;
+    p.stages = stages;
+    p.n_qb = n_qb;
+    p.perm_mul = pick_perm_mul(uint32_t(p.n_super));
+    p.tau = tau;
+    p.buf = buf;
+    p.cnt = cnt;
+    p.cap = cap;
+
+    CUtensorMap map_c, map_q;
+    if (n_rows > 0) {
+        int rc = tc::make_map(&map_c, corpus, n_rows, dim, stride, tc::TILE_ROWS, 1);
+        if (rc) return rc;
+        rc = tc::make_map(&map_q, q_hi, n_q, dim, dim, NH, 1);
+        if (rc) return rc;
+    }
+    TT_CUDA_OK(cudaFuncSetAttribute(scan_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
+    TT_CUDA_OK(cudaFuncSetAttribute(gemm_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
+
+    // phases: the first visits ~4 K' rows, each later one `growth` times the rows visited before it
+    int growth = 4;
+    if (const char* e = getenv("TT_GEMM_GROWTH")) {
+        const int g = atoi(e);
+        if (g >= 1 && g <= 64) growth = g;
+    }
+    const int grid = n_sms & ~1;
+    int seen = 0;
+    int next = (4 * kprime + 255) / 256;
+    bool done = p.n_super == 0;
+    if (done) {
+        gemm_cut_kernel<<<n_q, CUT_THREADS, cap * 8, st>>>(buf, cnt, tau, ovf, cap, kprime, 1, id_base, out_ids, out_approx,
+                                                           out_thresh);
+        TT_LAUNCH_OK("gemm_cut_kernel");
+    }
+    while (!done) {
+        int upto = seen + next;
+        if (upto >= p.n_super || p.n_super - upto < next / 2) upto = p.n_super;  // fold a short tail into this phase
+        p.i0 = seen;
+        p.i1 = upto;
+        scan_gemm_kernel<<<grid, THREADS3, smem, st>>>(map_c, map_q, p);
+        TT_LAUNCH_OK("scan_gemm_kernel");
+        done = upto == p.n_super;
+        gemm_cut_kernel<<<n_q, CUT_THREADS, cap * 8, st>>>(buf, cnt, tau, ovf, cap, kprime, done ? 1 : 0, id_base, out_ids,
+                                                           out_approx, out_thresh);
+        TT_LAUNCH_OK("gemm_cut_kernel");
+        seen = upto;
+        next = seen * growth;
+    }
+    return TT_OK;
+}
+
+}  // namespace tt

@@ -23,56 +23,6 @@ namespace tc2 {
 
 using namespace tc;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-// Remote arrive with the default (.release.cta) semantics: a cluster-scope release would put a GPU-wide MEMBAR on
-// the producer's / epilogue's critical path.  No generic-proxy data is published through these barriers (TMA bytes
-// are tracked by complete_tx, TMEM reads are ordered by tcgen05.wait::ld + tcgen05.fence).
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load whose completion is signalled on a barrier that may live in the peer CTA (cta_group::2)
-__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
-                                                 uint32_t bar_cluster_addr, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%2, %3, %4}], [%5], %6;"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster_addr), "l"(policy)
-        : "memory");
-}
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_m256(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(256 >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrive on the barrier at the same shared-memory offset in BOTH CTAs once the MMAs issued so far have retired
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-    asm volatile(
-        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-        ::"r"(bar), "h"(uint16_t(3))
-        : "memory");
-}
-
 struct Params {
     const float* inv_norm;
     int64_t n_rows;

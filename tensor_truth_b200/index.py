@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import os
 import threading
 from dataclasses import dataclass
 from typing import Optional
@@ -34,6 +35,13 @@ EPS_F32_CORPUS = 4.2e-3    # fp32 master scanned through a bf16 shadow: + 2^-8 c
 EPS_HI_ONLY = 3.95e-3      # added when the query travels as bf16 hi only (|q - bf16(q)| <= 2^-8 |q|)
 HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first (64 queries per corpus pass)
 MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist workspace: 148 * K' * 12 B per query)
+GEMM_ABOVE = 256           # hi-only batches at least this large take the GEMM-shaped stage 1 (scan_gemm.cu): one list per query
+GEMM_SLICE = 4096          # queries per GEMM-shaped corpus pass (candidate buffers: 16 K' * 8 B per query)
+
+
+def gemm_kprime(k: int) -> int:
+    """Shortlist length per query of the GEMM-shaped stage 1 (a single global list, so it is much deeper than k)."""
+    return 128 if k <= 16 else 256 if k <= 64 else 512
 
 
 _NULL_CTX = contextlib.nullcontext()
@@ -140,10 +148,34 @@ class DeviceIndex:
         self.n_nodes = tree.n_nodes
 
     # ------------------------------------------------------------------ workspaces
-    def _buffers(self, b: int, k: int, slot: int = 0):
+    def _use_gemm(self, b: int, hi_only: bool = True) -> bool:
+        """Wide hi-only batches: the tensor-bound regime, served by the GEMM-shaped stage 1."""
+        return (hi_only and b >= GEMM_ABOVE and self.variant in (SCAN_AUTO, _lib.SCAN_TCGEN05) and self.dim % 64 == 0
+                and self.n_rows > 0 and not os.environ.get("TT_NO_GEMM"))
+
+    def _buffers(self, b: int, k: int, slot: int = 0, hi_only: Optional[bool] = None):
         """Workspace set for a (batch, k) shape; ``slot`` separates sets used concurrently on different streams."""
-        key = (b, k, slot)
+        gemm = self._use_gemm(b, b > HI_ONLY_ABOVE if hi_only is None else hi_only)
+        key = (b, k, slot, gemm)
         w = self._ws.get(key)
+        if w is None and gemm:
+            dev, kp = self.device, gemm_kprime(k)
+            sl = min(b, int(os.environ.get("TT_GEMM_SLICE", GEMM_SLICE)))
+            w = {
+                "gemm": True, "kprime": kp, "slice": sl,
+                "q_hi": torch.empty((b, self.dim), dtype=torch.bfloat16, device=dev),
+                "q_lo": None,
+                "cand_ids": torch.empty((b, kp), dtype=torch.int64, device=dev),
+                "cand_approx": torch.empty((b, kp), dtype=torch.float32, device=dev),
+                "cand_thresh": torch.empty((b, 1), dtype=torch.float32, device=dev),
+                "ws": torch.empty(max(1, int(self.lib.tt_rescore_workspace_bytes(b, kp))), dtype=torch.uint8, device=dev),
+                "gemm_ws": torch.empty(int(self.lib.tt_scan_gemm_workspace_bytes(sl, kp)), dtype=torch.uint8, device=dev),
+                "keys": torch.empty((b, k), dtype=torch.float32, device=dev),
+                "scores": torch.empty((b, k), dtype=torch.float32, device=dev),
+                "ids": torch.empty((b, k), dtype=torch.int64, device=dev),
+                "margin": torch.empty((b,), dtype=torch.float32, device=dev),
+            }
+            self._ws[key] = w
         if w is None:
             dev, n_cand = self.device, self.n_lists * self.kprime
             w = {
@@ -195,7 +227,7 @@ class DeviceIndex:
         b = int(q.shape[0])
         if hi_only is None:
             hi_only = b > HI_ONLY_ABOVE
-        w = out if out is not None else self._buffers(b, k)
+        w = out if out is not None else self._buffers(b, k, hi_only=hi_only)
         l2 = self.score_mode != SCORE_COSINE
         if l2 and not (self.norm_lo > 0.0 and self.norm_hi <= 1.05 * self.norm_lo):
             # chroma_l2_exp on rows of clearly unequal norm: cosine order says little about squared-L2 order, the
@@ -208,24 +240,33 @@ class DeviceIndex:
         if l2:  # (near-)unit-norm rows: the cosine bound of a dropped row bounds its L2 key (tt_l2_cert_t)
             cert = _lib.L2Cert(self.norm_lo, self.norm_hi, eps)
         L, st = self.lib, self._stream()
-        n_cand = self.n_lists * self.kprime
+        gemm = bool(w.get("gemm")) and hi_only
+        n_cand, n_lists = (w["kprime"], 1) if gemm else (self.n_lists * self.kprime, self.n_lists)
         with self._on_device():
             check(L.tt_prepare_queries(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), st))
             if self.scan_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus), ptr(self.inv_norm),
-                                      ptr(w["q_hi"]), None if hi_only else ptr(w["q_lo"]), b, self.kprime, self.id_base,
-                                      self.variant,
-                                      ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]),
-                                      ptr(w["scan_ws"]), w["scan_ws"].numel(), st))
+            if gemm:  # the tensor-bound regime: GEMM-shaped scan, one shortlist per query, GEMM_SLICE queries per corpus pass
+                for a in range(0, b, w["slice"]):
+                    n = min(w["slice"], b - a)
+                    check(L.tt_scan_gemm_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus),
+                                                   ptr(self.inv_norm), ptr(w["q_hi"][a:]), n, n_cand, self.id_base,
+                                                   ptr(w["cand_ids"][a:]), ptr(w["cand_approx"][a:]), ptr(w["cand_thresh"][a:]),
+                                                   ptr(w["gemm_ws"]), w["gemm_ws"].numel(), st))
+            else:
+                check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus), ptr(self.inv_norm),
+                                          ptr(w["q_hi"]), None if hi_only else ptr(w["q_lo"]), b, self.kprime, self.id_base,
+                                          self.variant,
+                                          ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]),
+                                          ptr(w["scan_ws"]), w["scan_ws"].numel(), st))
             if self.scan_events is not None:
                 e1.record()
                 self.scan_events.append((e0, e1))
             src = self.master if self.master is not None else self.corpus
             check(L.tt_rescore_topk_push(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
                                          self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q), b,
-                                         ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), self.n_lists, k, self.score_mode,
+                                         ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), n_lists, k, self.score_mode,
                                          ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
                                          ptr(w["ws"]), w["ws"].numel(), C.byref(xchg) if xchg is not None else None,
                                          C.byref(cert) if cert is not None else None, st))
@@ -268,7 +309,7 @@ class DeviceIndex:
         """Queries whose certificate failed: (a hi-only batch first gets the tighter hi+lo scan,) then the exact fp64 scan."""
         if hi_lo_first:
             sub = q.index_select(0, bad)
-            r2 = self.search(sub, k, out=dict(self._buffers(int(sub.shape[0]), k, slot=-1)), hi_only=False)
+            r2 = self.search(sub, k, out=dict(self._buffers(int(sub.shape[0]), k, slot=-1, hi_only=False)), hi_only=False)
             ok = r2.margin > r2.eps
             good = bad[ok]
             if good.numel():
