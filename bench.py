@@ -50,6 +50,16 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_tensor_peak():
+    """Dense bf16 TFLOP/s for a kernel timed inside a long step (the sustained figure)."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md ~1.4 PFLOP/s sustained)"
+
+
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
     """Samples SM clocks and throttle reasons of one GPU with NVML while the timed region runs."""
@@ -208,30 +218,31 @@ def run_b200(args):
 
     from tensor_truth_b200.index import MergeResult
 
-    def timed(batch: int, steps: int, warm: int, sample_clocks: bool, depth: int):
+    def timed(batch: int, steps: int, warm: int, sample_clocks: bool, depth: int, k: int = TOP_K, pool=None):
         """K steps of the device pipeline.  depth = 1: strictly serial, with CUDA events around every stage-1
         launch (the roofline numbers).  depth = 2: steps alternate between two streams, so step i+1's scan
         overlaps step i's re-score / select / (all-gather, merge) / auto-merge -- the throughput configuration."""
         margins = torch.full((steps + warm, batch), float("inf"), dtype=torch.float32, device=device)
-        n_pool = QUERY_POOL // batch if batch <= QUERY_POOL else 1
+        pool = queries if pool is None else pool
+        n_pool = max(1, int(pool.shape[0]) // batch)
         streams = [torch.cuda.Stream(device) for _ in range(depth)]
-        bufs = [idx._buffers(batch, TOP_K, slot=s) for s in range(depth)]
-        mouts = [MergeResult(torch.empty((batch, 2 * TOP_K), dtype=torch.int64, device=device),
-                             torch.empty((batch, 2 * TOP_K), dtype=torch.float64, device=device),
+        bufs = [idx._buffers(batch, k, slot=s) for s in range(depth)]
+        mouts = [MergeResult(torch.empty((batch, 2 * k), dtype=torch.int64, device=device),
+                             torch.empty((batch, 2 * k), dtype=torch.float64, device=device),
                              torch.empty((batch,), dtype=torch.int32, device=device)) for _ in range(depth)]
         eps = [idx.eps]
 
         def one(i):
             s = i % depth
             with torch.cuda.stream(streams[s]):
-                q = queries[(i % n_pool) * batch:(i % n_pool) * batch + batch]
+                q = pool[(i % n_pool) * batch:(i % n_pool) * batch + batch]
                 if sharded is None:
                     w = dict(bufs[s])
                     w["margin"] = margins[i]
-                    r = idx.search(q, TOP_K, out=w)
+                    r = idx.search(q, k, out=w)
                     eps[0] = r.eps
                     return idx.automerge(r.ids, r.scores, out=mouts[s])
-                scores, ids = sharded.search(q, TOP_K, margins=margins[i], slot=s)
+                scores, ids = sharded.search(q, k, margins=margins[i], slot=s)
                 eps[0] = sharded.last.eps
                 return idx.automerge(ids, scores, out=mouts[s])
 
@@ -290,6 +301,34 @@ def run_b200(args):
     ser64 = timed(64, steps64, 3, False, depth=1)
     pip64 = timed(64, steps64, 3, False, depth=2)
     value64 = steps64 * 64 / (pip64["ms"] / 1e3)
+
+    # ---- wide batch (BASELINE configs[3] shape: 16k concurrent queries, top-100): the tensor-bound regime, served by
+    #      the GEMM-shaped stage 1 (scan_gemm.cu).  Roofline: dense bf16 tensor throughput.
+    wide = None
+    if args.wide_batch > 0:
+        bw, kw = args.wide_batch, args.wide_k
+        qw = make_queries(sc, corpus, lo, hi, bw, world).to(device)
+        tpeak, tpeak_src = measured_tensor_peak()
+        serw = timed(bw, args.wide_steps, 1, False, depth=1, k=kw, pool=qw)
+        flops = 2.0 * bw * float(hi - lo) * DIM
+        tfl = flops / (serw["scan_ms"] / 1e3) / 1e12
+        # spot check: the first 4 queries against the exact fp64 scan of the local shard
+        rw = idx.search(qw, kw, out=dict(idx._buffers(bw, kw, slot=0)))
+        exw = idx.search_exact(qw[:4], kw)
+        wide_ok = bool(torch.equal(rw.ids[:4], exw.ids) and torch.equal(rw.scores[:4], exw.scores))
+        wide = {"value": args.wide_steps * bw / (serw["ms"] / 1e3), "unit": UNIT, "batch": bw, "k": kw,
+                "ms_per_step": serw["ms"] / args.wide_steps, "steps": args.wide_steps,
+                "stage1_ms_per_step": serw["scan_ms"], "gemm_path": bool(idx._use_gemm(bw)),
+                "roofline": {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
+                             "traffic": None, "kernel": "scan_gemm_kernel (+ gemm_cut_kernel between phases)",
+                             "flops_per_step": flops, "peak_source": tpeak_src,
+                             "measured_in": "CUDA events around the whole stage 1 of each step (all phases and cuts)"},
+                "certificate_failures": serw["bad"], "min_margin": serw["min_margin"], "eps": serw["eps"],
+                "parity_vs_gpu_exact_scan_local_shard": wide_ok,
+                "mode": "hi-only bf16 queries, 256 x 256 tcgen05 pair tiles, data-driven thresholds in phases"}
+        del qw, rw, exw
+        idx._ws = {kk: v for kk, v in idx._ws.items() if not (isinstance(kk, tuple) and kk and kk[0] == bw)}
+        torch.cuda.empty_cache()
 
     # ---- parity spot check inside the bench: the timed path vs the on-GPU exact fp64 scan of the same shard(s)
     qs = queries[:4]
@@ -373,6 +412,7 @@ def run_b200(args):
                         "hbm_frac": local_bytes / (ser64["scan_ms"] / 1e3) / 1e9 / peak,
                         "certificate_failures": ser64["bad"] + pip64["bad"], "min_margin": pip64["min_margin"],
                         "eps": pip64["eps"], "mode": "hi-only bf16 queries, 64 per corpus pass"},
+            "wide": wide,
             "certificate_failures": bad1, "min_margin": pip1["min_margin"], "eps": pip1["eps"],
             "exchange": (sharded.transport + (" (fused into the select / merge kernels over peer memory)" if sharded.transport == "peer" else " all-gather")) if sharded is not None else None,
             "parity_vs_gpu_exact_scan": parity_ok,
@@ -442,6 +482,9 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_048_576)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--wide-batch", type=int, default=16384, help="queries per step of the wide-batch (C4-shaped) section; 0 = skip")
+    ap.add_argument("--wide-k", type=int, default=100)
+    ap.add_argument("--wide-steps", type=int, default=2)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

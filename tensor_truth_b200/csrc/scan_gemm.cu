@@ -50,15 +50,45 @@ struct Params {
     int cap;
 };
 
-// Rare path, out of line: append (score, row) to query q's buffer.
-static __device__ __noinline__ void append_candidate(unsigned long long* buf, int* cnt, int cap, int q, float s, uint32_t row) {
-    const int slot = atomicAdd(cnt + q, 1);
-    if (slot < cap) buf[size_t(q) * cap + slot] = pack_entry(s, row);
+constexpr int STG_CAP = 64;  // staged survivors per epilogue warp (16 B each)
+
+// v[j] for a warp-uniform j: a select tree instead of dynamic register indexing
+__device__ __forceinline__ float pick32(const float (&v)[32], int j) {
+    float a[16], b[8], c[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 16) ? v[16 + i] : v[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 8) ? a[8 + i] : a[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[4 + i] : b[i];
+    const float d0 = (j & 2) ? c[2] : c[0], d1 = (j & 2) ? c[3] : c[1];
+    return (j & 1) ? d1 : d0;
+}
+
+// Append the n staged (entry, query) records of this warp to their queries' buffers in HBM.  All 32 lanes' atomics
+// are in flight together (one round trip per 32 survivors instead of one each); lanes appending to the same query
+// share one atomic.  Out of line: the hot loop only pays for it when a stage fills up.
+static __device__ __noinline__ void flush_staged(const uint4* stg, int n, unsigned long long* buf, int* cnt, int cap) {
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < n; base += 32) {
+        const bool active = base + lane < n;
+        uint4 x = make_uint4(0u, 0u, 0u, 0u);
+        if (active) x = stg[base + lane];
+        const int q = active ? int(x.z) : -1 - lane;
+        const uint32_t peers = __match_any_sync(0xffffffffu, q);
+        const int leader = __ffs(peers) - 1;
+        int slot0 = 0;
+        if (active && lane == leader) slot0 = atomicAdd(cnt + q, __popc(peers));
+        slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+        const int slot = slot0 + __popc(peers & ((1u << lane) - 1u));
+        if (active && slot < cap) buf[size_t(q) * cap + slot] = (uint64_t(x.y) << 32) | x.x;
+    }
+    __syncwarp();
 }
 
 // Dynamic shared memory of each CTA (base rounded up to 1024 B):
-//   [ ring: stages x (A 16 KB | B 16 KB) ][ tau: 2 x 256 f32 ][ barriers: full[stages] (CTA 0), empty[stages],
-//     tmem_full[2], tmem_empty[2] (CTA 0) ][ tmem base ]
+//   [ ring: stages x (A 16 KB | B 16 KB) ][ tau: 2 x 256 f32 ][ staging: 8 warps x 64 x 16 B ]
+//   [ barriers: full[stages] (CTA 0), empty[stages], tmem_full[2], tmem_empty[2] (CTA 0) ][ tmem base ]
 // Ten warps: 0-7 epilogue (warps w and w+4 share the TMEM lane quarter w%4 and split the 256 query columns in
 // halves), 8 TMA producer, 9 TMEM alloc + MMA issue (leader CTA).
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS3, 1)
@@ -68,7 +98,8 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
 
     unsigned char* ring = smem;
     float* tau_s = reinterpret_cast<float*>(ring + size_t(p.stages) * STAGE_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tau_s + 2 * NQB);
+    uint4* stage_s = reinterpret_cast<uint4*>(tau_s + 2 * NQB);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stage_s + (EPI3 / 32) * STG_CAP);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + p.stages;
     uint64_t* tmem_full = bars + 2 * p.stages;
@@ -156,20 +187,38 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
         // ===================================================== epilogue: thread = (corpus row, 128 of the 256 query columns)
         const int quarter = warp & 3, half = warp >> 2;
         const uint32_t te0 = mapa(smem_u32(tmem_empty), 0), te1 = mapa(smem_u32(tmem_empty + 1), 0);
+        uint4* stg = stage_s + warp * STG_CAP;
+        int n_stg = 0;  // warp-uniform
+        const int64_t row_in_super = int64_t(rank) * TILE_ROWS + quarter * 32 + lane;
+        // thresholds and inv_norm of a tile are fetched one tile ahead (their latency hides behind the current tile)
+        float tau_n = INFINITY, inv_n = 1.f;
+        if (cluster_id < n_work) {
+            const int64_t w = cluster_id;
+            const int super = int((uint64_t(p.i0 + int(w / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
+            const int64_t row = int64_t(super) * 256 + row_in_super;
+            tau_n = __ldcg(p.tau + size_t(w % p.n_qb) * NQB + threadIdx.x);
+            if (p.inv_norm && row < p.n_rows) inv_n = __ldg(p.inv_norm + row);
+        }
         int it = 0;
         for (int64_t w = cluster_id; w < n_work; w += n_clusters, ++it) {
             const int a = it & 1;
             const int qb = int(w % p.n_qb);
             const int super = int((uint64_t(p.i0 + int(w / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
-            const int64_t row = int64_t(super) * 256 + int64_t(rank) * TILE_ROWS + quarter * 32 + lane;
+            const int64_t row = int64_t(super) * 256 + row_in_super;
             const bool row_ok = row < p.n_rows;
-            float inv = 1.f;
-            if (p.inv_norm && row_ok) inv = __ldg(p.inv_norm + row);
+            const float inv = inv_n;
 
             // this tile's thresholds (double-buffered by `a`: one barrier per tile keeps readers and writers apart)
             float* th = tau_s + a * NQB;
-            th[threadIdx.x] = __ldcg(p.tau + size_t(qb) * NQB + threadIdx.x);
+            th[threadIdx.x] = tau_n;
             epi_bar_sync<EPI3>();
+            if (w + n_clusters < n_work) {
+                const int64_t w2 = w + n_clusters;
+                const int super2 = int((uint64_t(p.i0 + int(w2 / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
+                const int64_t row2 = int64_t(super2) * 256 + row_in_super;
+                tau_n = __ldcg(p.tau + size_t(w2 % p.n_qb) * NQB + threadIdx.x);
+                inv_n = (p.inv_norm && row2 < p.n_rows) ? __ldg(p.inv_norm + row2) : 1.f;
+            }
 
             mbar_wait(smem_u32(tmem_full + a), uint32_t(it >> 1) & 1u);
             tcgen05_fence_after();
@@ -192,11 +241,35 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
                     m = fmaxf(m, fmaf(v[j4 * 4 + 3], inv, -t4.w));
                 }
                 if (__any_sync(0xffffffffu, row_ok && m > 0.f)) {
-                    const int q0 = qb * NQB + half * (NQB / 2) + c32;
+                    // survivors of this chunk: branch-free bit mask per lane, then one warp-uniform round per column
+                    // that has any; survivors are staged in shared memory and appended in groups of >= 32.
+                    uint32_t hm = 0u;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float s = v[j] * inv;
-                        if (row_ok && s > th[half * (NQB / 2) + c32 + j]) append_candidate(p.buf, p.cnt, p.cap, q0 + j, s, uint32_t(row));
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 t4 = lds_f4(th_addr + (c32 + j4 * 4) * 4);
+                        hm |= (v[j4 * 4 + 0] * inv > t4.x ? 1u : 0u) << (j4 * 4 + 0);
+                        hm |= (v[j4 * 4 + 1] * inv > t4.y ? 1u : 0u) << (j4 * 4 + 1);
+                        hm |= (v[j4 * 4 + 2] * inv > t4.z ? 1u : 0u) << (j4 * 4 + 2);
+                        hm |= (v[j4 * 4 + 3] * inv > t4.w ? 1u : 0u) << (j4 * 4 + 3);
+                    }
+                    if (!row_ok) hm = 0u;
+                    uint32_t any = __reduce_or_sync(0xffffffffu, hm);
+                    const int q0 = qb * NQB + half * (NQB / 2) + c32;
+                    while (any) {
+                        const int j = __ffs(any) - 1;
+                        any &= any - 1u;
+                        const bool hit = (hm >> j) & 1u;
+                        const uint32_t who = __ballot_sync(0xffffffffu, hit);
+                        if (hit) {
+                            const uint64_t e = pack_entry(pick32(v, j) * inv, uint32_t(row));
+                            stg[n_stg + __popc(who & ((1u << lane) - 1u))] = make_uint4(uint32_t(e), uint32_t(e >> 32), uint32_t(q0 + j), 0u);
+                        }
+                        n_stg += __popc(who);
+                        __syncwarp();
+                        if (n_stg >= 32) {
+                            flush_staged(stg, n_stg, p.buf, p.cnt, p.cap);
+                            n_stg = 0;
+                        }
                     }
                 }
             }
@@ -204,6 +277,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(a ? te1 : te0);  // this warp is done with the accumulator (leader's barrier)
         }
+        if (n_stg > 0) flush_staged(stg, n_stg, p.buf, p.cnt, p.cap);
     }
 
     tcgen05_fence_before();
@@ -226,44 +300,111 @@ __global__ void gemm_init_kernel(int* cnt, float* tau, int* ovf, int n_q, int n_
     }
 }
 
-// One block per query: sort the buffer (key desc, id asc), keep the K' best at its front, tau := K'-th key.
-// final: also emit the shortlist in the stage-1 output format (one list per query).
+// One block per query: keep the K' best entries (key desc, id asc) at the front of the buffer, tau := K'-th key.
+// The K'-th largest packed entry is found by an MSB-first radix select (8 bits per pass, stops as soon as the
+// current digit bin holds exactly the entries still wanted -- normally after the 4 passes over the score bits);
+// nothing is sorted between phases.  final: the K' survivors are sorted and emitted in the stage-1 output format.
 constexpr int CUT_THREADS = 512;
 __global__ void __launch_bounds__(CUT_THREADS)
 gemm_cut_kernel(unsigned long long* buf, int* cnt, float* tau, int* ovf, int cap, int kp, int final_pass, int64_t id_base,
                 int64_t* out_ids, float* out_approx, float* out_thresh) {
-    extern __shared__ uint64_t sort_s[];
-    const int q = blockIdx.x;
+    extern __shared__ uint64_t cut_s[];  // [cap] entries, then [kp] survivors
+    __shared__ int hist[256];
+    __shared__ int sh_bin, sh_want, sh_n_sel;
+    __shared__ unsigned long long sh_min;
+    uint64_t* ent = cut_s;
+    uint64_t* sel = cut_s + cap;
+    const int q = blockIdx.x, t = threadIdx.x;
     const int raw = cnt[q];
     const int n = min(raw, cap);
     unsigned long long* B = buf + size_t(q) * cap;
     const bool over = raw > cap || ovf[q] != 0;
-    if (n > kp || final_pass) {
-        int n2 = 1;
-        while (n2 < n) n2 <<= 1;
-        for (int i = threadIdx.x; i < n2; i += CUT_THREADS) sort_s[i] = i < n ? B[i] : 0ull;
-        __syncthreads();
-        if (n2 > 1) block_bitonic_sort_desc(sort_s, n2);
-        const int keep = min(n, kp);
-        if (n > kp)
-            for (int i = threadIdx.x; i < keep; i += CUT_THREADS) B[i] = sort_s[i];
-        if (final_pass) {
-            for (int i = threadIdx.x; i < kp; i += CUT_THREADS) {
-                const uint64_t e = i < keep ? sort_s[i] : 0ull;
-                out_ids[size_t(q) * kp + i] = e ? int64_t(id_base + entry_id(e)) : int64_t(-1);
-                out_approx[size_t(q) * kp + i] = e ? entry_key(e) : -INFINITY;
-            }
-        }
-        if (threadIdx.x == 0) {
-            const float t = n > kp ? entry_key(sort_s[kp - 1]) : tau[q];  // n <= kp: nothing dropped by this cut
-            if (n > kp) {
-                cnt[q] = kp;
-                tau[q] = t;
-            }
-            if (final_pass) out_thresh[q] = over ? INFINITY : t;
-        }
+    if (t == 0 && over) ovf[q] = 1;
+    if (n <= kp && !final_pass) return;  // nothing to drop yet
+
+    for (int i = t; i < n; i += CUT_THREADS) ent[i] = B[i];
+    if (t == 0) {
+        sh_n_sel = 0;
+        sh_min = ~0ull;
     }
-    if (threadIdx.x == 0 && over) ovf[q] = 1;
+    __syncthreads();
+    int n_keep = n;
+    if (n > kp) {
+        uint64_t prefix = 0ull, mask = 0ull;
+        int want = kp;  // still to take among the entries matching `prefix` under `mask`
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            if (t < 256) hist[t] = 0;
+            __syncthreads();
+            for (int i = t; i < n; i += CUT_THREADS) {
+                const uint64_t e = ent[i];
+                if ((e & mask) == prefix) atomicAdd(&hist[int(e >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (t < 32) {  // bins from 255 down: lane l owns bins 255-8l .. 248-8l
+                int local[8], sum = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    local[u] = hist[255 - 8 * t - u];
+                    sum += local[u];
+                }
+                int inc = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (t >= d) inc += o;
+                }
+                int before = inc - sum;  // entries in bins above this lane's
+                if (before < want && want <= inc) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (before < want && want <= before + local[u]) {
+                            sh_bin = 255 - 8 * t - u;
+                            sh_want = want - before;
+                        }
+                        before += local[u];
+                    }
+                }
+            }
+            __syncthreads();
+            const int bin = sh_bin;
+            want = sh_want;
+            prefix |= uint64_t(bin) << shift;
+            mask |= 0xffull << shift;
+            if (hist[bin] == want) break;  // every entry matching the prefix is wanted: selection = {e & mask >= prefix}
+            __syncthreads();
+        }
+        for (int i = t; i < n; i += CUT_THREADS) {
+            const uint64_t e = ent[i];
+            if ((e & mask) >= prefix) {
+                const int slot = atomicAdd(&sh_n_sel, 1);
+                if (slot < kp) sel[slot] = e;  // (entries are distinct, so exactly kp match; the guard is for safety)
+                atomicMin(&sh_min, static_cast<unsigned long long>(e));
+            }
+        }
+        __syncthreads();
+        n_keep = kp;  // == sh_n_sel: entries are distinct
+        if (!final_pass)
+            for (int i = t; i < kp; i += CUT_THREADS) B[i] = sel[i];
+        if (t == 0) {
+            cnt[q] = kp;
+            tau[q] = entry_key(sh_min);
+        }
+    } else {
+        for (int i = t; i < n; i += CUT_THREADS) sel[i] = ent[i];
+    }
+    if (final_pass) {
+        int n2 = 1;
+        while (n2 < n_keep) n2 <<= 1;
+        for (int i = n_keep + t; i < n2; i += CUT_THREADS) sel[i] = 0ull;
+        __syncthreads();
+        if (n2 > 1) block_bitonic_sort_desc(sel, n2);
+        for (int i = t; i < kp; i += CUT_THREADS) {
+            const uint64_t e = i < n_keep ? sel[i] : 0ull;
+            out_ids[size_t(q) * kp + i] = e ? int64_t(id_base + entry_id(e)) : int64_t(-1);
+            out_approx[size_t(q) * kp + i] = e ? entry_key(e) : -INFINITY;
+        }
+        if (t == 0) out_thresh[q] = over ? INFINITY : (n > kp ? entry_key(sh_min) : tau[q]);
+    }
 }
 
 static uint32_t pick_perm_mul(uint32_t n) {
@@ -301,13 +442,14 @@ int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride
     gemm_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(cnt, tau, ovf, n_q, n_pad);
     TT_LAUNCH_OK("gemm_init_kernel");
 
-    int stages = (tc::SMEM_LIMIT - 1024 - 2 * NQB * 4 - 256) / (STAGE_BYTES + 16);
+    int stages = (tc::SMEM_LIMIT - 1024 - 2 * NQB * 4 - (EPI3 / 32) * STG_CAP * 16 - 256) / (STAGE_BYTES + 16);
     if (stages > 8) stages = 8;
     if (const char* e = getenv("TT_GEMM_STAGES")) {
         const int want = atoi(e);
         if (want >= 2 && want < stages) stages = want;
     }
-    const size_t smem = 1024 + size_t(stages) * STAGE_BYTES + 2 * NQB * 4 + (2 * size_t(stages) + 4) * 8 + 16;
+    const size_t smem = 1024 + size_t(stages) * STAGE_BYTES + 2 * NQB * 4 + (EPI3 / 32) * STG_CAP * 16 +
+                        (2 * size_t(stages) + 4) * 8 + 16;
 
     Params p;
     p.inv_norm = inv_norm;
@@ -330,7 +472,7 @@ int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride
         if (rc) return rc;
     }
     TT_CUDA_OK(cudaFuncSetAttribute(scan_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
-    TT_CUDA_OK(cudaFuncSetAttribute(gemm_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, cap * 8));
+    TT_CUDA_OK(cudaFuncSetAttribute(gemm_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (cap + kprime) * 8));
 
     // phases: the first visits ~4 K' rows, each later one `growth` times the rows visited before it
     int growth = 4;
@@ -343,7 +485,7 @@ int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride
     int next = (4 * kprime + 255) / 256;
     bool done = p.n_super == 0;
     if (done) {
-        gemm_cut_kernel<<<n_q, CUT_THREADS, cap * 8, st>>>(buf, cnt, tau, ovf, cap, kprime, 1, id_base, out_ids, out_approx,
+        gemm_cut_kernel<<<n_q, CUT_THREADS, (cap + kprime) * 8, st>>>(buf, cnt, tau, ovf, cap, kprime, 1, id_base, out_ids, out_approx,
                                                            out_thresh);
         TT_LAUNCH_OK("gemm_cut_kernel");
     }
@@ -355,7 +497,7 @@ int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride
         scan_gemm_kernel<<<grid, THREADS3, smem, st>>>(map_c, map_q, p);
         TT_LAUNCH_OK("scan_gemm_kernel");
         done = upto == p.n_super;
-        gemm_cut_kernel<<<n_q, CUT_THREADS, cap * 8, st>>>(buf, cnt, tau, ovf, cap, kprime, done ? 1 : 0, id_base, out_ids,
+        gemm_cut_kernel<<<n_q, CUT_THREADS, (cap + kprime) * 8, st>>>(buf, cnt, tau, ovf, cap, kprime, done ? 1 : 0, id_base, out_ids,
                                                            out_approx, out_thresh);
         TT_LAUNCH_OK("gemm_cut_kernel");
         seen = upto;
