@@ -35,7 +35,7 @@ def _worker(rank, world, port, transport, out_dir):
     torch.cuda.set_device(rank)
     dev = torch.device(f"cuda:{rank}")
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    tree, bits, inv, q = make_small(50_000, 12, dim=1024, levels=3, seed=31)
+    tree, bits, inv, q = make_small(50_000, 300, dim=1024, levels=3, seed=31)
     lo, hi = shard_bounds(bits.shape[0], world, rank)
     idx = DeviceIndex(bits[lo:hi], tree, id_base=lo, device=dev)
     sh = ShardedIndex(idx)
@@ -47,6 +47,12 @@ def _worker(rank, world, port, transport, out_dir):
             scores, ids = sh.search(qd[:b], 10)
             torch.cuda.synchronize()
             assert (ids.cpu().numpy() == ids_o[:b]).all() and (scores.cpu().numpy() == sc_o[:b]).all(), (rep, b)
+    # a wide batch: every rank's stage 1 is the GEMM-shaped scan (one shortlist per query), same exchange
+    assert idx._use_gemm(300)
+    for rep in range(2):
+        scores, ids = sh.search(qd, 10)
+        torch.cuda.synchronize()
+        assert (ids.cpu().numpy() == ids_o).all() and (scores.cpu().numpy() == sc_o).all(), rep
     ids_h, sc_h, lens = sh.retrieve_host(torch.from_numpy(q[:3]), 10)
     for b in range(3):
         exp = oracle.retrieve(bits, q[b], 10, tree)
