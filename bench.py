@@ -126,11 +126,11 @@ def physical_index(local_rank: int) -> int:
     return local_rank
 
 
-def build_shard(n_rows, rank, world, device, levels=LEVELS):
+def build_shard(n_rows, rank, world, device, levels=None):
     from tensor_truth_b200.sharded import shard_bounds
     from tensor_truth_b200.synth import SynthCorpus
 
-    sc = SynthCorpus(n_rows, DIM, levels, SEED, device=device)
+    sc = SynthCorpus(n_rows, DIM, levels if levels is not None else LEVELS, SEED, device=device)
     lo, hi = shard_bounds(n_rows, world, rank)
     corpus, inv = sc.rows(lo, hi)
     return sc, corpus, inv, lo, hi
@@ -218,11 +218,12 @@ def run_b200(args):
 
     from tensor_truth_b200.index import MergeResult
 
-    def timed(batch: int, steps: int, warm: int, sample_clocks: bool, depth: int, k: int = TOP_K, pool=None):
+    def timed(batch: int, steps: int, warm: int, sample_clocks: bool, depth: int, k: int = 0, pool=None):
         """K steps of the device pipeline.  depth = 1: strictly serial, with CUDA events around every stage-1
         launch (the roofline numbers).  depth = 2: steps alternate between two streams, so step i+1's scan
         overlaps step i's re-score / select / (all-gather, merge) / auto-merge -- the throughput configuration."""
         margins = torch.full((steps + warm, batch), float("inf"), dtype=torch.float32, device=device)
+        k = k or TOP_K
         pool = queries if pool is None else pool
         n_pool = max(1, int(pool.shape[0]) // batch)
         streams = [torch.cuda.Stream(device) for _ in range(depth)]
@@ -297,15 +298,22 @@ def run_b200(args):
         pass
 
     # ---- batch-64 (same corpus, one pass of 64 hi-only queries; tensor work rises, HBM bytes per pass do not)
-    steps64 = max(3, min(args.steps, 40))
-    ser64 = timed(64, steps64, 3, False, depth=1)
-    pip64 = timed(64, steps64, 3, False, depth=2)
-    value64 = steps64 * 64 / (pip64["ms"] / 1e3)
+    skip = set(x for x in args.skip.split(",") if x)
+    batch64 = None
+    if "batch64" not in skip:
+        steps64 = max(3, min(args.steps, 40))
+        ser64 = timed(64, steps64, 3, False, depth=1)
+        pip64 = timed(64, steps64, 3, False, depth=2)
+        batch64 = {"value": steps64 * 64 / (pip64["ms"] / 1e3), "unit": UNIT, "ms_per_step": pip64["ms"] / steps64,
+                   "steps": steps64, "serial_value": steps64 * 64 / (ser64["ms"] / 1e3), "scan_ms_per_step": ser64["scan_ms"],
+                   "hbm_frac": float(hi - lo) * DIM * 2 / (ser64["scan_ms"] / 1e3) / 1e9 / peak,
+                   "certificate_failures": ser64["bad"] + pip64["bad"], "min_margin": pip64["min_margin"],
+                   "eps": pip64["eps"], "mode": "hi-only bf16 queries, 64 per corpus pass"}
 
     # ---- wide batch (BASELINE configs[3] shape: 16k concurrent queries, top-100): the tensor-bound regime, served by
     #      the GEMM-shaped stage 1 (scan_gemm.cu).  Roofline: dense bf16 tensor throughput.
     wide = None
-    if args.wide_batch > 0:
+    if args.wide_batch > 0 and "wide" not in skip:
         try:
             bw, kw = args.wide_batch, args.wide_k
             qw = make_queries(sc, corpus, lo, hi, bw, world).to(device)
@@ -374,7 +382,7 @@ def run_b200(args):
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same corpus bytes
     cpu = None
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and "cpu" not in skip:
         sample = min(args.cpu_sample_rows, hi - lo)
         bits = corpus[:sample].view(torch.int16).cpu().numpy().view(np.uint16)
         inv_h = inv[:sample].cpu().numpy()
@@ -395,7 +403,7 @@ def run_b200(args):
             "serial": {"value": args.steps / (ser1["ms"] / 1e3), "ms_per_step": ser1["ms"] / args.steps,
                        "note": "same K steps with no overlap between consecutive steps (one stream)"},
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"C2: exact cosine top-{TOP_K} + auto-merge, {n_rows} x {DIM} bf16 leaf embeddings, "
+            "config": {"workload": f"{args.tag}: exact cosine top-{TOP_K} + auto-merge, {n_rows} x {DIM} bf16 leaf embeddings, "
                                    f"{LEVELS}-level tree, batch-1 queries, corpus row-sharded over {world} GPU(s)",
                        "rows_per_gpu": hi - lo, "batch": 1, "k": TOP_K, "kprime": args.kprime, "variant": args.variant,
                        "l2": "no flush: every step streams the whole shard (>= 2.5 GB) through a 126 MB L2",
@@ -410,11 +418,7 @@ def run_b200(args):
             "e2e": e2e,
             "gpu_launches": args.steps * (4 + nl1 + (1 if world > 1 else 0)),
             "clocks": clocks,
-            "batch64": {"value": value64, "unit": UNIT, "ms_per_step": pip64["ms"] / steps64, "steps": steps64,
-                        "serial_value": steps64 * 64 / (ser64["ms"] / 1e3), "scan_ms_per_step": ser64["scan_ms"],
-                        "hbm_frac": local_bytes / (ser64["scan_ms"] / 1e3) / 1e9 / peak,
-                        "certificate_failures": ser64["bad"] + pip64["bad"], "min_margin": pip64["min_margin"],
-                        "eps": pip64["eps"], "mode": "hi-only bf16 queries, 64 per corpus pass"},
+            "batch64": batch64,
             "wide": wide,
             "certificate_failures": bad1, "min_margin": pip1["min_margin"], "eps": pip1["eps"],
             "exchange": (sharded.transport + (" (fused into the select / merge kernels over peer memory)" if sharded.transport == "peer" else " all-gather")) if sharded is not None else None,
@@ -481,16 +485,26 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=N_ROWS)
-    ap.add_argument("--kprime", type=int, default=32)
+    ap.add_argument("--kprime", type=int, default=0, help="per-CTA shortlist length (0 = by k)")
+    ap.add_argument("--k", type=int, default=10, help="similarity_top_k (BASELINE: 10; C5: 200)")
+    ap.add_argument("--levels", type=int, default=3, help="levels of the node tree (C5: 4)")
+    ap.add_argument("--skip", default="", help="comma list of secondary sections to skip: batch64,wide,e2e,cpu")
     ap.add_argument("--variant", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_048_576)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tag", default="C2", help="BASELINE config label written into config.workload")
     ap.add_argument("--wide-batch", type=int, default=16384, help="queries per step of the wide-batch (C4-shaped) section; 0 = skip")
     ap.add_argument("--wide-k", type=int, default=100)
     ap.add_argument("--wide-steps", type=int, default=2)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    global TOP_K, LEVELS, METRIC
+    TOP_K, LEVELS = args.k, args.levels
+    if args.kprime <= 0:  # per-CTA shortlist length: deeper for larger k (clustered hits share a tile, hence a CTA)
+        args.kprime = 32 if TOP_K <= 16 else 64 if TOP_K <= 32 else 128
+    if (TOP_K, LEVELS, args.rows) != (10, 3, N_ROWS):
+        METRIC = (f"queries/sec exact top-{TOP_K} (+auto-merge, {LEVELS}-level tree) over {args.rows} x {DIM} chunks, batch-1")
     if args.impl == "reference":
         run_reference(args)
     else:
