@@ -193,6 +193,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; rank 0 must print ONE line
         dist.init_process_group("nccl", device_id=device)
     _lib.lib()  # fail loudly if the CUDA library is missing
 

@@ -35,7 +35,8 @@ EPS_F32_CORPUS = 4.2e-3    # fp32 master scanned through a bf16 shadow: + 2^-8 c
 EPS_HI_ONLY = 3.95e-3      # added when the query travels as bf16 hi only (|q - bf16(q)| <= 2^-8 |q|)
 HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first (64 queries per corpus pass)
 MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist workspace: 148 * K' * 12 B per query)
-GEMM_ABOVE = 256           # hi-only batches at least this large take the GEMM-shaped stage 1 (scan_gemm.cu): one list per query
+GEMM_ABOVE = 65            # hi-only batches at least this large (more than one pass of the 64-query pair kernel) take the
+                           # GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass per 4096 queries, one list per query
 GEMM_SLICE = 4096          # queries per GEMM-shaped corpus pass (candidate buffers: 16 K' * 8 B per query)
 
 
@@ -150,7 +151,7 @@ class DeviceIndex:
     # ------------------------------------------------------------------ workspaces
     def _use_gemm(self, b: int, hi_only: bool = True) -> bool:
         """Wide hi-only batches: the tensor-bound regime, served by the GEMM-shaped stage 1."""
-        return (hi_only and b >= GEMM_ABOVE and self.variant in (SCAN_AUTO, _lib.SCAN_TCGEN05) and self.dim % 64 == 0
+        return (hi_only and b >= int(os.environ.get("TT_GEMM_ABOVE", GEMM_ABOVE)) and self.variant in (SCAN_AUTO, _lib.SCAN_TCGEN05) and self.dim % 64 == 0
                 and self.n_rows > 0 and not os.environ.get("TT_NO_GEMM"))
 
     def _buffers(self, b: int, k: int, slot: int = 0, hi_only: Optional[bool] = None):
