@@ -37,6 +37,7 @@ HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first (64 que
 MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist workspace: 148 * K' * 12 B per query)
 GEMM_ABOVE = 65            # hi-only batches at least this large (more than one pass of the 64-query pair kernel) take the
                            # GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass per 4096 queries, one list per query
+GRAPH_AFTER = 3            # retrieve_host: eager calls of a (batch, k) shape before its pipeline is captured in a CUDA graph
 GEMM_SLICE = 4096          # queries per GEMM-shaped corpus pass (candidate buffers: 16 K' * 8 B per query)
 
 
@@ -204,9 +205,10 @@ class DeviceIndex:
     def _row_stride(self, t: torch.Tensor) -> int:
         return max(int(t.stride(0)), self.dim)  # an empty tensor reports stride 0
 
-    @staticmethod
-    def _stream():
-        return torch.cuda.current_stream().cuda_stream
+    def _stream(self):
+        """Raw handle of torch's current stream on this index's GPU (the C call: ``torch.cuda.current_stream()`` costs
+        ~15 us of Python per call, three of them per query)."""
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
     def _check_queries(self, q: torch.Tensor) -> torch.Tensor:
         if q.dim() != 2 or q.shape[1] != self.dim:
@@ -369,6 +371,53 @@ class DeviceIndex:
                                  "event": torch.cuda.Event()}
         return r
 
+    def _pipeline_graph(self, b: int, k: int, ratio_thresh: float, merged: bool):
+        """The whole device pipeline of one ``retrieve_host`` shape as ONE CUDA graph: H2D of the queries from a pinned
+        staging buffer -> prepare -> stage 1 -> re-score/select -> auto-merge -> D2H of the result record.  Captured
+        after ``GRAPH_AFTER`` eager calls of the shape; a replay costs one launch instead of ~10 (the kernels, their
+        arguments and the buffers are the same ones the eager path uses).  Returns None while the shape is still
+        warming up, or for good if capture is not possible (the eager path then keeps serving)."""
+        key = ("graph", b, k, float(ratio_thresh), merged)
+        g = self._ws.get(key)
+        if g is None:
+            g = self._ws[key] = {"calls": 0, "graph": None, "dead": bool(os.environ.get("TT_NO_GRAPH"))}
+        if g["graph"] is not None or g["dead"]:
+            return g if g["graph"] is not None else None
+        g["calls"] += 1
+        if g["calls"] <= GRAPH_AFTER:
+            return None
+        try:
+            rec = self._record(b, k, merged)
+            d = rec["d"]
+            w = dict(self._buffers(b, k))
+            w["margin"] = d["margin"]
+            if not merged:
+                w["ids"], w["scores"] = d["ids"], d["scores"]
+            q_pin = torch.zeros((b, self.dim), dtype=torch.float32).pin_memory()
+            q_dev = torch.zeros((b, self.dim), dtype=torch.float32, device=self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                q_dev.copy_(q_pin, non_blocking=True)
+                r = self.search(q_dev, k, out=w)
+                if merged:
+                    self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+                rec["host"].copy_(rec["dev"], non_blocking=True)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g.update(graph=graph, q_pin=q_pin, q_dev=q_dev, result=r, rec=rec)
+            return g
+        except Exception as exc:  # capture refused (driver, another thread capturing, ...): keep the eager path
+            import warnings
+
+            warnings.warn(f"tensor_truth_b200: CUDA-graph capture of the retrieve pipeline failed ({exc}); staying eager")
+            g["dead"] = True
+            try:
+                torch.cuda.synchronize(self.device)
+            except Exception:
+                pass
+            return None
+
     def retrieve_host(self, q_host: torch.Tensor, k: int, ratio_thresh: float = 0.5, merge: bool = True):
         """Query embeddings in host memory -> merged ``(ids, scores, lens)`` in host memory (numpy).
         The H2D copy of the queries and the single D2H read of the result record are part of the call;
@@ -379,19 +428,27 @@ class DeviceIndex:
                      for i in range(0, int(q_host.shape[0]), MAX_HOST_BATCH)]
             return tuple(np.concatenate([p[j] for p in parts], axis=0) for j in range(3))
         with self._lock:
-            q = q_host.to(self.device, torch.float32, non_blocking=True)
-            q = self._check_queries(q)
-            b = int(q.shape[0])
-            rec = self._record(b, k, merged)
-            d, h = rec["d"], rec["h"]
-            w = dict(self._buffers(b, k))
-            w["margin"] = d["margin"]
-            if not merged:
-                w["ids"], w["scores"] = d["ids"], d["scores"]
-            r = self.search(q, k, out=w)
-            if merged:
-                self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
-            rec["host"].copy_(rec["dev"], non_blocking=True)
+            b = int(q_host.shape[0])
+            g = self._pipeline_graph(b, k, ratio_thresh, merged) if (q_host.dim() == 2 and q_host.shape[1] == self.dim) else None
+            if g is not None:
+                g["q_pin"].copy_(q_host)
+                q, r, rec = g["q_dev"], g["result"], g["rec"]
+                d, h = rec["d"], rec["h"]
+                with self._on_device():
+                    g["graph"].replay()
+            else:
+                q = q_host.to(self.device, torch.float32, non_blocking=True)
+                q = self._check_queries(q)
+                rec = self._record(b, k, merged)
+                d, h = rec["d"], rec["h"]
+                w = dict(self._buffers(b, k))
+                w["margin"] = d["margin"]
+                if not merged:
+                    w["ids"], w["scores"] = d["ids"], d["scores"]
+                r = self.search(q, k, out=w)
+                if merged:
+                    self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+                rec["host"].copy_(rec["dev"], non_blocking=True)
             rec["event"].record()
             rec["event"].synchronize()
             bad = np.nonzero(~(h["margin"].numpy() > r.eps))[0]

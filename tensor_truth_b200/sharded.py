@@ -167,7 +167,7 @@ class ShardedIndex:
         with self.local._on_device():
             check(L.tt_merge_topk_pulled(region_ptr, region_ptr + x.ids_off_bytes, x.world, x.rec_stride_bytes // 4,
                                          x.rec_stride_bytes // 8, b, k, k_out, self.local.score_mode, ptr(o[0]), ptr(o[1]),
-                                         C.byref(x), torch.cuda.current_stream().cuda_stream))
+                                         C.byref(x), self.local._stream()))
         return o
 
     def _local_search(self, q, k, keys_out, ids_out, slot=0):
@@ -185,7 +185,7 @@ class ShardedIndex:
         base = recv.data_ptr()
         with self.local._on_device():
             check(L.tt_merge_topk(base, base + ids_off, world, rec // 4, rec // 8, b, k, k_out,
-                                  self.local.score_mode, ptr(o[0]), ptr(o[1]), torch.cuda.current_stream().cuda_stream))
+                                  self.local.score_mode, ptr(o[0]), ptr(o[1]), self.local._stream()))
         return o
 
     def search(self, q, k, margins: Optional[torch.Tensor] = None, slot: int = 0):
@@ -232,7 +232,7 @@ class ShardedIndex:
 
             with local._on_device():
                 self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), send.numel() // 4 * 4, C.byref(x),
-                                                                 torch.cuda.current_stream().cuda_stream))
+                                                                 self.local._stream()))
             scores, mids = self._merge_pulled(x, region, b, k, k, 0)
         merged = bool(merge and local.tree is not None)
         rec = local._record(b, k, merged)

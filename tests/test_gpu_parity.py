@@ -603,3 +603,48 @@ def test_empty_index_and_empty_batch():
     assert (_np(r.ids) == -1).all() and np.isneginf(_np(r.scores)).all()
     ids, scores, lens = idx.retrieve_host(torch.ones((1, 128)), 4, merge=False)
     assert lens.tolist() == [0]
+
+
+def test_retrieve_host_graph_replay_equals_eager(c1, monkeypatch):
+    """retrieve_host captures its device pipeline in a CUDA graph after a few eager calls of a shape: the replays must
+    give what the eager path (and the oracle) gives, for new queries, and still walk the repair ladder when needed."""
+    from tensor_truth_b200 import index as index_mod
+
+    tree, bits, inv, q = c1
+    idx = _index(bits, tree)
+    eager = _index(bits, tree)
+    monkeypatch.setattr(index_mod, "GRAPH_AFTER", 10 ** 9)  # `eager` never captures ...
+    want = [eager.retrieve_host(torch.from_numpy(q[i:i + 1]), 10) for i in range(12)]
+    monkeypatch.setattr(index_mod, "GRAPH_AFTER", 2)        # ... `idx` does on its third call
+    got = [idx.retrieve_host(torch.from_numpy(q[i:i + 1]), 10) for i in range(12)]
+    g = idx._ws[("graph", 1, 10, 0.5, True)]
+    assert g["graph"] is not None, "the pipeline was not captured"
+    for a, b in zip(want, got):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y, equal_nan=True)
+    exp = oracle.retrieve(bits, q[11], 10, tree)
+    ids, scores, lens = got[11]
+    assert [(int(o), float(s)) for o, s in zip(ids[0, :lens[0]], scores[0, :lens[0]])] == exp
+    # a batch shape of its own graph, leaves only
+    for rep in range(4):
+        ids_b, sc_b, lens_b = idx.retrieve_host(torch.from_numpy(q[8 * rep:8 * rep + 8]), 10, merge=False)
+        ids_o, sc_o, _ = cport.scan_topk(bits, q[8 * rep:8 * rep + 8], 10)
+        assert (ids_b == ids_o).all() and (sc_b == sc_o.astype(np.float64)).all()
+    assert idx._ws[("graph", 8, 10, 0.5, False)]["graph"] is not None
+
+
+def test_graph_replay_still_repairs_unproven_queries(monkeypatch):
+    from tensor_truth_b200 import index as index_mod
+
+    monkeypatch.setattr(index_mod, "GRAPH_AFTER", 1)
+    rng = np.random.default_rng(17)
+    base = rng.standard_normal(1024).astype(np.float32)
+    c = base[None, :] * (1.0 + 2e-3 * rng.standard_normal((30_000, 1024)).astype(np.float32))
+    bits = oracle.f32_to_bf16_bits(c)
+    q = (base[None, :] * (1.0 + 1e-3 * rng.standard_normal((6, 1024)))).astype(np.float32)
+    ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
+    idx = _index(bits, None)
+    for i in range(6):
+        ids, scores, lens = idx.retrieve_host(torch.from_numpy(q[i:i + 1]), 10, merge=False)
+        assert (ids[0] == ids_o[i]).all() and (scores[0] == sc_o[i].astype(np.float64)).all()
+    assert idx._ws[("graph", 1, 10, 0.5, False)]["graph"] is not None and idx.fallbacks >= 4
