@@ -94,6 +94,26 @@ int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t 
                       void* ws, size_t ws_bytes, void* stream);
 
 /*
+ * Stage 1 over a SEGMENTED corpus: several indexes concatenated row-wise in one matrix, segment s = rows
+ * [seg_end_host[s-1], seg_end_host[s]) (seg_end_host[n_seg-1] == n_rows).  Replaces the per-index fan-out of
+ * MultiIndexRetriever._retrieve_impl (rag_engine.py:416-461: one vector-store query per index on a thread pool)
+ * by ONE corpus pass in which every (segment, query) pair keeps its own shortlists -- a "virtual query"
+ * v = s * n_q + q in the outputs, which stage 2 and tt_automerge then treat like any query:
+ *
+ *   out_ids / out_approx  [n_seg * n_q, n_lists * kprime]      out_thresh  [n_seg * n_q, n_lists]
+ *
+ * Same contract per virtual query as tt_scan_topk_bf16, with "every row" read as "every row of segment s".
+ * tcgen05 variant only (dim % 128 == 0), hi+lo queries (q_lo_bf16 required), n_seg <= TT_MAX_SEGMENTS.
+ * seg_end_host is a HOST array, read during the call.
+ */
+#define TT_MAX_SEGMENTS 16
+int tt_scan_topk_bf16_segmented(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
+                                const float* inv_norm, const void* q_hi_bf16, const void* q_lo_bf16, int n_q,
+                                int kprime, int64_t id_base, const int64_t* seg_end_host, int n_seg,
+                                int64_t* out_ids, float* out_approx, float* out_thresh,
+                                void* ws, size_t ws_bytes, void* stream);
+
+/*
  * Stage 1 for very wide batches (hundreds to tens of thousands of concurrent queries; BASELINE config C4,
  * the tensor-bound regime).  Same role and same output contract as tt_scan_topk_bf16 with ONE list per
  * query (n_lists = 1), queries as bf16 hi halves only:

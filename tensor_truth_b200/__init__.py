@@ -17,7 +17,11 @@ def __getattr__(name):  # torch-dependent parts load lazily
         from . import index
 
         return getattr(index, name)
-    if name in ("B200VectorIndexRetriever", "B200AutoMergingRetriever", "NodeTable", "build_retriever"):
+    if name == "SegmentedIndex":
+        from . import segmented
+
+        return segmented.SegmentedIndex
+    if name in ("B200VectorIndexRetriever", "B200AutoMergingRetriever", "B200MultiIndexRetriever", "NodeTable", "build_retriever"):
         from . import retriever
 
         return getattr(retriever, name)

@@ -16,6 +16,7 @@ OK = 0
 DTYPE_BF16, DTYPE_F32 = 0, 1
 SCORE_COSINE, SCORE_CHROMA_L2_EXP = 0, 1
 SCAN_AUTO, SCAN_SIMT, SCAN_TCGEN05 = 0, 1, 2
+MAX_SEGMENTS = 16
 
 # every symbol include/tt_b200.h declares: name -> (restype, argtypes)
 _P, _I, _L, _Z, _D = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
@@ -27,6 +28,7 @@ SIGNATURES = {
     "tt_prepare_queries": (_I, [_P, _I, _I, _P, _P, _P]),
     "tt_scan_workspace_bytes": (_Z, []),
     "tt_scan_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _I, _P, _P, _P, _P, _Z, _P]),
+    "tt_scan_topk_bf16_segmented": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _P, _I, _P, _P, _P, _P, _Z, _P]),
     "tt_scan_gemm_workspace_bytes": (_Z, [_I, _I]),
     "tt_scan_gemm_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _I, _I, _L, _P, _P, _P, _P, _Z, _P]),
     "tt_rescore_workspace_bytes": (_Z, [_I, _I]),

@@ -19,6 +19,9 @@ bool scan_tc_supported(int64_t n_rows, int dim, int64_t stride, int kprime, cons
 int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
                    const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
                    float* out_approx, float* out_thresh, int n_lists, int* sched, cudaStream_t st);
+int scan_tc_segmented(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
+                      const void* q_lo, int n_q, int kprime, int64_t id_base, const int64_t* seg_end, int n_seg,
+                      int64_t* out_ids, float* out_approx, float* out_thresh, int n_lists, int* sched, cudaStream_t st);
 bool scan_tc2_supported(int dim, int kprime, int n_lists);
 int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
                     const void* q_hi, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
@@ -146,6 +149,34 @@ int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t 
                                 id_base, out_ids, out_approx, out_thresh, n_lists, TT_STREAM(stream));
     set_error("tt_scan_topk_bf16: unknown variant %d", variant);
     return TT_ERR_INVALID;
+}
+
+int tt_scan_topk_bf16_segmented(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
+                                const float* inv_norm, const void* q_hi_bf16, const void* q_lo_bf16, int n_q, int kprime,
+                                int64_t id_base, const int64_t* seg_end_host, int n_seg, int64_t* out_ids,
+                                float* out_approx, float* out_thresh, void* ws, size_t ws_bytes, void* stream) {
+    TT_CHECK_ARG(ws == nullptr || ws_bytes >= tt_scan_workspace_bytes(), "tt_scan_topk_bf16_segmented: workspace %zu < %zu bytes",
+                 ws_bytes, tt_scan_workspace_bytes());
+    TT_CHECK_ARG(n_rows > 0 && n_q >= 0, "tt_scan_topk_bf16_segmented: n_rows=%lld n_q=%d", (long long)n_rows, n_q);
+    TT_CHECK_ARG(kprime == 32 || kprime == 64 || kprime == 128, "tt_scan_topk_bf16_segmented: kprime=%d not in {32,64,128}", kprime);
+    TT_CHECK_ARG(id_base >= 0 && id_base + n_rows <= (int64_t(1) << 32), "tt_scan_topk_bf16_segmented: ids must stay below 2^32");
+    TT_CHECK_ARG(seg_end_host && n_seg >= 1 && n_seg <= TT_MAX_SEGMENTS, "tt_scan_topk_bf16_segmented: n_seg=%d not in [1, %d]",
+                 n_seg, TT_MAX_SEGMENTS);
+    for (int s = 0; s < n_seg; ++s)
+        TT_CHECK_ARG(seg_end_host[s] >= (s ? seg_end_host[s - 1] : 0) && seg_end_host[s] <= n_rows,
+                     "tt_scan_topk_bf16_segmented: segment ends must be non-decreasing and <= n_rows");
+    TT_CHECK_ARG(seg_end_host[n_seg - 1] == n_rows, "tt_scan_topk_bf16_segmented: the last segment must end at n_rows");
+    if (n_q == 0) return TT_OK;
+    TT_CHECK_ARG(corpus_bf16 && q_hi_bf16 && q_lo_bf16 && out_ids && out_approx && out_thresh,
+                 "tt_scan_topk_bf16_segmented: null pointer");
+    const int n_lists = sm_count(current_device());
+    if (n_lists <= 0) {
+        set_error("tt_scan_topk_bf16_segmented: no CUDA device");
+        return TT_ERR_CUDA;
+    }
+    return scan_tc_segmented(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, q_lo_bf16, n_q, kprime, id_base,
+                             seg_end_host, n_seg, out_ids, out_approx, out_thresh, n_lists, reinterpret_cast<int*>(ws),
+                             TT_STREAM(stream));
 }
 
 size_t tt_scan_gemm_workspace_bytes(int n_q, int kprime) {

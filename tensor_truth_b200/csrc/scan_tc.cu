@@ -22,6 +22,8 @@ namespace tt {
 
 namespace tc {
 
+constexpr int MAX_SEGMENTS = 16;
+
 struct Params {
     const float* inv_norm;
     int64_t n_rows;
@@ -39,6 +41,10 @@ struct Params {
     float* out_approx;
     float* out_thresh;
     int* sched;      // {next-tile counter, finished-CTA counter}, both zero between launches; NULL = static interleave
+    // Segmented corpus (several indexes concatenated): rows [seg_end[s-1], seg_end[s]) form segment s and
+    // every (segment, query) pair keeps its own shortlist -- a "virtual query" v = s * n_q + q in the outputs.
+    int n_seg;       // >= 1
+    int seg_end[MAX_SEGMENTS];
 };
 
 constexpr int SCHED_SLOTS = 4;  // tile-id ring between the producer and the MMA / epilogue roles
@@ -61,10 +67,11 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
     const int q_bytes = p.n_chunks * N * 128;
     unsigned char* q_s = smem;
     unsigned char* ring = q_s + q_bytes;
+    const int NL = p.n_seg * NQ;  // shortlists: one per (segment, query column)
     uint64_t* lists = reinterpret_cast<uint64_t*>(ring + size_t(p.stages) * STAGE_BYTES);
-    float* thresh_s = reinterpret_cast<float*>(lists + size_t(NQ) * p.cap);
-    int* cnt_s = reinterpret_cast<int*>(thresh_s + NQ);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(cnt_s + NQ);  // 8-byte aligned: NQ is a multiple of 8
+    float* thresh_s = reinterpret_cast<float*>(lists + size_t(NL) * p.cap);
+    int* cnt_s = reinterpret_cast<int*>(thresh_s + NL);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(cnt_s + NL);  // 8-byte aligned: NQ is a multiple of 8
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + p.stages;
     uint64_t* q_full = bars + 2 * p.stages;
@@ -95,9 +102,9 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < NQ) {
-        thresh_s[threadIdx.x] = int(threadIdx.x) < p.nq_here ? -INFINITY : INFINITY;  // unused columns never pass
-        cnt_s[threadIdx.x] = 0;
+    for (int l = threadIdx.x; l < NL; l += THREADS) {
+        thresh_s[l] = (l % NQ) < p.nq_here ? -INFINITY : INFINITY;  // unused columns never pass
+        cnt_s[l] = 0;
     }
     if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
@@ -215,22 +222,29 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
             tcgen05_fence_before();
             mbar_arrive(smem_u32(tmem_empty + a));  // accumulator is in registers: hand TMEM back
 
-            filter_and_push<NQ, HILO, N>(acc, inv, row_ok, uint32_t(row), nq, lists, cnt_s, thresh_s, kp, cap, warp, lane);
+            int seg = 0;  // the row's segment picks the block of lists it competes in (uniform per tile except at a boundary)
+            while (seg < p.n_seg - 1 && row >= p.seg_end[seg]) ++seg;
+            filter_and_push<NQ, HILO, N>(acc, inv, row_ok, uint32_t(row), NL, lists, cnt_s, thresh_s, kp, cap, warp, lane,
+                                         seg * NQ);
         }
 
-        // ---- final cut of every list to its K' best, then emit this CTA's shortlist
+        // ---- final cut of every list to its K' best, then emit this CTA's shortlists
         epi_bar_sync();
-        cut_lists(lists, cnt_s, thresh_s, nq, kp, cap, warp, lane, true);
+        cut_lists(lists, cnt_s, thresh_s, NL, kp, cap, warp, lane, true);
         epi_bar_sync();
-        for (int j = 0; j < nq; ++j) {
-            const int n = cnt_s[j];
-            const size_t o = (size_t(p.q0 + j) * gridDim.x + blockIdx.x) * kp;
-            for (int s = t; s < kp; s += EPI_THREADS) {
-                const uint64_t e = s < n ? lists[size_t(j) * cap + s] : 0ull;
-                p.out_ids[o + s] = e ? int64_t(p.id_base + entry_id(e)) : int64_t(-1);
-                p.out_approx[o + s] = e ? entry_key(e) : -INFINITY;
+        for (int sg = 0; sg < p.n_seg; ++sg) {
+            for (int j = 0; j < nq; ++j) {
+                const int l = sg * NQ + j;
+                const int n = cnt_s[l];
+                const size_t v = size_t(sg) * p.n_q + size_t(p.q0 + j);  // virtual query
+                const size_t o = (v * gridDim.x + blockIdx.x) * kp;
+                for (int s = t; s < kp; s += EPI_THREADS) {
+                    const uint64_t e = s < n ? lists[size_t(l) * cap + s] : 0ull;
+                    p.out_ids[o + s] = e ? int64_t(p.id_base + entry_id(e)) : int64_t(-1);
+                    p.out_approx[o + s] = e ? entry_key(e) : -INFINITY;
+                }
+                if (t == 0) p.out_thresh[v * gridDim.x + blockIdx.x] = thresh_s[l];
             }
-            if (t == 0) p.out_thresh[size_t(p.q0 + j) * gridDim.x + blockIdx.x] = thresh_s[j];
         }
     }
 
@@ -248,8 +262,8 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
 // Lists hold K' + spare entries; spare = 128 never needs a retry (a tile pushes at most 128 rows per query);
 // with many queries per pass the spare shrinks so that the ring keeps enough bytes in flight.
 template <int N, int CH, bool HILO>
-static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* smem_out) {
-    constexpr int NQ = HILO ? N / 2 : N;
+static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* smem_out, int n_seg = 1) {
+    const int NQ = (HILO ? N / 2 : N) * n_seg;  // shortlists per CTA
     const size_t q_bytes = size_t(dim / CHUNK_COLS) * N * 128;
     const size_t base = 1024 /*align slack*/ + q_bytes + size_t(NQ) * 8 + 160;
     const size_t per_stage = size_t(CH) * CHUNK_BYTES + 16;
@@ -284,11 +298,11 @@ static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* s
 template <int N, int CH, bool HILO>
 static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
                   const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
-                  float* out_thresh, int n_lists, int* sched, cudaStream_t st) {
+                  float* out_thresh, int n_lists, int* sched, cudaStream_t st, int n_seg = 1, const int64_t* seg_end = nullptr) {
     constexpr int NQ = HILO ? N / 2 : N;
     int spare = 0, stages = 0;
     size_t smem = 0;
-    if (!plan<N, CH, HILO>(dim, kprime, &spare, &stages, &smem)) {
+    if (!plan<N, CH, HILO>(dim, kprime, &spare, &stages, &smem, n_seg)) {
         set_error("scan_tc: dim=%d kprime=%d does not fit shared memory with N=%d", dim, kprime, N);
         return TT_ERR_UNSUPPORTED;
     }
@@ -307,6 +321,8 @@ static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, c
     p.out_thresh = out_thresh;
     p.cap = kprime + spare;
     p.stages = stages;
+    p.n_seg = n_seg;
+    for (int i = 0; i < MAX_SEGMENTS; ++i) p.seg_end[i] = (seg_end && i < n_seg) ? int(seg_end[i]) : int(n_rows);
 
     CUtensorMap map_c, map_qhi, map_qlo;
     int rc = make_map(&map_c, corpus, n_rows, dim, stride, TILE_ROWS, CH);
@@ -358,6 +374,19 @@ int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, 
     if (n_q <= 32 || !tc::plan<64, 1, false>(dim, kprime, &sp, &sg, &sm)) TT_TC(32, 2, false);
     TT_TC(64, 1, false);
 #undef TT_TC
+}
+
+// Segmented corpus: n_seg <= 16 row ranges, up to 8 queries per pass (hi+lo), one shortlist per (segment, query).
+int scan_tc_segmented(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
+                      const void* q_lo, int n_q, int kprime, int64_t id_base, const int64_t* seg_end, int n_seg,
+                      int64_t* out_ids, float* out_approx, float* out_thresh, int n_lists, int* sched, cudaStream_t st) {
+    if (!scan_tc_supported(n_rows, dim, stride, kprime, corpus) || !q_lo || n_seg < 1 || n_seg > tc::MAX_SEGMENTS) {
+        set_error("scan_tc_segmented: unsupported shape (n_rows=%lld dim=%d stride=%lld kprime=%d n_seg=%d)",
+                  (long long)n_rows, dim, (long long)stride, kprime, n_seg);
+        return TT_ERR_UNSUPPORTED;
+    }
+    return tc::launch<16, 2, true>(corpus, n_rows, dim, stride, inv_norm, q_hi, q_lo, n_q, kprime, id_base, out_ids,
+                                   out_approx, out_thresh, n_lists, sched, st, n_seg, seg_end);
 }
 
 }  // namespace tt

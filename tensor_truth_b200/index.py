@@ -47,6 +47,8 @@ def gemm_kprime(k: int) -> int:
 
 
 _NULL_CTX = contextlib.nullcontext()
+_CAPTURE_LOCK = threading.Lock()  # one CUDA-graph capture at a time per process: torch.cuda.graph() synchronises the device on
+                                  # entry, which is an error while another thread's stream is capturing
 
 
 @dataclass
@@ -196,6 +198,10 @@ class DeviceIndex:
             self._ws[key] = w
         return w
 
+    def _result_rows(self, b: int) -> int:
+        """Result lists a batch of b queries produces (SegmentedIndex: one per segment and query)."""
+        return b
+
     def _on_device(self):
         """Context that makes this index's GPU current -- a no-op object when it already is (the common case)."""
         if torch.cuda.current_device() == self._dev_index:
@@ -276,11 +282,12 @@ class DeviceIndex:
         # cosine: proven iff margin > eps;  L2: the bound already contains eps, proven iff margin > 0
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if l2 else eps, bool(hi_only))
 
-    def search_exact(self, q: torch.Tensor, k: int, out: Optional[dict] = None) -> SearchResult:
+    def search_exact(self, q: torch.Tensor, k: int, out: Optional[dict] = None, rows: Optional[tuple] = None) -> SearchResult:
         """fp64 scoring of every row (CUDA cores): certificate-failure fallback, the chroma_l2_exp path and the
-        on-GPU secondary oracle."""
+        on-GPU secondary oracle.  ``rows = (lo, hi)`` restricts the scan to that local row range (one segment)."""
         q = self._check_queries(q)
         b = int(q.shape[0])
+        lo, hi = rows if rows is not None else (0, self.n_rows)
         dev = self.device
         if out is not None:
             keys, scores, ids = out["keys"], out["scores"], out["ids"]
@@ -292,8 +299,8 @@ class DeviceIndex:
         with torch.cuda.device(dev):
             nbytes = int(self.lib.tt_scan_exact_workspace_bytes(dev.index or 0, b, k))
             ws = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
-            check(self.lib.tt_scan_exact_f64(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
-                                             self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q), b, k,
+            check(self.lib.tt_scan_exact_f64(ptr(src[lo:hi]), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
+                                             hi - lo, self.dim, self._row_stride(src), self.id_base + lo, ptr(q), b, k,
                                              self.score_mode, ptr(keys), ptr(scores), ptr(ids), ptr(ws), ws.numel(),
                                              self._stream()))
         return SearchResult(keys, scores, ids, None)
@@ -386,10 +393,13 @@ class DeviceIndex:
         g["calls"] += 1
         if g["calls"] <= GRAPH_AFTER:
             return None
+        if not _CAPTURE_LOCK.acquire(blocking=False):  # someone else is capturing: stay eager this time, try again later
+            return None
         try:
-            rec = self._record(b, k, merged)
+            vb = self._result_rows(b)
+            rec = self._record(vb, k, merged)
             d = rec["d"]
-            w = dict(self._buffers(b, k))
+            w = dict(self._buffers(vb, k))
             w["margin"] = d["margin"]
             if not merged:
                 w["ids"], w["scores"] = d["ids"], d["scores"]
@@ -410,13 +420,17 @@ class DeviceIndex:
         except Exception as exc:  # capture refused (driver, another thread capturing, ...): keep the eager path
             import warnings
 
-            warnings.warn(f"tensor_truth_b200: CUDA-graph capture of the retrieve pipeline failed ({exc}); staying eager")
-            g["dead"] = True
+            g["failures"] = g.get("failures", 0) + 1
+            g["dead"] = g["failures"] >= 3  # e.g. another thread synchronised the device mid-capture: worth another try
+            if g["dead"]:
+                warnings.warn(f"tensor_truth_b200: CUDA-graph capture of the retrieve pipeline failed ({exc}); staying eager")
             try:
                 torch.cuda.synchronize(self.device)
             except Exception:
                 pass
             return None
+        finally:
+            _CAPTURE_LOCK.release()
 
     def retrieve_host(self, q_host: torch.Tensor, k: int, ratio_thresh: float = 0.5, merge: bool = True):
         """Query embeddings in host memory -> merged ``(ids, scores, lens)`` in host memory (numpy).
@@ -439,9 +453,10 @@ class DeviceIndex:
             else:
                 q = q_host.to(self.device, torch.float32, non_blocking=True)
                 q = self._check_queries(q)
-                rec = self._record(b, k, merged)
+                vb = self._result_rows(b)
+                rec = self._record(vb, k, merged)
                 d, h = rec["d"], rec["h"]
-                w = dict(self._buffers(b, k))
+                w = dict(self._buffers(vb, k))
                 w["margin"] = d["margin"]
                 if not merged:
                     w["ids"], w["scores"] = d["ids"], d["scores"]

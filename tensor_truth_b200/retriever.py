@@ -162,3 +162,85 @@ def build_retriever(corpus, tree, similarity_top_k: int = 10, embed_model: Any =
     table = NodeTable(nodes=nodes) if nodes is not None else None
     base = B200VectorIndexRetriever(index, similarity_top_k, embed_model, table)
     return B200AutoMergingRetriever(base, None, simple_ratio_thresh)
+
+
+class B200MultiIndexRetriever(_RetrieverBase):
+    """``MultiIndexRetriever(retrievers=[AutoMergingRetriever(...) per index])`` (rag_engine.py:368-526, built at
+    :688-692) over ONE ``SegmentedIndex`` holding all the indexes: the query is embedded once and one pass of the
+    device pipeline answers every index, instead of m vector-store queries on a thread pool (:416-461).
+
+    What the reference class does to the per-index results is kept as it is: every node is tagged
+    ``metadata["_source_index"] = idx`` (:432-450); with more than one index and ``balance_strategy ==
+    "top_k_per_index"`` each index keeps its first ``max(1, total // n_indexes)`` nodes and the union is sorted by
+    ``score or 0.0``, descending, stable (:463-507); results are cached per query *string* in an LRU (:399-404) that
+    ``clear_cache()`` empties (:520-526).  A segment that returns nothing simply contributes nothing (:453-455 is the
+    reference's "skip a failing index")."""
+
+    def __init__(self, index, similarity_top_k: int = 10, embed_model: Any = None,
+                 node_tables: Optional[Sequence[NodeTable]] = None, simple_ratio_thresh: float = 0.5,
+                 enable_cache: bool = True, cache_size: int = 128, balance_strategy: str = "top_k_per_index",
+                 auto_merge: bool = True):
+        from functools import lru_cache
+
+        self.index = index
+        self.similarity_top_k = int(similarity_top_k)
+        self.embed_model = embed_model
+        self.simple_ratio_thresh = float(simple_ratio_thresh)
+        self.enable_cache = enable_cache
+        self.balance_strategy = balance_strategy
+        self.auto_merge = bool(auto_merge and index.tree is not None)
+        if node_tables is None:
+            trees = index.seg_trees or [None] * index.n_seg
+            node_tables = [NodeTable(node_ids=getattr(t, "node_ids", None) if t is not None else None) for t in trees]
+        if len(node_tables) != index.n_seg:
+            raise ValueError("one node table per segment")
+        self.node_tables = list(node_tables)
+        self._embedder = B200VectorIndexRetriever.__new__(B200VectorIndexRetriever)  # reuse its bundle -> tensor logic
+        self._embedder.embed_model = embed_model
+        self._pending: dict = {}
+        self._retrieve_cached = lru_cache(maxsize=cache_size)(self._retrieve_impl) if enable_cache else self._retrieve_impl
+
+    def _retrieve_impl(self, query_text: str) -> List[NodeWithScore]:
+        qb = self._pending.pop((threading.get_ident(), query_text), None) or QueryBundle(query_str=query_text)
+        q = self._embedder._query_tensor(qb)
+        ids, scores, lens = self.index.retrieve_host(q, self.similarity_top_k, self.simple_ratio_thresh, merge=self.auto_merge)
+        combined: List[NodeWithScore] = []
+        for s in range(self.index.n_seg):
+            n = int(lens[s, 0])
+            if n < 0:
+                raise RuntimeError("auto-merge output overflow")
+            for o, sc in zip(ids[s, 0, :n], scores[s, 0, :n]):
+                seg, local = self.index.segment_of(int(o))
+                node = self.node_tables[seg](local)
+                if isinstance(getattr(node, "metadata", None), dict):
+                    node.metadata["_source_index"] = s
+                combined.append(NodeWithScore(node=node, score=float(sc)))
+        if self.index.n_seg > 1 and self.balance_strategy == "top_k_per_index":
+            combined = self._balance_top_k_per_index(combined)
+        return combined
+
+    @staticmethod
+    def _balance_top_k_per_index(nodes: List[NodeWithScore]) -> List[NodeWithScore]:
+        by_index: dict = {}
+        for n in nodes:
+            by_index.setdefault(n.node.metadata.get("_source_index", 0), []).append(n)
+        if not by_index:
+            return []
+        limit = max(1, len(nodes) // len(by_index))
+        kept = [n for group in by_index.values() for n in group[:limit]]
+        kept.sort(key=lambda n: n.score if n.score else 0.0, reverse=True)
+        return kept
+
+    def _retrieve(self, query_bundle: QueryBundle) -> List[NodeWithScore]:
+        # the cache key is the query string, like the reference's; a bundle that already carries an embedding hands it
+        # to the (possibly cached-away) implementation through a side slot instead of being re-embedded
+        if getattr(query_bundle, "embedding", None) is not None:
+            self._pending[(threading.get_ident(), query_bundle.query_str)] = query_bundle
+        try:
+            return self._retrieve_cached(query_bundle.query_str)
+        finally:
+            self._pending.pop((threading.get_ident(), query_bundle.query_str), None)
+
+    def clear_cache(self) -> None:
+        if self.enable_cache and hasattr(self._retrieve_cached, "cache_clear"):
+            self._retrieve_cached.cache_clear()

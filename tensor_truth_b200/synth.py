@@ -98,7 +98,7 @@ class SynthCorpus:
         v = v / v.norm(dim=1, keepdim=True).clamp_min(1e-30)
         c = v.to(torch.bfloat16)
         rows = c.shape[0]
-        dup = torch.arange(1023, rows, 1024, device=self.device)
+        dup = torch.arange(1023, max(rows, 1023), 1024, device=self.device)
         if dup.numel():
             c[dup] = c[dup - 1]
         cf = c.to(torch.float32)

@@ -133,3 +133,55 @@ def tree_from_relations(node_ids, parent, children, prev, nxt, leaf_order) -> No
         if b is not None and b in ordinal:
             next_id[o] = ordinal[b]
     return NodeTree(parent_of, child_count, prev_id, next_id, len(leaf_order), [], list(order))
+
+
+def concat_trees(trees: List[NodeTree]):
+    """Several indexes' trees as ONE ordinal space (multi-index as one segmented corpus).
+
+    Combined ordinals: the leaves of all segments first, in segment order (ordinal == row of the concatenated
+    corpus), then the internal nodes of segment 0, of segment 1, ...  Returns ``(tree, leaf_off, internal_off)``:
+    a leaf ``o`` of segment ``s`` becomes ``leaf_off[s] + o``, an internal node ``o`` (``o >= n_leaf_s``) becomes
+    ``internal_off[s] + o - n_leaf_s``.  ``locate`` maps back."""
+    n_leaf_total = sum(t.n_leaf for t in trees)
+    leaf_off, internal_off = [], []
+    lo, io = 0, n_leaf_total
+    for t in trees:
+        leaf_off.append(lo)
+        internal_off.append(io)
+        lo += t.n_leaf
+        io += t.n_nodes - t.n_leaf
+    n = io
+    if n >= 2**31:
+        raise ValueError("node count exceeds int32 ordinals")
+    parent_of = np.full(n, -1, dtype=np.int32)
+    child_count = np.zeros(n, dtype=np.int32)
+    prev_id = np.full(n, -1, dtype=np.int32)
+    next_id = np.full(n, -1, dtype=np.int32)
+    node_ids: Optional[List[str]] = [""] * n if all(t.node_ids is not None for t in trees) else None
+    for s, t in enumerate(trees):
+        nl = t.n_leaf
+
+        def remap(a, nl=nl, s=s):
+            a = a.astype(np.int64)
+            return np.where(a < 0, -1, np.where(a < nl, a + leaf_off[s], a - nl + internal_off[s])).astype(np.int32)
+
+        dst_leaf = slice(leaf_off[s], leaf_off[s] + nl)
+        dst_int = slice(internal_off[s], internal_off[s] + t.n_nodes - nl)
+        for src, dst in ((t.parent_of, parent_of), (t.prev_id, prev_id), (t.next_id, next_id)):
+            m = remap(src)
+            dst[dst_leaf] = m[:nl]
+            dst[dst_int] = m[nl:]
+        child_count[dst_leaf] = t.child_count[:nl]
+        child_count[dst_int] = t.child_count[nl:]
+        if node_ids is not None:
+            node_ids[dst_leaf] = t.node_ids[:nl]
+            node_ids[dst_int] = t.node_ids[nl:]
+    return NodeTree(parent_of, child_count, prev_id, next_id, n_leaf_total, [], node_ids), leaf_off, internal_off
+
+
+def locate(ordinal: int, trees: List[NodeTree], leaf_off: List[int], internal_off: List[int]):
+    """Combined ordinal -> ``(segment, ordinal within that segment's own tree)``."""
+    n_leaf_total = leaf_off[-1] + trees[-1].n_leaf
+    offs = leaf_off if ordinal < n_leaf_total else internal_off
+    s = int(np.searchsorted(np.asarray(offs), ordinal, side="right")) - 1
+    return (s, ordinal - leaf_off[s]) if ordinal < n_leaf_total else (s, ordinal - internal_off[s] + trees[s].n_leaf)

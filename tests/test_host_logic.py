@@ -195,3 +195,77 @@ def test_query_is_embedded_once_across_per_index_retrievers():
     assert Embedder.calls == 1
     assert all(o.shape == (1, 16) and float(o[0, 0]) == 0.25 for o in outs)
     assert qb.embedding == [0.25] * 16
+
+
+# --------------------------------------------------------------------------- multi-index as one segmented corpus (N4), host side
+def test_concat_trees_keeps_every_relation_and_maps_back():
+    from tensor_truth_b200.tree import concat_trees, locate
+
+    trees = [build_uniform_tree(50, 3, 1), build_uniform_tree(7, 3, 2), build_uniform_tree(120, 2, 3)]
+    t, leaf_off, int_off = concat_trees(trees)
+    t.validate()
+    assert t.n_leaf == 177 and t.n_nodes == sum(x.n_nodes for x in trees)
+    seen = set()
+    for o in range(t.n_nodes):
+        s, l = locate(o, trees, leaf_off, int_off)
+        seen.add((s, l))
+        assert (o < t.n_leaf) == (l < trees[s].n_leaf)
+        assert t.child_count[o] == trees[s].child_count[l]
+        for comb, own in ((t.parent_of, trees[s].parent_of), (t.prev_id, trees[s].prev_id), (t.next_id, trees[s].next_id)):
+            if own[l] < 0:
+                assert comb[o] == -1
+            else:
+                assert locate(int(comb[o]), trees, leaf_off, int_off) == (s, int(own[l]))
+    assert len(seen) == t.n_nodes
+
+
+def test_b200_multi_index_retriever_matches_reference_golden_cases():
+    """The combining logic of B200MultiIndexRetriever on the scenarios recorded from the reference's own
+    MultiIndexRetriever (tests/golden/multi_index_ref.json), with a stand-in for the device index."""
+    import json
+    import os
+
+    from tensor_truth_b200.retriever import B200MultiIndexRetriever, NodeTable
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "multi_index_ref.json")) as f:
+        cases = json.load(f)["cases"]
+
+    class FakeSegmented:
+        tree = object()
+        seg_trees = None
+
+        def __init__(self, lists):
+            self.lists = lists
+            self.n_seg = len(lists)
+            self.off = np.cumsum([0] + [len(x) for x in lists])
+
+        def segment_of(self, o):
+            s = int(np.searchsorted(self.off, o, side="right")) - 1
+            return s, o - int(self.off[s])
+
+        def retrieve_host(self, q, k, ratio, merge=True):
+            w = max(1, max(len(x) for x in self.lists))
+            ids = np.full((self.n_seg, 1, w), -1, np.int64)
+            sc = np.zeros((self.n_seg, 1, w))
+            lens = np.zeros((self.n_seg, 1), np.int32)
+            for s, x in enumerate(self.lists):
+                lens[s, 0] = len(x)
+                for j, (_, score) in enumerate(x):
+                    ids[s, 0, j] = self.off[s] + j
+                    sc[s, 0, j] = score
+            return ids, sc, lens
+
+    ran = 0
+    for case in cases:
+        if any(x == "raise" for x in case["lists"]) or any(sc is None for x in case["lists"] for _, sc in x):
+            continue  # a device index neither raises per segment nor reports a missing score
+        idx = FakeSegmented(case["lists"])
+        tables = [NodeTable(node_ids=[i for i, _ in x]) for x in case["lists"]]
+        m = B200MultiIndexRetriever(idx, 10, embed_model=SimpleNamespace(get_agg_embedding_from_queries=lambda s: [0.0] * 8),
+                                    node_tables=tables, balance_strategy=case["strategy"])
+        got = [[n.node.id_, n.score, n.node.metadata["_source_index"]] for n in m.retrieve("the query")]
+        if case["strategy"] == "none":
+            got = sorted(got, key=lambda t: t[0])
+        assert got == case["expected"], case["name"]
+        ran += 1
+    assert ran >= 15
