@@ -220,33 +220,95 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
     const int b = blockIdx.x;
     if (x.wait_world) xchg_wait(x);
     const int total = packed ? n_in : n_lists * k_in;
-    int carried = 0;  // entries [0, carried) of s hold the running top-k
-    for (int base = 0; base < total || base == 0;) {
-        const int room = chunk - carried;
-        const int take = min(room, total - base);
-        for (int i = threadIdx.x; i < room; i += SEL_THREADS) {
-            uint64_t e = 0ull;
-            if (i < take) {
-                const int j = base + i;
-                if (packed) {
-                    e = packed[size_t(b) * n_in + j];
-                } else {
-                    const int l = j / k_in, t = j - l * k_in;
-                    const size_t o = size_t(b) * k_in + t;
-                    const int64_t id = in_ids[size_t(l) * ids_stride + o];
-                    e = id >= 0 ? pack_entry(in_keys[size_t(l) * keys_stride + o], uint32_t(id)) : 0ull;
+    auto load = [&](int j) -> uint64_t {
+        if (packed) return packed[size_t(b) * n_in + j];
+        const int l = j / k_in, t = j - l * k_in;
+        const size_t o = size_t(b) * k_in + t;
+        const int64_t id = in_ids[size_t(l) * ids_stride + o];
+        return id >= 0 ? pack_entry(in_keys[size_t(l) * keys_stride + o], uint32_t(id)) : 0ull;
+    };
+    int lim = chunk;  // s[0, lim) is sorted when the selection is done
+    if (total > chunk) {
+        // More candidates than one sort holds (k = 200 over 148 shortlists of 128): find the k-th largest packed entry
+        // with an MSB-first radix select over the input (8 bits per pass, L2-resident re-reads, stops as soon as the
+        // digit bin holds exactly the entries still wanted), then sort only the k survivors.
+        __shared__ int hist[256];
+        __shared__ int sh_bin, sh_want, sh_n;
+        uint64_t prefix = 0ull, mask = 0ull;
+        int want = k;
+        if (threadIdx.x == 0) sh_n = 0;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+            __syncthreads();
+            for (int j = threadIdx.x; j < total; j += SEL_THREADS) {
+                const uint64_t e = load(j);
+                if ((e & mask) == prefix) atomicAdd(&hist[int(e >> shift) & 255], 1);
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {  // bins from 255 down: lane l owns bins 255-8l .. 248-8l
+                const int t = threadIdx.x;
+                int local[8], sum = 0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    local[u] = hist[255 - 8 * t - u];
+                    sum += local[u];
+                }
+                int inc = sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (t >= d) inc += o;
+                }
+                int before = inc - sum;
+                if (before < want && want <= inc) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (before < want && want <= before + local[u]) {
+                            sh_bin = 255 - 8 * t - u;
+                            sh_want = want - before;
+                        }
+                        before += local[u];
+                    }
                 }
             }
-            s[carried + i] = e;
+            __syncthreads();
+            const int bin = sh_bin;
+            want = sh_want;
+            prefix |= uint64_t(bin) << shift;
+            mask |= 0xffull << shift;
+            if (hist[bin] == want) break;
+            __syncthreads();
+        }
+        // distinct entries: exactly k pass; if the k-th largest is an empty slot (fewer than k candidates) all real ones do
+        for (int j = threadIdx.x; j < total; j += SEL_THREADS) {
+            const uint64_t e = load(j);
+            if (e != 0ull && (e & mask) >= prefix) {
+                const int slot = atomicAdd(&sh_n, 1);
+                if (slot < chunk) s[slot] = e;
+            }
         }
         __syncthreads();
-        block_bitonic_sort_desc(s, chunk);
-        carried = min(k, chunk);
-        base += take;
-        if (take == 0) break;
+        const int n_sel = min(sh_n, chunk);
+        lim = 32;
+        while (lim < n_sel || lim < k) lim <<= 1;  // <= chunk: chunk is a power of two >= 2k
+        for (int i = n_sel + threadIdx.x; i < lim; i += SEL_THREADS) s[i] = 0ull;
+        __syncthreads();
+        block_bitonic_sort_desc(s, lim);
+    } else {
+        int carried = 0;  // entries [0, carried) of s hold the running top-k
+        for (int base = 0; base < total || base == 0;) {
+            const int room = chunk - carried;
+            const int take = min(room, total - base);
+            for (int i = threadIdx.x; i < room; i += SEL_THREADS) s[carried + i] = i < take ? load(base + i) : 0ull;
+            __syncthreads();
+            block_bitonic_sort_desc(s, chunk);
+            carried = min(k, chunk);
+            base += take;
+            if (take == 0) break;
+        }
     }
     for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
-        const uint64_t e = i < chunk ? s[i] : 0ull;
+        const uint64_t e = i < lim ? s[i] : 0ull;
         const size_t o = size_t(b) * k + i;
         const float key = e ? entry_key(e) : -INFINITY;
         if (out_keys) out_keys[o] = key;
@@ -268,7 +330,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
         if (l2c) qq = block_sqnorm(cert.q + size_t(b) * cert.dim, cert.dim, red64);
         if (threadIdx.x == 0) {
             for (int w = 1; w < SEL_THREADS / 32; ++w) m = fmaxf(m, red[w]);
-            const uint64_t ek = (k - 1 < chunk) ? s[k - 1] : 0ull;
+            const uint64_t ek = (k - 1 < lim) ? s[k - 1] : 0ull;
             float margin;
             if (m == -INFINITY) margin = INFINITY;            // nothing was left out of any shortlist
             else if (!ek) margin = -INFINITY;                 // fewer than k candidates although rows were dropped
