@@ -648,3 +648,41 @@ def test_graph_replay_still_repairs_unproven_queries(monkeypatch):
         ids, scores, lens = idx.retrieve_host(torch.from_numpy(q[i:i + 1]), 10, merge=False)
         assert (ids[0] == ids_o[i]).all() and (scores[0] == sc_o[i].astype(np.float64)).all()
     assert idx._ws[("graph", 1, 10, 0.5, False)]["graph"] is not None and idx.fallbacks >= 4
+
+
+def test_c2_full_size_10m_rows_properties():
+    """BASELINE configs[1] at its full size (10M x 1024, 20.5 GB in HBM): too large for the CPU oracle, so checked through
+    size-independent properties -- the certified path equals the exact fp64 scan (batch-1, batch-64 and a wide batch
+    through the GEMM-shaped scan), a stored row retrieves itself, and the merged result is what the oracle's auto-merge
+    makes of the device top-k."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2**30:
+        pytest.skip("needs ~25 GB of free HBM")
+    n = 10_000_000
+    sc = SynthCorpus(n, 1024, levels=3, seed=1234, device="cuda")
+    corpus, inv = sc.rows(0, n)
+    q = sc.finish_queries(sc.queries(128, lookup=lambda t: corpus[t])).cuda()
+    idx = _index(corpus, sc.tree, inv_norm=inv)
+    ex = idx.search_exact(q[:8], 10)
+    for b in (1, 8):
+        r = idx.search_certified(q[:b], 10)
+        torch.cuda.synchronize()
+        assert torch.equal(r.ids, ex.ids[:b]) and torch.equal(r.scores, ex.scores[:b])
+    r64 = idx.search_certified(q[:64], 10)       # one pass of the 64-query pair kernel
+    r128 = idx.search_certified(q, 10)           # the GEMM-shaped scan
+    torch.cuda.synchronize()
+    assert torch.equal(r64.ids[:8], ex.ids) and torch.equal(r64.scores[:8], ex.scores)
+    assert torch.equal(r128.ids[:64], r64.ids) and torch.equal(r128.scores[:64], r64.scores)
+    assert idx.fallbacks == 0
+    t = torch.tensor([0, 4_999_999, n - 1], device="cuda")
+    rs = idx.search(corpus[t].float(), 10)
+    torch.cuda.synchronize()
+    assert _np(rs.ids)[:, 0].tolist() == [0, 4_999_999, n - 1]
+    m = idx.automerge(r64.ids, r64.scores)
+    torch.cuda.synchronize()
+    got = _merged_lists(m)
+    ids, scores = _np(r64.ids), _np(r64.scores)
+    tr = sc.tree
+    for b in range(0, 64, 9):
+        pairs = [(int(o), float(s)) for o, s in zip(ids[b], scores[b]) if o >= 0]
+        assert got[b] == oracle.auto_merge(pairs, tr.parent_of, tr.child_count, tr.prev_id, tr.next_id)
