@@ -1,0 +1,43 @@
+"""bench.py's output contract, as far as it can be checked without a GPU: the CPU arm (`--impl reference`) prints ONE
+JSON line with the keys the driver reads, and the GPU arm refuses to run without a CUDA device instead of falling back."""
+
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, cwd=ROOT,
+                          timeout=600)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    p = _run("--impl", "reference", "--rows", "131072", "--steps", "3", "--warmup", "3", "--cpu-sample-rows", "65536")
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["warmup"] >= 3 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["data"] == "synthetic" and d["gpu_launches"] == 0
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       capture_output=True, text=True, cwd=ROOT, env=env, timeout=120)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_gpu_arm_does_not_fall_back_to_the_cpu():
+    import torch
+
+    if torch.cuda.is_available():
+        return  # the GPU arm itself is exercised on the GPU box (gpurun)
+    p = _run("--steps", "1", "--rows", "4096", "--skip", "batch64,wide,cpu")
+    assert p.returncode != 0 and p.stdout.strip() == ""
