@@ -310,7 +310,8 @@ def run_b200(args):
                    "steps": steps64, "serial_value": steps64 * 64 / (ser64["ms"] / 1e3), "scan_ms_per_step": ser64["scan_ms"],
                    "hbm_frac": float(hi - lo) * DIM * 2 / (ser64["scan_ms"] / 1e3) / 1e9 / peak,
                    "certificate_failures": ser64["bad"] + pip64["bad"], "min_margin": pip64["min_margin"],
-                   "eps": pip64["eps"], "mode": "hi-only bf16 queries, 64 per corpus pass"}
+                   "eps": pip64["eps"], "mode": "hi-only bf16 queries, 64 per corpus pass",
+                   "kernel": "scan_gemm_kernel<64,2>" if idx._use_gemm(64) else "scan_tc2_kernel<64,2>"}
 
     # ---- wide batch (BASELINE configs[3] shape: 16k concurrent queries, top-100): the tensor-bound regime, served by
     #      the GEMM-shaped stage 1 (scan_gemm.cu).  Roofline: dense bf16 tensor throughput.

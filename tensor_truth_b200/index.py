@@ -35,8 +35,8 @@ EPS_F32_CORPUS = 4.2e-3    # fp32 master scanned through a bf16 shadow: + 2^-8 c
 EPS_HI_ONLY = 3.95e-3      # added when the query travels as bf16 hi only (|q - bf16(q)| <= 2^-8 |q|)
 HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first (64 queries per corpus pass)
 MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist workspace: 148 * K' * 12 B per query)
-GEMM_ABOVE = 65            # hi-only batches at least this large (more than one pass of the 64-query pair kernel) take the
-                           # GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass per 4096 queries, one list per query
+GEMM_ABOVE = 33            # hi-only batches at least this large take the GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass
+                           # per 4096 queries, one list per query (64 queries: 3.04 ms at 10M rows vs 3.35 ms for the pair kernel)
 GRAPH_AFTER = 3            # retrieve_host: eager calls of a (batch, k) shape before its pipeline is captured in a CUDA graph
 GEMM_SLICE = 4096          # queries per GEMM-shaped corpus pass (candidate buffers: 16 K' * 8 B per query)
 

@@ -214,7 +214,7 @@ def test_c1_oracle_live_and_error_bound(c1, vname, variant):
         torch.cuda.synchronize()
         assert (_np(r1.ids)[0] == ids_o[b]).all() and (_np(r1.scores)[0] == sc_o[b]).all()
     # stage-1 approximate scores vs exact fp64 cosine of the same rows
-    w = idx._buffers(64, 10)
+    w = idx._buffers(64, 10, hi_only=False)
     idx.search(qd, 10, hi_only=False)
     torch.cuda.synchronize()
     cand, approx = _np(w["cand_ids"]), _np(w["cand_approx"])
@@ -229,9 +229,13 @@ def test_c1_oracle_live_and_error_bound(c1, vname, variant):
     assert worst < idx.eps / 4, worst
 
 
-def test_c1_batch64_hi_only_single_pass(c1):
+@pytest.mark.parametrize("stage1", ["gemm64", "pair"])
+def test_c1_batch64_hi_only_single_pass(c1, stage1, monkeypatch):
     """64 queries in ONE corpus pass (bf16 hi halves only, N = 64 MMA columns): same exact answer, wider certificate,
-    and the repair ladder (hi+lo re-scan, then exact scan) for queries the hi-only certificate cannot prove."""
+    and the repair ladder (hi+lo re-scan, then exact scan) for queries the hi-only certificate cannot prove.  Both
+    64-column kernels: the GEMM-shaped scan (default) and the CTA-pair kernel with on-chip lists (TT_NO_GEMM)."""
+    if stage1 == "pair":
+        monkeypatch.setenv("TT_NO_GEMM", "1")
     tree, bits, inv, q = c1
     ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
     idx = _index(bits, tree, variant=_lib.SCAN_TCGEN05)
@@ -668,7 +672,7 @@ def test_c2_full_size_10m_rows_properties():
         r = idx.search_certified(q[:b], 10)
         torch.cuda.synchronize()
         assert torch.equal(r.ids, ex.ids[:b]) and torch.equal(r.scores, ex.scores[:b])
-    r64 = idx.search_certified(q[:64], 10)       # one pass of the 64-query pair kernel
+    r64 = idx.search_certified(q[:64], 10)       # one pass, 64 MMA columns
     r128 = idx.search_certified(q, 10)           # the GEMM-shaped scan
     torch.cuda.synchronize()
     assert torch.equal(r64.ids[:8], ex.ids) and torch.equal(r64.scores[:8], ex.scores)
