@@ -133,6 +133,7 @@ class ShardedIndex:
         self._out: dict = {}
         self.group = group
         self._peers: dict = {}
+        self._host_bufs: dict = {}
         # peer pushes need symmetric memory (NVLink peer mappings); without it the exchange is an NCCL all-gather
         self.transport = "nccl" if os.environ.get("TT_EXCHANGE", "peer") == "nccl" or self.plumbing.world == 1 else "peer"
 
@@ -215,13 +216,20 @@ class ShardedIndex:
         local = self.local
         q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
         b = int(q.shape[0])
-        margins = torch.empty((b,), dtype=torch.float32, device=self.device)
+        hb = self._host_bufs.get(b)
+        if hb is None:  # margins on the device + a pinned host mirror + the event the certificate check waits on
+            hb = self._host_bufs[b] = (torch.empty((b,), dtype=torch.float32, device=self.device),
+                                       torch.empty((b,), dtype=torch.float32).pin_memory(), torch.cuda.Event())
+        margins, margins_h, ev = hb
         send, recv, keys, ids = self.plumbing.buffers(b, k)
         self._margins = margins
         r = self._local_search(q, k, keys, ids)
-        bad = torch.nonzero(~(margins > r.eps)).flatten()
+        margins_h.copy_(margins, non_blocking=True)
+        ev.record()
+        ev.synchronize()
+        bad = (~(margins_h > r.eps)).nonzero().flatten()
         if bad.numel():  # rank-local repair (writes into the send record); the exchange below is reached by every rank
-            local._repair(q, k, r, bad, hi_lo_first=r.hi_only)
+            local._repair(q, k, r, bad.to(self.device), hi_lo_first=r.hi_only)
         pb = self.peers(b, k)
         if pb is None:
             self.plumbing.exchange(send, recv)
