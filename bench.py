@@ -193,8 +193,11 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device(f"cuda:{local_rank}")
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; rank 0 must print ONE line
+        # NCCL writes its version banner (any NCCL_DEBUG level >= VERSION, which this image sets) and its logs to stdout;
+        # rank 0 must print ONE line there
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=device)
     _lib.lib()  # fail loudly if the CUDA library is missing
 
