@@ -690,3 +690,47 @@ def test_c2_full_size_10m_rows_properties():
     for b in range(0, 64, 9):
         pairs = [(int(o), float(s)) for o, s in zip(ids[b], scores[b]) if o >= 0]
         assert got[b] == oracle.auto_merge(pairs, tr.parent_of, tr.child_count, tr.prev_id, tr.next_id)
+
+
+@pytest.mark.parametrize("seed,levels,fan_hi,k", [(1, 4, 3, 24), (2, 3, 2, 40), (3, 4, 4, 12), (4, 5, 2, 64), (5, 3, 6, 200)])
+def test_automerge_randomised_against_the_oracle(seed, levels, fan_hi, k):
+    """Thousands of random retrieval lists over small, bushy trees -- far more fill-ins, duplicate inserts, ties and
+    multi-level cascades than clustered top-k lists ever produce -- in ONE launch; ids and float64 scores must equal the
+    sequential restatement (oracle/automerge.py) bit for bit, for several ratio thresholds."""
+    rng = np.random.default_rng(seed)
+    n_leaf = 400
+    tree = build_uniform_tree(n_leaf, levels, seed, fan_lo=2, fan_hi=fan_hi)
+    n_cases = 800
+    ids = np.full((n_cases, k), -1, np.int64)
+    sc = np.zeros((n_cases, k), np.float32)
+    for c in range(n_cases):
+        n = int(rng.integers(1, k + 1))
+        span = int(rng.integers(n, min(n_leaf, 4 * n) + 1))     # dense windows of leaves: siblings land together
+        lo = int(rng.integers(0, n_leaf - span + 1))
+        picked = lo + rng.choice(span, size=min(n, span), replace=False)
+        s = np.round(rng.uniform(0.2, 0.9, size=picked.size), 2 if c % 3 else 1).astype(np.float32)  # coarse: many ties
+        order = np.lexsort((picked, -s))                          # what stage 2 emits: score desc, id asc
+        ids[c, :picked.size], sc[c, :picked.size] = picked[order], s[order]
+    arrs = [torch.from_numpy(a).cuda() for a in (tree.parent_of, tree.child_count, tree.prev_id, tree.next_id)]
+    d_ids, d_sc = torch.from_numpy(ids).cuda(), torch.from_numpy(sc).cuda()
+    max_out = 2 * k
+    L = _lib.lib()
+    merged_something = 0
+    for thresh in (0.5, 0.34, 0.75):
+        o_ids = torch.empty((n_cases, max_out), dtype=torch.int64, device="cuda")
+        o_sc = torch.empty((n_cases, max_out), dtype=torch.float64, device="cuda")
+        o_len = torch.empty((n_cases,), dtype=torch.int32, device="cuda")
+        _lib.check(L.tt_automerge(_lib.ptr(d_ids), _lib.ptr(d_sc), n_cases, k, *[_lib.ptr(a) for a in arrs], tree.n_nodes,
+                                  thresh, 64, _lib.ptr(o_ids), _lib.ptr(o_sc), _lib.ptr(o_len), max_out,
+                                  torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        g_ids, g_sc, g_len = _np(o_ids), _np(o_sc), _np(o_len)
+        for c in range(n_cases):
+            pairs = [(int(o), float(s)) for o, s in zip(ids[c], sc[c]) if o >= 0]
+            exp = oracle.auto_merge(pairs, tree.parent_of, tree.child_count, tree.prev_id, tree.next_id, thresh)
+            n = int(g_len[c])
+            assert n >= 0, (c, "output overflow")
+            got = [(int(a), float(b)) for a, b in zip(g_ids[c, :n], g_sc[c, :n])]
+            assert got == exp, (seed, thresh, c)
+            merged_something += any(o >= n_leaf for o, _ in exp)
+    assert merged_something > n_cases  # the cases really exercise merging
