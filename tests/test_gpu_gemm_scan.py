@@ -198,3 +198,23 @@ def test_big_gemm_path_equals_pair_kernel_path_and_exact_scan(monkeypatch):
     ex = idx.search_exact(q[:4], 100)
     torch.cuda.synchronize()
     assert torch.equal(g_ids[:4], ex.ids) and torch.equal(g_sc[:4], ex.scores)
+
+
+@pytest.mark.parametrize("b", [1, 40, 300])
+def test_massive_ties_resolve_by_smaller_id(b):
+    """A corpus made of verbatim copies of 40 distinct vectors: every score is shared by ~750 rows, so the top-k is
+    decided by the tie rule alone (smaller id first).  No approximate shortlist can prove that; whatever the ladder
+    does (batch-1 kernel, GEMM-shaped scan, exact scan), the answer must be the oracle's."""
+    rng = np.random.default_rng(41)
+    base = rng.standard_normal((40, 256)).astype(np.float32)
+    assign = rng.integers(0, 40, size=30_000)
+    bits = oracle.f32_to_bf16_bits(base[assign])
+    q = (base[rng.integers(0, 40, size=b)] + 0.05 * rng.standard_normal((b, 256))).astype(np.float32)
+    ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
+    idx = _index(bits, None)
+    r = idx.search_certified(torch.from_numpy(q).cuda(), 10)
+    torch.cuda.synchronize()
+    assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
+    assert (np.diff(_np(r.ids), axis=1) > 0).all()  # ten copies of the best vector, ids ascending
+    if b > 32:  # one shortlist of 128 per query cannot hold ~750 tied rows: the certificate must have refused
+        assert idx.retries + idx.fallbacks > 0
