@@ -405,7 +405,7 @@ def run_b200(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms1 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms1 / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "serial": {"value": args.steps / (ser1["ms"] / 1e3), "ms_per_step": ser1["ms"] / args.steps,
                        "note": "same K steps with no overlap between consecutive steps (one stream)"},
             "dtype": "bf16", "data": "synthetic",
@@ -498,6 +498,9 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--cpu-sample-rows", type=int, default=1_048_576)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="label only: 'strong' = --rows is the total (default: the same 10M rows at every N); 'weak' when the "
+                         "caller scales --rows with N (C3: 12.5M rows per GPU)")
     ap.add_argument("--tag", default="C2", help="BASELINE config label written into config.workload")
     ap.add_argument("--wide-batch", type=int, default=16384, help="queries per step of the wide-batch (C4-shaped) section; 0 = skip")
     ap.add_argument("--wide-k", type=int, default=100)
