@@ -480,6 +480,6 @@ class DeviceIndex:
 
     def close(self) -> None:
         """Drop device memory (``RAGService.clear`` -> ``MultiIndexRetriever.clear_cache`` path, rag_service.py:720)."""
-        self._ws.clear()
+        self._ws.clear()  # workspaces, result records, captured graphs and their pinned staging buffers
         self.corpus = self.master = self.inv_norm = None
         self.parent_of = self.child_count = self.prev_id = self.next_id = None

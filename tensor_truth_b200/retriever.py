@@ -74,6 +74,17 @@ class _RetrieverBase:
         qb = QueryBundle(str_or_query_bundle) if isinstance(str_or_query_bundle, str) else str_or_query_bundle
         return self._retrieve(qb)
 
+    def close(self) -> None:
+        """Drop the device memory behind this retriever (corpus, tree arrays, workspaces, captured graphs).  The
+        reference releases its retrievers in ``RAGService.clear()`` (rag_service.py:720-740: ``clear_cache()``, then the
+        engine is dropped and ``torch.cuda.empty_cache()`` runs); deleting the retriever has the same effect here, and a
+        patched ``clear()`` can call this to free HBM at once."""
+        idx = getattr(self, "index", None)
+        if idx is not None and hasattr(idx, "close"):
+            idx.close()
+        if hasattr(self, "clear_cache"):
+            self.clear_cache()
+
     async def aretrieve(self, str_or_query_bundle: QueryType) -> List[NodeWithScore]:
         return self.retrieve(str_or_query_bundle)
 

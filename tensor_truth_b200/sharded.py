@@ -210,6 +210,13 @@ class ShardedIndex:
     def tree(self):
         return self.local.tree
 
+    def close(self) -> None:
+        self._peers.clear()
+        self._out.clear()
+        self._host_bufs.clear()
+        self.plumbing._bufs.clear()
+        self.local.close()
+
     def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True):
         """Host queries in, merged (+ auto-merged) lists out (numpy), with the certificate enforced per rank.
         Same contract as ``DeviceIndex.retrieve_host``, so the retriever classes take either; every rank must call it."""

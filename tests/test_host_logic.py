@@ -269,3 +269,17 @@ def test_b200_multi_index_retriever_matches_reference_golden_cases():
         assert got == case["expected"], case["name"]
         ran += 1
     assert ran >= 15
+
+
+def test_retriever_close_releases_the_index_and_the_cache():
+    from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200MultiIndexRetriever, B200VectorIndexRetriever
+
+    closed = []
+    idx = SimpleNamespace(tree=object(), close=lambda: closed.append("index"), n_seg=1, seg_trees=None)
+    base = B200VectorIndexRetriever(idx, 10)
+    B200AutoMergingRetriever(base, None).close()
+    assert closed == ["index"]
+    m = B200MultiIndexRetriever(idx, 10)
+    m._retrieve_cached.__wrapped__  # an lru_cache wrapper
+    m.close()
+    assert closed == ["index", "index"] and m._retrieve_cached.cache_info().currsize == 0
