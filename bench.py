@@ -372,17 +372,18 @@ def run_b200(args):
     base_r = B200VectorIndexRetriever(idx if sharded is None else sharded, similarity_top_k=TOP_K)
     am = B200AutoMergingRetriever(base_r, None)  # over a ShardedIndex every rank makes the same call (SPMD)
     call = lambda i: am.retrieve(QueryBundle(query_str=f"q{i}", embedding=q_lists[i % QUERY_POOL]))  # noqa: E731
-    for i in range(3):
+    e2e_warm = 8  # past DeviceIndex's GRAPH_AFTER: the one-off CUDA-graph capture of the pipeline belongs to the warm-up
+    for i in range(e2e_warm):
         out = call(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        out = call(3 + i)
+        out = call(e2e_warm + i)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     n_out = len(out)
     e2e = {"value": e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": DIM * 4,
-           "d2h_bytes_per_step": idx._record(1, TOP_K, True)["bytes"], "steps": e2e_steps,
+           "d2h_bytes_per_step": idx._record(1, TOP_K, True)["bytes"], "steps": e2e_steps, "warmup": e2e_warm,
            "api": "B200AutoMergingRetriever.retrieve(QueryBundle)" + ("" if sharded is None else " over ShardedIndex, every rank"),
            "fallbacks": idx.fallbacks, "nodes_returned_last": n_out}
 
