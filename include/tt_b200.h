@@ -195,8 +195,10 @@ int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int64_t ke
  *   tt_exchange_push       = the same publication of an already finished record (after a host-side repair).
  *   tt_merge_topk_pulled   = tt_merge_topk whose kernel first waits (acquire) until all `world` flags of
  *                            this rank's slot have reached `epoch`.
- * record layout: keys float[n_q*k] at offset 0, ids int64[n_q*k] at ids_off_bytes; records of consecutive
- * source ranks are rec_stride_bytes apart.  A slot may be reused once every rank has merged it (sharded.py
+ * record layout: keys float[n_q*k] at offset 0, ids int64[n_q*k] at ids_off_bytes and, when margins_off_bytes
+ * != 0, this rank's certificate margins float[n_q] at margins_off_bytes (so that every rank can see, in its own
+ * receive region, whether EVERY shard's top-k was proven exact -- no second host round trip); records of
+ * consecutive source ranks are rec_stride_bytes apart.  A slot may be reused once every rank has merged it (sharded.py
  * keeps a ring of 4 slots per stream pair, which the data dependencies of the pipeline make sufficient).
  */
 #define TT_MAX_PEERS 16
@@ -208,6 +210,7 @@ typedef struct tt_exchange {
     void* peer_recv[TT_MAX_PEERS];      /* peer p: base of ITS receive region for this slot, as mapped here */
     uint32_t* peer_flags[TT_MAX_PEERS]; /* peer p: ITS flag array for this slot, as mapped here             */
     uint32_t* ticket;                   /* local device word, zero between calls (one per slot)             */
+    uint64_t margins_off_bytes;         /* 0: margins are not exchanged                                     */
 } tt_exchange_t;
 
 /*

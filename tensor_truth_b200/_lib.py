@@ -52,7 +52,7 @@ class Exchange(C.Structure):
 
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("epoch", C.c_uint32), ("rec_stride_bytes", C.c_uint64),
                 ("ids_off_bytes", C.c_uint64), ("peer_recv", C.c_void_p * MAX_PEERS), ("peer_flags", C.c_void_p * MAX_PEERS),
-                ("ticket", C.c_void_p)]
+                ("ticket", C.c_void_p), ("margins_off_bytes", C.c_uint64)]
 
 
 class L2Cert(C.Structure):

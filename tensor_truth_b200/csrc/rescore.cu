@@ -108,7 +108,8 @@ struct Xchg {
     int wait_world;  // > 0: wait for that many sources before reading the input lists
     int rank;
     unsigned epoch;
-    unsigned long long rec_stride, ids_off;       // layout of a receive region: [source rank][keys | ids]
+    unsigned long long rec_stride, ids_off;       // layout of a receive region: [source rank][keys | ids | margins]
+    unsigned long long margins_off;               // 0: margins are not exchanged
     unsigned long long recv[TT_MAX_PEERS];        // peer p: base of its receive region for this slot
     unsigned long long flags[TT_MAX_PEERS];       // peer p: its flag array for this slot (element [rank] is ours)
     unsigned* ticket;                             // local counter, zero between launches
@@ -193,6 +194,14 @@ __device__ __forceinline__ void xchg_store(const Xchg& x, size_t o, float key, i
         const unsigned long long rec = x.recv[p] + (unsigned long long)x.rank * x.rec_stride;
         reinterpret_cast<float*>(rec)[o] = key;
         reinterpret_cast<int64_t*>(rec + x.ids_off)[o] = id;
+    }
+}
+
+__device__ __forceinline__ void xchg_store_margin(const Xchg& x, int b, float margin) {
+    if (!x.margins_off) return;
+    for (int p = 0; p < x.push_world; ++p) {
+        const unsigned long long rec = x.recv[p] + (unsigned long long)x.rank * x.rec_stride;
+        reinterpret_cast<float*>(rec + x.margins_off)[b] = margin;
     }
 }
 
@@ -316,7 +325,6 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
         if (out_ids) out_ids[o] = e ? int64_t(entry_id(e)) : int64_t(-1);
         if (x.push_world) xchg_store(x, o, key, e ? int64_t(entry_id(e)) : int64_t(-1));
     }
-    if (x.push_world) xchg_publish(x);
     if (out_margin) {
         float m = -INFINITY;
         if (thresh)
@@ -338,8 +346,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const uint64_t* __r
             else if (l2c) margin = entry_key(ek) - l2_upper_bound(m + cert.eps, qq, cert.nlo, cert.nhi);  // > 0 proves it
             else margin = -INFINITY;                          // cosine-ordered shortlist, no norm bounds given
             out_margin[b] = margin;
+            if (x.push_world) xchg_store_margin(x, b, margin);
         }
     }
+    if (x.push_world) xchg_publish(x);  // after the margin: the flag covers the whole record
 }
 
 // ------------------------------------------------------------------ select, small k: k rounds of block-wide max
@@ -411,7 +421,6 @@ __global__ void __launch_bounds__(SEL_THREADS) select_small_kernel(
         if (out_ids) out_ids[o] = w ? int64_t(entry_id(w)) : int64_t(-1);
         if (x.push_world) xchg_store(x, o, key, w ? int64_t(entry_id(w)) : int64_t(-1));
     }
-    if (x.push_world) xchg_publish(x);
     if (out_margin) {
         float m = -INFINITY;
         if (thresh)
@@ -433,8 +442,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_small_kernel(
             else if (l2c) margin = entry_key(ek) - l2_upper_bound(m + cert.eps, qq, cert.nlo, cert.nhi);
             else margin = -INFINITY;
             out_margin[b] = margin;
+            if (x.push_world) xchg_store_margin(x, b, margin);
         }
     }
+    if (x.push_world) xchg_publish(x);  // after the margin: the flag covers the whole record
 }
 
 static int pow2_at_least(int n) {
@@ -452,6 +463,7 @@ static int fill_xchg(Xchg* x, const tt_exchange_t* h, bool push, bool wait) {
     x->epoch = h->epoch;
     x->rec_stride = h->rec_stride_bytes;
     x->ids_off = h->ids_off_bytes;
+    x->margins_off = h->margins_off_bytes;
     if (push) {
         TT_CHECK_ARG(h->ticket != nullptr, "tt_exchange: null ticket");
         x->push_world = h->world;

@@ -84,8 +84,11 @@ class PeerBuffers:
         import torch.distributed._symmetric_memory as symm_mem
 
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.b, self.k = b, k
         rec, self.ids_off, _ = record_layout(b, k)
-        self.rec_stride = (rec + 15) // 16 * 16
+        self.margins_off = rec               # [keys | ids | margins float32 B]: the source's certificate margins ride along
+        self.rec_bytes = rec + 4 * b         # what one source writes (and what tt_exchange_push copies)
+        self.rec_stride = (self.rec_bytes + 15) // 16 * 16
         self.region = self.world * self.rec_stride
         self.flags_off = (self.DEPTH * self.region + 127) // 128 * 128
         total = self.flags_off + (self.DEPTH * self.world * 4 + 127) // 128 * 128
@@ -102,6 +105,7 @@ class PeerBuffers:
             x = Exchange()
             x.world, x.rank = self.world, self.rank
             x.rec_stride_bytes, x.ids_off_bytes = self.rec_stride, self.ids_off
+            x.margins_off_bytes = self.margins_off
             for p in range(self.world):
                 x.peer_recv[p] = self.ptrs[p] + slot * self.region
                 x.peer_flags[p] = self.ptrs[p] + self.flags_off + slot * self.world * 4
@@ -116,7 +120,25 @@ class PeerBuffers:
         slot = (self.epoch - 1) % self.DEPTH
         x = self._x[slot]  # the library copies it into the kernel parameters at launch, so reuse is safe
         x.epoch = self.epoch
+        self.last_slot = slot
         return x, self.ptrs[self.rank] + slot * self.region
+
+    def margins_view(self, slot: int) -> torch.Tensor:
+        """float32 [world, B] view of the margins every source pushed into this rank's receive region of ``slot``."""
+        base = slot * self.region
+        recs = self.buf[base: base + self.world * self.rec_stride].view(self.world, self.rec_stride)
+        return recs[:, self.margins_off: self.margins_off + 4 * self.b].view(torch.float32)
+
+    def send_record(self):
+        """A local record in the layout of one source's slice of a receive region (for tt_exchange_push): the uint8
+        buffer and its keys [B,k] / ids [B,k] / margins [B] views."""
+        if not hasattr(self, "_send"):
+            buf = torch.zeros(self.rec_stride, dtype=torch.uint8, device=self.buf.device)
+            b, k = self.b, self.k
+            self._send = (buf, buf[: b * k * 4].view(torch.float32).view(b, k),
+                          buf[self.ids_off: self.ids_off + b * k * 8].view(torch.int64).view(b, k),
+                          buf[self.margins_off: self.margins_off + 4 * b].view(torch.float32))
+        return self._send
 
 
 class ShardedIndex:
@@ -217,9 +239,81 @@ class ShardedIndex:
         self.plumbing._bufs.clear()
         self.local.close()
 
+    def _finish_host(self, mids, scores, b, k, ratio_thresh, merged, extra=None):
+        """Auto-merge (or copy) the merged top-k into the result record and start its D2H copy; ``extra`` = (device
+        tensor, pinned host tensor) copied along.  The caller synchronises on the record's event."""
+        local = self.local
+        rec = local._record(b, k, merged)
+        d = rec["d"]
+        if merged:
+            from .index import MergeResult
+
+            local.automerge(mids, scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+        else:
+            d["ids"].copy_(mids)
+            d["scores"].copy_(scores)
+        rec["host"].copy_(rec["dev"], non_blocking=True)
+        if extra is not None:
+            extra[1].copy_(extra[0], non_blocking=True)
+        rec["event"].record()
+        return rec
+
+    @staticmethod
+    def _unpack_host(rec, merged):
+        h = rec["h"]
+        ids_h, scores_h = h["ids"].numpy().copy(), h["scores"].numpy().astype("float64")
+        lens = h["lens"].numpy().copy() if merged else (ids_h >= 0).sum(axis=1).astype("int32")
+        return ids_h, scores_h, lens
+
+    def _retrieve_host_peer(self, pb, q, b, k, ratio_thresh, merged):
+        """Peer transport, ONE host synchronisation per query batch: the selecting kernel pushes this rank's record AND
+        its certificate margins to every peer, so after the merge every rank finds all ranks' margins in its own
+        receive region and they come back with the result.  Only if some rank's top-k was not proven (every rank sees
+        that, from identical data) do all ranks take a second round: local repair, plain push, merge again."""
+        import ctypes as C
+
+        local = self.local
+        hb = self._host_bufs.get(("all", b))
+        if hb is None:
+            hb = self._host_bufs[("all", b)] = (torch.empty((b,), dtype=torch.float32, device=self.device),
+                                                torch.empty((pb.world, b), dtype=torch.float32).pin_memory())
+        margins, all_h = hb
+        x, region = pb.next()
+        slot = pb.last_slot
+        w = dict(local._buffers(b, k))
+        w["margin"] = margins
+        r = self.last = local.search(q, k, out=w, xchg=x)
+        scores, mids = self._merge_pulled(x, region, b, k, k, 0)
+        rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged, extra=(pb.margins_view(slot), all_h))
+        rec["event"].synchronize()
+        proven = all_h.numpy() > r.eps           # [world, B], the same on every rank
+        if not proven.all():
+            mine = (~proven[pb.rank]).nonzero()[0]
+            if mine.size:
+                local._repair(q, k, r, torch.from_numpy(mine).to(self.device), hi_lo_first=r.hi_only)
+            send, s_keys, s_ids, s_margins = pb.send_record()
+            s_keys.copy_(r.keys)
+            s_ids.copy_(r.ids)
+            s_margins.fill_(float("inf"))         # what is sent now is exact (proven before, or repaired)
+            x2, region2 = pb.next()
+            with local._on_device():
+                self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), pb.rec_bytes // 4 * 4, C.byref(x2),
+                                                                 local._stream()))
+            scores, mids = self._merge_pulled(x2, region2, b, k, k, 0)
+            rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged)
+            rec["event"].synchronize()
+            self.second_rounds = getattr(self, "second_rounds", 0) + 1
+        return self._unpack_host(rec, merged)
+
     def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True):
         """Host queries in, merged (+ auto-merged) lists out (numpy), with the certificate enforced per rank.
         Same contract as ``DeviceIndex.retrieve_host``, so the retriever classes take either; every rank must call it."""
+        merged = bool(merge and self.local.tree is not None)
+        if self.transport == "peer":
+            q0 = self.local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
+            pb0 = self.peers(int(q0.shape[0]), k)
+            if pb0 is not None:
+                return self._retrieve_host_peer(pb0, q0, int(q0.shape[0]), k, ratio_thresh, merged)
         local = self.local
         q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
         b = int(q.shape[0])
@@ -237,31 +331,9 @@ class ShardedIndex:
         bad = (~(margins_h > r.eps)).nonzero().flatten()
         if bad.numel():  # rank-local repair (writes into the send record); the exchange below is reached by every rank
             local._repair(q, k, r, bad.to(self.device), hi_lo_first=r.hi_only)
-        pb = self.peers(b, k)
-        if pb is None:
-            self.plumbing.exchange(send, recv)
-            scores, mids = self._merge(recv, self.plumbing.world, b, k, k)
-        else:
-            x, region = pb.next()
-            import ctypes as C
-
-            with local._on_device():
-                self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), send.numel() // 4 * 4, C.byref(x),
-                                                                 self.local._stream()))
-            scores, mids = self._merge_pulled(x, region, b, k, k, 0)
-        merged = bool(merge and local.tree is not None)
-        rec = local._record(b, k, merged)
-        d, h = rec["d"], rec["h"]
-        if merged:
-            from .index import MergeResult
-
-            local.automerge(mids, scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
-        else:
-            d["ids"].copy_(mids)
-            d["scores"].copy_(scores)
-        rec["host"].copy_(rec["dev"], non_blocking=True)
-        rec["event"].record()
+        # NCCL transport (or symmetric memory unavailable): certificate first (one sync), then all-gather + merge
+        self.plumbing.exchange(send, recv)
+        scores, mids = self._merge(recv, self.plumbing.world, b, k, k)
+        rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged)
         rec["event"].synchronize()
-        ids_h, scores_h = h["ids"].numpy().copy(), h["scores"].numpy().astype("float64")
-        lens = h["lens"].numpy().copy() if merged else (ids_h >= 0).sum(axis=1).astype("int32")
-        return ids_h, scores_h, lens
+        return self._unpack_host(rec, merged)

@@ -59,6 +59,22 @@ def _worker(rank, world, port, transport, out_dir):
         got = [(int(o), float(s)) for o, s in zip(ids_h[b, :lens[b]], sc_h[b, :lens[b]])]
         assert got == exp
     assert sh.transport == ("peer" if transport == "peer" else "nccl")  # no silent fallback
+    # one shard whose top-k cannot be proven (near-duplicate rows), one that can: the host path must notice on EVERY rank
+    # (the margins travel with the records), repair on the rank concerned and exchange a second time
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal(1024).astype(np.float32)
+    dup = oracle.f32_to_bf16_bits(base[None, :] * (1.0 + 2e-3 * rng.standard_normal((25_000, 1024)).astype(np.float32)))
+    mixed = np.concatenate([bits[:25_000], dup])
+    lo2, hi2 = shard_bounds(mixed.shape[0], world, rank)
+    sh2 = ShardedIndex(DeviceIndex(mixed[lo2:hi2], None, id_base=lo2, device=dev))
+    q2 = np.stack([q[0], (base * (1.0 + 1e-3 * rng.standard_normal(1024))).astype(np.float32), q[1]])
+    ids_m, sc_m, _ = cport.scan_topk(mixed, q2, 10)
+    for rep in range(3):
+        ids_h, sc_h, lens = sh2.retrieve_host(torch.from_numpy(q2), 10, merge=False)
+        assert (ids_h == ids_m).all() and (sc_h == sc_m.astype(np.float64)).all(), rep
+    if transport == "peer":
+        assert sh2.second_rounds == 3      # every rank took the second round, every time
+    assert (sh2.local.fallbacks > 0) == (rank == 1)
     open(os.path.join(out_dir, f"ok-{transport}-{rank}"), "w").write("ok")
     dist.destroy_process_group()
 
