@@ -253,6 +253,28 @@ int tt_automerge(const int64_t* ids, const float* scores, int n_q, int k,
                  double ratio_thresh, int max_rounds,
                  int64_t* out_ids, double* out_scores, int32_t* out_len, int max_out, void* stream);
 
+/*
+ * The stage AFTER the retrieval path: the dense layers of the cross-encoder reranker
+ * (SentenceTransformerRerank.postprocess_nodes; services/model_manager.py:333-337, services/rag_service.py:343-346).
+ * tensor_truth_b200/rerank.py strings them into an XLM-RoBERTa encoder; attention itself is a library call there.
+ *
+ * tt_linear_bf16:  y[T, n_out] = act(x[T, k_in] W[n_out, k_in]^T + bias) (+ residual[T, n_out]), all bf16 except
+ *                  bias (fp32, nullable); fp32 accumulation on tcgen05 (256 x 256 tiles per CTA pair), the layer tail
+ *                  fused into the epilogue.  activation: 0 none, 1 exact (erf) GELU.  residual nullable.
+ *                  k_in % 128 == 0, n_out % 256 == 0, 16-byte aligned pointers.
+ * tt_layernorm_bf16: y = LayerNorm(x) over the last dimension (fp32 statistics), dim % 8 == 0, dim <= 2048.
+ * tt_embed_layernorm_bf16: y[t] = LayerNorm(word_emb[word_ids[t]] + pos_emb[pos_ids[t]] (+ type_emb[0])).
+ */
+#define TT_ACT_NONE 0
+#define TT_ACT_GELU 1
+int tt_linear_bf16(const void* x_bf16, int64_t n_rows, int k_in, const void* w_bf16, int n_out, const float* bias,
+                   const void* residual_bf16, int activation, void* y_bf16, void* stream);
+int tt_layernorm_bf16(const void* x_bf16, int64_t n_rows, int dim, const float* gamma, const float* beta, float eps,
+                      void* y_bf16, void* stream);
+int tt_embed_layernorm_bf16(const int32_t* word_ids, const int32_t* pos_ids, int64_t n_rows, int dim,
+                            const void* word_emb_bf16, const void* pos_emb_bf16, const void* type_emb_bf16,
+                            const float* gamma, const float* beta, float eps, void* y_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,9 @@ SIGNATURES = {
     "tt_rescore_topk_push": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P, _P, _P]),
     "tt_exchange_push": (_I, [_P, _Z, _P, _P]),
     "tt_merge_topk_pulled": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "tt_linear_bf16": (_I, [_P, _L, _I, _P, _I, _P, _P, _I, _P, _P]),
+    "tt_layernorm_bf16": (_I, [_P, _L, _I, _P, _P, C.c_float, _P, _P]),
+    "tt_embed_layernorm_bf16": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, C.c_float, _P, _P]),
     "tt_automerge_max_k": (_I, []),
     "tt_automerge": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _L, _D, _I, _P, _P, _P, _I, _P]),
 }

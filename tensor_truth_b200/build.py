@@ -12,7 +12,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtt_b200.so")
-SOURCES = ["api.cu", "scan_simt.cu", "scan_tc.cu", "scan_tc2.cu", "scan_gemm.cu", "rescore.cu", "automerge.cu"]
+SOURCES = ["api.cu", "scan_simt.cu", "scan_tc.cu", "scan_tc2.cu", "scan_gemm.cu", "linear.cu", "rescore.cu", "automerge.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -31,6 +31,11 @@ bool scan_gemm_supported(int dim, int kprime, int n_lists);
 int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
                      int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx, float* out_thresh,
                      void* ws, int n_sms, cudaStream_t st);
+int launch_linear(const void* x, int64_t n_rows, int k_in, const void* w, int n_out, const float* bias, const void* residual,
+                  int activation, void* y, int n_sms, cudaStream_t st);
+int launch_layernorm(const void* x, int64_t n_rows, int dim, const float* gamma, const float* beta, float eps, void* y,
+                     const int* word_ids, const int* pos_ids, const void* word_emb, const void* pos_emb, const void* type_emb,
+                     cudaStream_t st);
 int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
                    const float* q, int n_q, const int64_t* cand_ids, int n_cand, int mode, uint64_t* packed,
                    cudaStream_t st);
@@ -329,6 +334,49 @@ int tt_merge_topk_pulled(const float* keys, const int64_t* ids, int n_lists, int
                          nullptr, 0, nullptr, out_scores, out_ids, nullptr, TT_STREAM(stream), xchg, false, xchg != nullptr);
 }
 
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int tt_linear_bf16(const void* x_bf16, int64_t n_rows, int k_in, const void* w_bf16, int n_out, const float* bias,
+                   const void* residual_bf16, int activation, void* y_bf16, void* stream) {
+    TT_CHECK_ARG(n_rows >= 0 && n_rows < (int64_t(1) << 31) - 256, "tt_linear_bf16: n_rows=%lld", (long long)n_rows);
+    TT_CHECK_ARG(k_in >= 128 && k_in % 128 == 0, "tt_linear_bf16: k_in=%d must be a positive multiple of 128", k_in);
+    TT_CHECK_ARG(n_out >= 256 && n_out % 256 == 0, "tt_linear_bf16: n_out=%d must be a positive multiple of 256", n_out);
+    TT_CHECK_ARG(activation == TT_ACT_NONE || activation == TT_ACT_GELU, "tt_linear_bf16: activation %d", activation);
+    if (n_rows == 0) return TT_OK;
+    TT_CHECK_ARG(x_bf16 && w_bf16 && y_bf16, "tt_linear_bf16: null pointer");
+    TT_CHECK_ARG(aligned16(x_bf16) && aligned16(w_bf16) && aligned16(y_bf16) && aligned16(residual_bf16) && aligned16(bias),
+                 "tt_linear_bf16: pointers must be 16-byte aligned");
+    const int n_sms = sm_count(current_device());
+    if (n_sms < 2) {
+        set_error("tt_linear_bf16: no CUDA device");
+        return TT_ERR_CUDA;
+    }
+    return launch_linear(x_bf16, n_rows, k_in, w_bf16, n_out, bias, residual_bf16, activation, y_bf16, n_sms, TT_STREAM(stream));
+}
+
+int tt_layernorm_bf16(const void* x_bf16, int64_t n_rows, int dim, const float* gamma, const float* beta, float eps,
+                      void* y_bf16, void* stream) {
+    TT_CHECK_ARG(n_rows >= 0 && dim >= 8 && dim % 8 == 0 && dim <= 2048, "tt_layernorm_bf16: n_rows=%lld dim=%d",
+                 (long long)n_rows, dim);
+    if (n_rows == 0) return TT_OK;
+    TT_CHECK_ARG(x_bf16 && gamma && beta && y_bf16 && aligned16(x_bf16) && aligned16(y_bf16), "tt_layernorm_bf16: bad pointer");
+    return launch_layernorm(x_bf16, n_rows, dim, gamma, beta, eps, y_bf16, nullptr, nullptr, nullptr, nullptr, nullptr,
+                            TT_STREAM(stream));
+}
+
+int tt_embed_layernorm_bf16(const int32_t* word_ids, const int32_t* pos_ids, int64_t n_rows, int dim,
+                            const void* word_emb_bf16, const void* pos_emb_bf16, const void* type_emb_bf16,
+                            const float* gamma, const float* beta, float eps, void* y_bf16, void* stream) {
+    TT_CHECK_ARG(n_rows >= 0 && dim >= 8 && dim % 8 == 0 && dim <= 2048, "tt_embed_layernorm_bf16: n_rows=%lld dim=%d",
+                 (long long)n_rows, dim);
+    if (n_rows == 0) return TT_OK;
+    TT_CHECK_ARG(word_ids && pos_ids && word_emb_bf16 && pos_emb_bf16 && gamma && beta && y_bf16 && aligned16(word_emb_bf16) &&
+                     aligned16(pos_emb_bf16) && aligned16(type_emb_bf16) && aligned16(y_bf16),
+                 "tt_embed_layernorm_bf16: bad pointer");
+    return launch_layernorm(nullptr, n_rows, dim, gamma, beta, eps, y_bf16, word_ids, pos_ids, word_emb_bf16, pos_emb_bf16,
+                            type_emb_bf16, TT_STREAM(stream));
+}
 
 int tt_automerge_max_k(void) { return automerge_max_k(); }
 
