@@ -1,0 +1,232 @@
+"""The stage after the retrieval path: cross-encoder reranking.
+
+The reference loads ``SentenceTransformerRerank(model="BAAI/bge-reranker-v2-m3", top_n=..., device=...)``
+(/root/reference/src/tensortruth/services/model_manager.py:333-337) and runs
+``postprocessor.postprocess_nodes(source_nodes, query_bundle=QueryBundle(query_str=...))`` on what the retriever
+returned (services/rag_service.py:343-346): every (query, node text) pair goes through an XLM-RoBERTa
+sequence-classification model, the node's score is overwritten with the model's sigmoid output, the list is sorted by it
+and cut to ``top_n``.
+
+``B200CrossEncoder`` is that model's forward pass on the B200 kernels of this package:
+
+* all pairs of a call are PACKED (no padding) into one ``[T, hidden]`` activation matrix;
+* input layer: ``tt_embed_layernorm_bf16`` (word + position + token-type embeddings, LayerNorm);
+* every dense layer: ``tt_linear_bf16`` -- tcgen05 GEMM with bias / exact GELU / residual add fused in the epilogue
+  (QKV as one [3H, H] GEMM, attention output + residual, FFN up + GELU, FFN down + residual);
+* LayerNorms: ``tt_layernorm_bf16``;
+* attention itself is a LIBRARY call (PyTorch's packed ``varlen_attn``; ``scaled_dot_product_attention`` on padded pairs
+  when that is missing) -- not part of this package's kernels;
+* the classification head (dense + tanh + 1-unit projection on the <s> token) is a [n_pairs, hidden] problem and runs
+  in torch fp32.
+
+Weights come from a Hugging Face ``XLMRobertaForSequenceClassification`` state dict (``CrossEncoderWeights``); the
+tokenizer is injected (``tokenize(pairs, max_length) -> List[List[int]]``: in a deployment the model's own
+``AutoTokenizer``).  Neither the checkpoint nor the SentencePiece model is available in the build image, so tests and
+benchmarks use randomly initialised weights of the same architecture and compare against the Hugging Face
+implementation run in fp32 on the same weights.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr
+
+ACT_NONE, ACT_GELU = 0, 1
+
+try:  # PyTorch >= 2.10: attention over packed sequences (cu_seqlens), no padding
+    from torch.nn.attention.varlen import varlen_attn as _varlen_attn
+except Exception:  # pragma: no cover
+    _varlen_attn = None
+
+
+@dataclass
+class _Layer:
+    w_qkv: torch.Tensor
+    b_qkv: torch.Tensor
+    w_o: torch.Tensor
+    b_o: torch.Tensor
+    ln1_g: torch.Tensor
+    ln1_b: torch.Tensor
+    w_ff1: torch.Tensor
+    b_ff1: torch.Tensor
+    w_ff2: torch.Tensor
+    b_ff2: torch.Tensor
+    ln2_g: torch.Tensor
+    ln2_b: torch.Tensor
+
+
+class CrossEncoderWeights:
+    """Device copies of an ``XLMRobertaForSequenceClassification`` (``num_labels == 1``) checkpoint in the layout the
+    kernels want: GEMM operands bf16 ``[out, in]`` (the nn.Linear layout is already K-major), biases / LayerNorm
+    parameters fp32, Q, K and V fused into one ``[3H, H]`` weight."""
+
+    def __init__(self, state_dict, config, device):
+        dev = torch.device(device)
+        sd = {k: v for k, v in state_dict.items()}
+        pre = "roberta." if any(k.startswith("roberta.") for k in sd) else ""
+
+        def bf(name):
+            return sd[name].detach().to(dev, torch.bfloat16).contiguous()
+
+        def f32(name):
+            return sd[name].detach().to(dev, torch.float32).contiguous()
+
+        self.hidden = int(config.hidden_size)
+        self.n_heads = int(config.num_attention_heads)
+        self.inter = int(config.intermediate_size)
+        self.eps = float(config.layer_norm_eps)
+        self.pad_id = int(config.pad_token_id)
+        if self.hidden % 256 or self.inter % 256 or self.hidden % self.n_heads:
+            raise ValueError("hidden and intermediate sizes must be multiples of 256 (tt_linear_bf16 tile)")
+        e = pre + "embeddings."
+        self.word_emb, self.pos_emb, self.type_emb = bf(e + "word_embeddings.weight"), bf(e + "position_embeddings.weight"), \
+            bf(e + "token_type_embeddings.weight")
+        self.emb_ln_g, self.emb_ln_b = f32(e + "LayerNorm.weight"), f32(e + "LayerNorm.bias")
+        self.layers: List[_Layer] = []
+        for i in range(int(config.num_hidden_layers)):
+            p = f"{pre}encoder.layer.{i}."
+            a = p + "attention.self."
+            w_qkv = torch.cat([sd[a + "query.weight"], sd[a + "key.weight"], sd[a + "value.weight"]], dim=0)
+            b_qkv = torch.cat([sd[a + "query.bias"], sd[a + "key.bias"], sd[a + "value.bias"]], dim=0)
+            self.layers.append(_Layer(
+                w_qkv.detach().to(dev, torch.bfloat16).contiguous(), b_qkv.detach().to(dev, torch.float32).contiguous(),
+                bf(p + "attention.output.dense.weight"), f32(p + "attention.output.dense.bias"),
+                f32(p + "attention.output.LayerNorm.weight"), f32(p + "attention.output.LayerNorm.bias"),
+                bf(p + "intermediate.dense.weight"), f32(p + "intermediate.dense.bias"),
+                bf(p + "output.dense.weight"), f32(p + "output.dense.bias"),
+                f32(p + "output.LayerNorm.weight"), f32(p + "output.LayerNorm.bias")))
+        self.head_w1, self.head_b1 = f32("classifier.dense.weight"), f32("classifier.dense.bias")
+        self.head_w2, self.head_b2 = f32("classifier.out_proj.weight"), f32("classifier.out_proj.bias")
+        if self.head_w2.shape[0] != 1:
+            raise ValueError("a reranker head has one output unit")
+        self.device = dev
+
+    @classmethod
+    def from_hf_model(cls, model, device):
+        return cls(model.state_dict(), model.config, device)
+
+
+class B200CrossEncoder:
+    """Packed forward pass of the cross-encoder; ``logits(token_lists)`` -> float32 ``[n_pairs]`` on the device."""
+
+    def __init__(self, weights: CrossEncoderWeights, max_length: int = 512):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tensor_truth_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.w = weights
+        self.max_length = int(max_length)
+        self.lib = _lib.lib()
+        self._dev_index = weights.device.index if weights.device.index is not None else torch.cuda.current_device()
+
+    # ---- kernels
+    def _stream(self):
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
+
+    def _linear(self, x, w, b, residual=None, act=ACT_NONE):
+        y = torch.empty((x.shape[0], w.shape[0]), dtype=torch.bfloat16, device=x.device)
+        check(self.lib.tt_linear_bf16(ptr(x), int(x.shape[0]), int(x.shape[1]), ptr(w), int(w.shape[0]), ptr(b), ptr(residual),
+                                      act, ptr(y), self._stream()))
+        return y
+
+    def _layernorm(self, x, g, b):
+        y = torch.empty_like(x)
+        check(self.lib.tt_layernorm_bf16(ptr(x), int(x.shape[0]), int(x.shape[1]), ptr(g), ptr(b), self.w.eps, ptr(y),
+                                         self._stream()))
+        return y
+
+    # ---- attention: a LIBRARY call.  Packed (variable-length) attention when the installed PyTorch has it, else
+    #      scaled_dot_product_attention on the pairs padded to the longest one of the call.
+    def _attention(self, qkv: torch.Tensor, cu: torch.Tensor, dest: torch.Tensor, n: int, s_max: int,
+                   key_mask: torch.Tensor) -> torch.Tensor:
+        h, nh = self.w.hidden, self.w.n_heads
+        if _varlen_attn is not None:
+            q, k, v = qkv.view(-1, 3, nh, h // nh).unbind(1)
+            return _varlen_attn(q, k, v, cu, cu, s_max, s_max).reshape(-1, h)
+        padded = torch.zeros((n * s_max, 3 * h), dtype=qkv.dtype, device=qkv.device)
+        padded[dest] = qkv
+        q, k, v = padded.view(n, s_max, 3, nh, h // nh).permute(2, 0, 3, 1, 4)
+        out = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=key_mask)
+        return out.permute(0, 2, 1, 3).reshape(n * s_max, h)[dest].contiguous()
+
+    def logits(self, token_lists: Sequence[Sequence[int]]) -> torch.Tensor:
+        w = self.w
+        n = len(token_lists)
+        if n == 0:
+            return torch.empty((0,), dtype=torch.float32, device=w.device)
+        lens = [min(len(t), self.max_length) for t in token_lists]
+        if min(lens) == 0:
+            raise ValueError("empty token list")
+        s_max, total = max(lens), sum(lens)
+        flat, pos, dest, first = [], [], [], []
+        for i, (t, ln) in enumerate(zip(token_lists, lens)):
+            first.append(len(flat))
+            flat.extend(t[:ln])
+            pos.extend(range(w.pad_id + 1, w.pad_id + 1 + ln))   # RoBERTa position ids start after the padding index
+            dest.extend(range(i * s_max, i * s_max + ln))
+        dev = w.device
+        with torch.cuda.device(dev):
+            ids_d = torch.tensor(flat, dtype=torch.int32).to(dev, non_blocking=True)
+            pos_d = torch.tensor(pos, dtype=torch.int32).to(dev, non_blocking=True)
+            first_d = torch.tensor(first, dtype=torch.int64).to(dev, non_blocking=True)
+            cu_d = torch.tensor(first + [total], dtype=torch.int32).to(dev, non_blocking=True)
+            dest_d = key_mask = None
+            if _varlen_attn is None:
+                dest_d = torch.tensor(dest, dtype=torch.int64).to(dev, non_blocking=True)
+                key_mask = (torch.arange(s_max, device=dev)[None, :] < torch.tensor(lens, device=dev)[:, None])[:, None, None, :]
+            x = torch.empty((total, w.hidden), dtype=torch.bfloat16, device=dev)
+            check(self.lib.tt_embed_layernorm_bf16(ptr(ids_d), ptr(pos_d), total, w.hidden, ptr(w.word_emb), ptr(w.pos_emb),
+                                                   ptr(w.type_emb), ptr(w.emb_ln_g), ptr(w.emb_ln_b), w.eps, ptr(x),
+                                                   self._stream()))
+            for L in w.layers:
+                qkv = self._linear(x, L.w_qkv, L.b_qkv)
+                ctx = self._attention(qkv, cu_d, dest_d, n, s_max, key_mask)
+                x = self._layernorm(self._linear(ctx, L.w_o, L.b_o, residual=x), L.ln1_g, L.ln1_b)
+                hdn = self._linear(x, L.w_ff1, L.b_ff1, act=ACT_GELU)
+                x = self._layernorm(self._linear(hdn, L.w_ff2, L.b_ff2, residual=x), L.ln2_g, L.ln2_b)
+            cls = x[first_d].float()                              # the <s> token of every pair
+            hid = torch.tanh(cls @ w.head_w1.T + w.head_b1)
+            return (hid @ w.head_w2.T + w.head_b2).squeeze(-1)
+
+
+class B200CrossEncoderRerank:
+    """``SentenceTransformerRerank(model, top_n, device, keep_retrieval_score=False)``: ``postprocess_nodes(nodes,
+    query_bundle)`` scores every (query, node text) pair, overwrites ``node.score`` with the sigmoid of the model's
+    logit (what ``CrossEncoder.predict`` returns for a one-label model), sorts by it, descending, and keeps ``top_n``."""
+
+    def __init__(self, encoder: B200CrossEncoder, tokenize: Callable[[List[Tuple[str, str]], int], List[List[int]]],
+                 top_n: int = 2, keep_retrieval_score: bool = False):
+        self.encoder, self.tokenize = encoder, tokenize
+        self.top_n = int(top_n)
+        self.keep_retrieval_score = bool(keep_retrieval_score)
+
+    @staticmethod
+    def _text(node: Any) -> str:
+        inner = getattr(node, "node", node)
+        try:
+            from llama_index.core.schema import MetadataMode  # type: ignore
+
+            return inner.get_content(metadata_mode=MetadataMode.EMBED)
+        except Exception:
+            return inner.get_content()
+
+    def postprocess_nodes(self, nodes: List[Any], query_bundle: Optional[Any] = None, query_str: Optional[str] = None):
+        if query_bundle is None and query_str is not None:
+            from .schema import QueryBundle
+
+            query_bundle = QueryBundle(query_str=query_str)
+        if query_bundle is None:
+            raise ValueError("Missing query bundle in extra info.")
+        if len(nodes) == 0:
+            return []
+        pairs = [(query_bundle.query_str, self._text(n)) for n in nodes]
+        logits = self.encoder.logits(self.tokenize(pairs, self.encoder.max_length))
+        scores = torch.sigmoid(logits).cpu().tolist()
+        for node, score in zip(nodes, scores):
+            if self.keep_retrieval_score:
+                node.node.metadata["retrieval_score"] = node.score
+            node.score = float(score)
+        return sorted(nodes, key=lambda x: -x.score if x.score else 0)[: self.top_n]

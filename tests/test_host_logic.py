@@ -283,3 +283,33 @@ def test_retriever_close_releases_the_index_and_the_cache():
     m._retrieve_cached.__wrapped__  # an lru_cache wrapper
     m.close()
     assert closed == ["index", "index"] and m._retrieve_cached.cache_info().currsize == 0
+
+
+def test_rerank_postprocessor_semantics_with_a_stand_in_encoder():
+    """SentenceTransformerRerank.postprocess_nodes as restated in rerank.py: score overwrite with the sigmoid of the
+    logit, sort descending, top_n cut, optional retrieval_score, the upstream error for a missing query bundle."""
+    torch = pytest.importorskip("torch")
+    from tensor_truth_b200.rerank import B200CrossEncoderRerank
+
+    class Enc:
+        max_length = 16
+
+        def logits(self, toks):
+            return torch.tensor([float(len(t)) - 5.0 for t in toks])
+
+    seen = []
+
+    def tokenize(pairs, max_length):
+        seen.extend(pairs)
+        return [[0] * min(max_length, len(d.split())) for _, d in pairs]
+
+    nodes = [NodeWithScore(TextNode(id_=f"n{i}", text=" ".join(["w"] * (3 + 2 * i))), 0.5) for i in range(5)]
+    rr = B200CrossEncoderRerank(Enc(), tokenize, top_n=2, keep_retrieval_score=True)
+    out = rr.postprocess_nodes(list(nodes), query_bundle=QueryBundle(query_str="the question"))
+    assert [n.node.id_ for n in out] == ["n4", "n3"]
+    assert out[0].score == pytest.approx(1 / (1 + np.exp(-6.0))) and out[0].node.metadata["retrieval_score"] == 0.5
+    assert all(q == "the question" for q, _ in seen) and len(seen) == 5
+    assert rr.postprocess_nodes([], query_bundle=QueryBundle(query_str="q")) == []
+    with pytest.raises(ValueError, match="Missing query bundle"):
+        rr.postprocess_nodes(list(nodes))
+    assert len(rr.postprocess_nodes(list(nodes), query_str="as a plain string")) == 2
