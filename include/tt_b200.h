@@ -114,8 +114,8 @@ int tt_scan_topk_bf16_segmented(const void* corpus_bf16, int64_t n_rows, int dim
                                 void* ws, size_t ws_bytes, void* stream);
 
 /*
- * Stage 1 for very wide batches (hundreds to tens of thousands of concurrent queries; BASELINE config C4,
- * the tensor-bound regime).  Same role and same output contract as tt_scan_topk_bf16 with ONE list per
+ * Stage 1 for hi-only batches: from a few dozen to tens of thousands of concurrent queries (BASELINE configs[1]'s
+ * batch-64 -- HBM-bound, one 64-column pass -- up to config C4, the tensor-bound regime).  Same role and same output contract as tt_scan_topk_bf16 with ONE list per
  * query (n_lists = 1), queries as bf16 hi halves only:
  *
  *   out_ids    int64 [n_q, kprime]   the kprime rows with the best approximate score, best first; -1 = empty
@@ -124,8 +124,8 @@ int tt_scan_topk_bf16_segmented(const void* corpus_bf16, int64_t n_rows, int dim
  *                                    left out;  +inf: the query's candidate buffer overflowed (the
  *                                    certificate of tt_rescore_topk then fails and the caller re-runs it)
  *
- * A GEMM-shaped tcgen05 kernel (256 x 256 output tiles per CTA pair, corpus and query tiles both TMA-
- * streamed) visits the corpus in phases of geometrically growing size; between phases each query's
+ * A GEMM-shaped tcgen05 kernel (256 x 256 output tiles per CTA pair, 256 x 128 / 64 when the batch fits one
+ * narrower block; corpus and query tiles both TMA-streamed) visits the corpus in phases of geometrically growing size; between phases each query's
  * candidate buffer is cut to its kprime best and the K'-th score becomes the threshold the next phase's
  * epilogue filters with.  The score matrix never reaches HBM.
  * kprime in {128, 256, 512}; dim % 64 == 0; ws: tt_scan_gemm_workspace_bytes(n_q, kprime) bytes

@@ -1,14 +1,14 @@
-// Stage 1 for very wide query batches (hundreds to tens of thousands of concurrent queries): the
-// tensor-bound regime.  A GEMM-shaped kernel -- corpus AND query tiles both streamed through the TMA ring,
-// 256 x 256 output tiles per CTA pair (tcgen05.mma cta_group::2, M = 256, N = 256, accumulators double-buffered
-// in all 512 TMEM columns) -- whose epilogue never writes the score matrix: every accumulator element is
-// compared with its query's running threshold tau[q] and only the survivors are appended to that query's
-// candidate buffer in HBM.
+// Stage 1 for every batch whose queries travel as bf16 hi halves (more than 32 concurrent queries, up to tens of
+// thousands: the tensor-bound regime).  A GEMM-shaped kernel -- corpus AND query tiles both streamed through the TMA
+// ring, 256 x N output tiles per CTA pair (tcgen05.mma cta_group::2, M = 256; N = 256 with the accumulators
+// double-buffered in all 512 TMEM columns, N = 128 / 64 when the whole batch fits one narrower block) -- whose
+// epilogue never writes the score matrix: every accumulator element is compared with its query's running threshold
+// tau[q] and only the survivors are appended to that query's candidate buffer in HBM.
 //
 // The thresholds come from the data itself.  The corpus is visited in PHASES over a pseudo-random permutation
 // of its 256-row super-tiles: phase 0 is a small sample scanned with tau = -inf (everything is kept), after each
-// phase `cut_kernel` sorts every query's buffer, keeps its K' best and sets tau[q] to the K'-th approximate score
-// seen so far.  Each phase visits `growth` times the rows seen before it, so it appends about growth x K'
+// phase `gemm_cut_kernel` radix-selects the K' best of every query's buffer and sets tau[q] to the K'-th approximate
+// score seen so far.  Each phase visits `growth` times the rows seen before it, so it appends about growth x K'
 // candidates per query and the whole scan writes O(K' log(n_rows)) entries per query instead of n_rows.
 // A row that is dropped anywhere has a(r) <= tau at that moment <= the final K'-th score, which is the
 // `out_thresh` contract of tt_scan_topk_bf16 with a single list per query -- stage 2 (rescore.cu) and the
@@ -38,12 +38,12 @@ struct Params {
     int n_super;          // 256-row super-tiles in the corpus
     int n_chunks;         // dim / 64
     int stages;
-    int n_qb;             // 256-query blocks
+    int n_qb;             // NQB-query blocks
     int i0, i1;           // this phase: permuted super-tile indices [i0, i1)
     uint32_t perm_mul;    // super = (i * perm_mul) % n_super, gcd(perm_mul, n_super) == 1
-    const float* tau;     // [n_qb * 256] running thresholds (+inf in the padding columns)
+    const float* tau;     // [>= n_qb * NQB] running thresholds (+inf in the padding columns)
     unsigned long long* buf;  // [n_q, cap] packed (approx key, local row) entries
-    int* cnt;             // [n_qb * 256] entries appended so far (may exceed cap: overflow)
+    int* cnt;             // [>= n_qb * NQB] entries appended so far (may exceed cap: overflow)
     int cap;
 };
 
