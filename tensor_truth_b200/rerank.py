@@ -31,6 +31,7 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Any, Callable, List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -121,6 +122,8 @@ class B200CrossEncoder:
         self.max_length = int(max_length)
         self.lib = _lib.lib()
         self._dev_index = weights.device.index if weights.device.index is not None else torch.cuda.current_device()
+        self._pin: Optional[torch.Tensor] = None   # pinned staging buffer for the packed token ids / positions / offsets
+        self._pin_free = None
 
     # ---- kernels
     def _stream(self):
@@ -157,26 +160,37 @@ class B200CrossEncoder:
         n = len(token_lists)
         if n == 0:
             return torch.empty((0,), dtype=torch.float32, device=w.device)
-        lens = [min(len(t), self.max_length) for t in token_lists]
-        if min(lens) == 0:
+        lens = np.fromiter((min(len(t), self.max_length) for t in token_lists), dtype=np.int64, count=n)
+        if int(lens.min()) == 0:
             raise ValueError("empty token list")
-        s_max, total = max(lens), sum(lens)
-        flat, pos, dest, first = [], [], [], []
-        for i, (t, ln) in enumerate(zip(token_lists, lens)):
-            first.append(len(flat))
-            flat.extend(t[:ln])
-            pos.extend(range(w.pad_id + 1, w.pad_id + 1 + ln))   # RoBERTa position ids start after the padding index
-            dest.extend(range(i * s_max, i * s_max + ln))
+        s_max, total = int(lens.max()), int(lens.sum())
+        # pack on the host in ONE int32 buffer [ids | positions | cu_seqlens] -> one pinned H2D copy
+        first = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=first[1:])
+        need = 2 * total + n + 1
+        if self._pin is None or self._pin.numel() < need:
+            self._pin = torch.empty(max(need, 2 * self._pin.numel() if self._pin is not None else 0), dtype=torch.int32).pin_memory()
+            self._pin_free = torch.cuda.Event()
+        else:
+            self._pin_free.synchronize()  # the previous call's H2D copy has consumed the staging buffer
+        host = self._pin[:need]
+        hv = host.numpy()
+        for i, t in enumerate(token_lists):
+            hv[first[i]:first[i + 1]] = t[:lens[i]] if len(t) > lens[i] else t
+        # RoBERTa position ids start after the padding index: pad_id + 1 + offset inside the pair
+        hv[total:2 * total] = np.arange(total) - np.repeat(first[:-1], lens) + (w.pad_id + 1)
+        hv[2 * total:] = first
         dev = w.device
         with torch.cuda.device(dev):
-            ids_d = torch.tensor(flat, dtype=torch.int32).to(dev, non_blocking=True)
-            pos_d = torch.tensor(pos, dtype=torch.int32).to(dev, non_blocking=True)
-            first_d = torch.tensor(first, dtype=torch.int64).to(dev, non_blocking=True)
-            cu_d = torch.tensor(first + [total], dtype=torch.int32).to(dev, non_blocking=True)
+            packed = host.to(dev, non_blocking=True)
+            self._pin_free.record()
+            ids_d, pos_d, cu_d = packed[:total], packed[total:2 * total], packed[2 * total:]
+            first_d = cu_d[:-1].long()
             dest_d = key_mask = None
             if _varlen_attn is None:
-                dest_d = torch.tensor(dest, dtype=torch.int64).to(dev, non_blocking=True)
-                key_mask = (torch.arange(s_max, device=dev)[None, :] < torch.tensor(lens, device=dev)[:, None])[:, None, None, :]
+                dest = np.arange(total) - np.repeat(first[:-1], lens) + np.repeat(np.arange(n) * s_max, lens)
+                dest_d = torch.from_numpy(dest).to(dev, non_blocking=True)
+                key_mask = (torch.arange(s_max, device=dev)[None, :] < torch.from_numpy(lens).to(dev)[:, None])[:, None, None, :]
             x = torch.empty((total, w.hidden), dtype=torch.bfloat16, device=dev)
             check(self.lib.tt_embed_layernorm_bf16(ptr(ids_d), ptr(pos_d), total, w.hidden, ptr(w.word_emb), ptr(w.pos_emb),
                                                    ptr(w.type_emb), ptr(w.emb_ln_g), ptr(w.emb_ln_b), w.eps, ptr(x),
