@@ -41,3 +41,37 @@ def test_gpu_arm_does_not_fall_back_to_the_cpu():
         return  # the GPU arm itself is exercised on the GPU box (gpurun)
     p = _run("--steps", "1", "--rows", "4096", "--skip", "batch64,wide,cpu")
     assert p.returncode != 0 and p.stdout.strip() == ""
+
+
+def test_gpu_arm_prints_one_json_line_with_the_contract_keys():
+    """On a GPU box: the default arm on a small corpus -- ONE stdout line, every key the driver and the judge read."""
+    import pytest
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    p = _run("--rows", "300000", "--steps", "20", "--warmup", "3", "--wide-batch", "512", "--wide-k", "10", "--cpu-sample-rows", "65536")
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["warmup"] >= 3 and d["vs_baseline"] is None and d["value"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["bytes_per_launch"] == 300000 * 1024 * 2
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 and e["d2h_bytes_per_step"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
+    assert d["gpu_launches"] == 20 * 5 and "workload" in d["config"] and "l2" in d["config"]
+    assert d["clocks"]["sm_max_mhz"] and isinstance(d["clocks"]["reasons"], list)
+    assert d["parity_vs_gpu_exact_scan"] is True and d["certificate_failures"] == 0
+    w = d["wide"]
+    assert w["roofline"]["bound"] == "tensor" and w["gemm_path"] and w["parity_vs_gpu_exact_scan_local_shard"] is True
+
+
+test_gpu_arm_prints_one_json_line_with_the_contract_keys = __import__("pytest").mark.gpu(
+    test_gpu_arm_prints_one_json_line_with_the_contract_keys)
