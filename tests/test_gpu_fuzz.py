@@ -56,3 +56,22 @@ def test_random_shapes_against_the_strict_oracle(seed):
     assert (g_ids == ids_o).all(), cfg
     assert (g_keys == keys_o).all(), cfg
     assert (g_sc == sc_o).all(), cfg
+
+
+@pytest.mark.parametrize("dim", [8, 72, 96, 200])
+@pytest.mark.parametrize("b", [1, 40, 130])
+def test_widths_the_tensor_core_kernels_do_not_take(dim, b):
+    """Embedding widths that are not multiples of 64 / 128 go through the CUDA-core scan, whatever the batch size."""
+    rng = np.random.default_rng(dim * 7 + b)
+    c = rng.standard_normal((6000, dim)).astype(np.float32)
+    c[17] = c[4000]
+    bits = oracle.f32_to_bf16_bits(c)
+    q = rng.standard_normal((b, dim)).astype(np.float32)
+    q[0] = oracle.bf16_bits_to_f32(bits[17])
+    ids_o, sc_o, keys_o = cport.scan_topk(bits, q, 7)
+    idx = DeviceIndex(bits, None, device=torch.device("cuda:0"))
+    assert not idx._use_gemm(b) or dim % 64 == 0
+    r = idx.search_certified(torch.from_numpy(q).cuda(), 7)
+    torch.cuda.synchronize()
+    assert (r.ids.cpu().numpy() == ids_o).all() and (r.scores.cpu().numpy() == sc_o).all()
+    assert r.ids[0, :2].tolist() == [17, 4000]
