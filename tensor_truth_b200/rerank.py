@@ -31,6 +31,9 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Any, Callable, List, Optional, Sequence, Tuple
 
+import os
+import threading
+
 import numpy as np
 import torch
 
@@ -38,6 +41,9 @@ from . import _lib
 from ._lib import check, ptr
 
 ACT_NONE, ACT_GELU = 0, 1
+GRAPH_MAX_TOKENS = 4096    # calls with more packed tokens are GPU-bound: no graph
+GRAPH_TOKEN_STEP = 256     # token-count granularity of the graph buckets
+GRAPH_MAX_BUCKETS = 12     # captured graphs kept per encoder (each holds its activations: ~20 KB per token)
 
 try:  # PyTorch >= 2.10: attention over packed sequences (cu_seqlens), no padding
     from torch.nn.attention.varlen import varlen_attn as _varlen_attn
@@ -124,6 +130,8 @@ class B200CrossEncoder:
         self._dev_index = weights.device.index if weights.device.index is not None else torch.cuda.current_device()
         self._pin: Optional[torch.Tensor] = None   # pinned staging buffer for the packed token ids / positions / offsets
         self._pin_free = None
+        self._graphs: dict = {}
+        self._lock = threading.Lock()              # staging buffers and graphs are per encoder: one call at a time
 
     # ---- kernels
     def _stream(self):
@@ -155,6 +163,101 @@ class B200CrossEncoder:
         out = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=key_mask)
         return out.permute(0, 2, 1, 3).reshape(n * s_max, h)[dest].contiguous()
 
+    def _forward(self, packed: torch.Tensor, total: int, n: int, s_max: int, lens_np=None) -> torch.Tensor:
+        """Device forward over the packed int32 buffer ``[ids T | positions T | cu_seqlens n+1]`` -> logits ``[n]``."""
+        w = self.w
+        dev = w.device
+        ids_d, pos_d, cu_d = packed[:total], packed[total:2 * total], packed[2 * total:2 * total + n + 1]
+        first_d = cu_d[:-1].long()
+        dest_d = key_mask = None
+        if _varlen_attn is None:
+            lens_d = (cu_d[1:] - cu_d[:-1]).long()
+            within = torch.arange(total, device=dev) - torch.repeat_interleave(first_d, lens_d)
+            dest_d = within + torch.repeat_interleave(torch.arange(n, device=dev) * s_max, lens_d)
+            key_mask = (torch.arange(s_max, device=dev)[None, :] < lens_d[:, None])[:, None, None, :]
+        x = torch.empty((total, w.hidden), dtype=torch.bfloat16, device=dev)
+        check(self.lib.tt_embed_layernorm_bf16(ptr(ids_d), ptr(pos_d), total, w.hidden, ptr(w.word_emb), ptr(w.pos_emb),
+                                               ptr(w.type_emb), ptr(w.emb_ln_g), ptr(w.emb_ln_b), w.eps, ptr(x), self._stream()))
+        for L in w.layers:
+            qkv = self._linear(x, L.w_qkv, L.b_qkv)
+            ctx = self._attention(qkv, cu_d, dest_d, n, s_max, key_mask)
+            x = self._layernorm(self._linear(ctx, L.w_o, L.b_o, residual=x), L.ln1_g, L.ln1_b)
+            hdn = self._linear(x, L.w_ff1, L.b_ff1, act=ACT_GELU)
+            x = self._layernorm(self._linear(hdn, L.w_ff2, L.b_ff2, residual=x), L.ln2_g, L.ln2_b)
+        cls = x[first_d].float()                                  # the <s> token of every pair
+        hid = torch.tanh(cls @ w.head_w1.T + w.head_b1)
+        return (hid @ w.head_w2.T + w.head_b2).squeeze(-1)
+
+    @staticmethod
+    def _pack(hv: np.ndarray, token_lists, lens: np.ndarray, total: int, pad_id: int) -> None:
+        """Fill ``hv`` = [ids total | positions total | cu_seqlens n+1] (int32) for the given (already clipped) lengths."""
+        n = len(lens)
+        first = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=first[1:])
+        for i, t in enumerate(token_lists):
+            hv[first[i]:first[i + 1]] = t[:lens[i]] if len(t) > lens[i] else t
+        # RoBERTa position ids start after the padding index: pad_id + 1 + offset inside the pair
+        hv[total:2 * total] = np.arange(total) - np.repeat(first[:-1], lens) + (pad_id + 1)
+        hv[2 * total:2 * total + n + 1] = first
+
+    def _graph_bucket(self, total: int, n: int):
+        """Small calls (the interactive case: ~10 nodes of a few hundred tokens) are launch-bound -- ~170 launches for
+        ~1 ms of GPU work -- so their forward pass is replayed as ONE CUDA graph.  Graphs need fixed shapes: the call is
+        padded to a bucket (tokens to a multiple of GRAPH_TOKEN_STEP, pairs to a power of two) with dummy one-token-or-
+        longer sequences whose outputs are ignored; a bucket is captured on its second use, at most GRAPH_MAX_BUCKETS
+        are kept.  Returns None when the call is too large (GPU-bound: eager is as fast) or graphs are disabled."""
+        if _varlen_attn is None or total > GRAPH_MAX_TOKENS or os.environ.get("TT_NO_GRAPH"):
+            return None
+        n_b = 2
+        while n_b < n + 1:
+            n_b *= 2
+        t_b = (total + (n_b - n) + GRAPH_TOKEN_STEP - 1) // GRAPH_TOKEN_STEP * GRAPH_TOKEN_STEP
+        if t_b - total > (n_b - n) * self.max_length:
+            return None
+        key = (t_b, n_b)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= GRAPH_MAX_BUCKETS:
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._graphs[key] = {"uses": 0, "graph": None, "dead": False}
+        g["uses"] += 1
+        from .index import _CAPTURE_LOCK  # one capture at a time per process
+
+        if g["graph"] is None and not g["dead"] and g["uses"] >= 2 and _CAPTURE_LOCK.acquire(blocking=False):
+            try:
+                dev = self.w.device
+                host = torch.zeros(2 * t_b + n_b + 1, dtype=torch.int32).pin_memory()
+                # a valid dummy problem for the capture run: n_b sequences of equal length
+                lens0 = np.full(n_b, t_b // n_b, dtype=np.int64)
+                lens0[: t_b - int(lens0.sum())] += 1
+                self._pack(host.numpy(), [[0] * int(x) for x in lens0], lens0, t_b, self.w.pad_id)
+                dev_in = torch.zeros_like(host, device=dev)
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):  # warm-up outside the capture (library kernels may initialise lazily)
+                    dev_in.copy_(host, non_blocking=True)
+                    self._forward(dev_in, t_b, n_b, self.max_length)
+                side.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                    dev_in.copy_(host, non_blocking=True)
+                    out = self._forward(dev_in, t_b, n_b, self.max_length)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                # dev_in is what the graph's kernels read: it must live as long as the graph
+                g.update(graph=graph, host=host, dev_in=dev_in, out=out, done=torch.cuda.Event())
+            except Exception as exc:  # capture refused: this bucket stays eager
+                import warnings
+
+                warnings.warn(f"tensor_truth_b200: CUDA-graph capture of the cross-encoder failed ({exc}); staying eager")
+                g["dead"] = True
+                try:
+                    torch.cuda.synchronize(self.w.device)
+                except Exception:
+                    pass
+            finally:
+                _CAPTURE_LOCK.release()
+        return (g, t_b, n_b) if g["graph"] is not None else None
+
     def logits(self, token_lists: Sequence[Sequence[int]]) -> torch.Tensor:
         w = self.w
         n = len(token_lists)
@@ -164,46 +267,34 @@ class B200CrossEncoder:
         if int(lens.min()) == 0:
             raise ValueError("empty token list")
         s_max, total = int(lens.max()), int(lens.sum())
-        # pack on the host in ONE int32 buffer [ids | positions | cu_seqlens] -> one pinned H2D copy
-        first = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(lens, out=first[1:])
-        need = 2 * total + n + 1
-        if self._pin is None or self._pin.numel() < need:
-            self._pin = torch.empty(max(need, 2 * self._pin.numel() if self._pin is not None else 0), dtype=torch.int32).pin_memory()
-            self._pin_free = torch.cuda.Event()
-        else:
-            self._pin_free.synchronize()  # the previous call's H2D copy has consumed the staging buffer
-        host = self._pin[:need]
-        hv = host.numpy()
-        for i, t in enumerate(token_lists):
-            hv[first[i]:first[i + 1]] = t[:lens[i]] if len(t) > lens[i] else t
-        # RoBERTa position ids start after the padding index: pad_id + 1 + offset inside the pair
-        hv[total:2 * total] = np.arange(total) - np.repeat(first[:-1], lens) + (w.pad_id + 1)
-        hv[2 * total:] = first
-        dev = w.device
-        with torch.cuda.device(dev):
-            packed = host.to(dev, non_blocking=True)
+        with self._lock, torch.cuda.device(w.device):
+            bucket = self._graph_bucket(total, n)
+            if bucket is not None:
+                g, t_b, n_b = bucket
+                if g.get("busy"):
+                    g["done"].synchronize()          # the previous replay has consumed the staging buffer
+                # dummy sequences soak up the padding: every one gets at least one token, none more than max_length
+                pad = np.full(n_b - n, (t_b - total) // (n_b - n), dtype=np.int64)
+                pad[: (t_b - total) - int(pad.sum())] += 1
+                lens_b = np.concatenate([lens, pad])
+                lists_b = list(token_lists) + [[w.pad_id + 2] * int(x) for x in pad]
+                self._pack(g["host"].numpy(), lists_b, lens_b, t_b, w.pad_id)
+                g["graph"].replay()
+                g["done"].record()
+                g["busy"] = True
+                return g["out"][:n].clone()
+            # eager: pack on the host in ONE int32 buffer [ids | positions | cu_seqlens] -> one pinned H2D copy
+            need = 2 * total + n + 1
+            if self._pin is None or self._pin.numel() < need:
+                self._pin = torch.empty(max(need, 2 * self._pin.numel() if self._pin is not None else 0), dtype=torch.int32).pin_memory()
+                self._pin_free = torch.cuda.Event()
+            else:
+                self._pin_free.synchronize()  # the previous call's H2D copy has consumed the staging buffer
+            host = self._pin[:need]
+            self._pack(host.numpy(), token_lists, lens, total, w.pad_id)
+            packed = host.to(w.device, non_blocking=True)
             self._pin_free.record()
-            ids_d, pos_d, cu_d = packed[:total], packed[total:2 * total], packed[2 * total:]
-            first_d = cu_d[:-1].long()
-            dest_d = key_mask = None
-            if _varlen_attn is None:
-                dest = np.arange(total) - np.repeat(first[:-1], lens) + np.repeat(np.arange(n) * s_max, lens)
-                dest_d = torch.from_numpy(dest).to(dev, non_blocking=True)
-                key_mask = (torch.arange(s_max, device=dev)[None, :] < torch.from_numpy(lens).to(dev)[:, None])[:, None, None, :]
-            x = torch.empty((total, w.hidden), dtype=torch.bfloat16, device=dev)
-            check(self.lib.tt_embed_layernorm_bf16(ptr(ids_d), ptr(pos_d), total, w.hidden, ptr(w.word_emb), ptr(w.pos_emb),
-                                                   ptr(w.type_emb), ptr(w.emb_ln_g), ptr(w.emb_ln_b), w.eps, ptr(x),
-                                                   self._stream()))
-            for L in w.layers:
-                qkv = self._linear(x, L.w_qkv, L.b_qkv)
-                ctx = self._attention(qkv, cu_d, dest_d, n, s_max, key_mask)
-                x = self._layernorm(self._linear(ctx, L.w_o, L.b_o, residual=x), L.ln1_g, L.ln1_b)
-                hdn = self._linear(x, L.w_ff1, L.b_ff1, act=ACT_GELU)
-                x = self._layernorm(self._linear(hdn, L.w_ff2, L.b_ff2, residual=x), L.ln2_g, L.ln2_b)
-            cls = x[first_d].float()                              # the <s> token of every pair
-            hid = torch.tanh(cls @ w.head_w1.T + w.head_b1)
-            return (hid @ w.head_w2.T + w.head_b2).squeeze(-1)
+            return self._forward(packed, total, n, s_max)
 
 
 class B200CrossEncoderRerank:

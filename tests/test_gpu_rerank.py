@@ -116,3 +116,24 @@ def test_postprocess_nodes_semantics():
     with pytest.raises(ValueError):
         rr.postprocess_nodes(list(nodes))          # upstream: "Missing query bundle in extra info."
     assert rr.postprocess_nodes([], query_bundle=qb) == []
+
+
+def test_small_calls_replay_a_cuda_graph_and_match_the_eager_path(monkeypatch):
+    """Interactive-size calls are launch-bound and are replayed as a bucketed CUDA graph (padding: dummy sequences);
+    the replay must give what the eager path gives for the real pairs, call after call, for different token counts
+    falling into the same bucket."""
+    vocab = 4000
+    model = _model(256, 3, 4, 1024, vocab, seed=11)
+    rng = np.random.default_rng(11)
+    enc = B200CrossEncoder(CrossEncoderWeights.from_hf_model(model, "cuda:0"))
+    monkeypatch.setenv("TT_NO_GRAPH", "1")
+    batches = [_tokens(rng, 6, vocab, 60, 100) for _ in range(5)]          # ~480 tokens each: one (768, 8) bucket
+    eager = [enc.logits(b).clone() for b in batches]
+    monkeypatch.delenv("TT_NO_GRAPH")
+    got = [enc.logits(b).clone() for b in batches]
+    torch.cuda.synchronize()
+    assert any(g["graph"] is not None for g in enc._graphs.values()), "no bucket was captured"
+    for a, b in zip(eager, got):
+        assert float((a - b).abs().max()) < 2e-3
+    ref = _hf_logits(model, batches[4])
+    assert float((got[4] - ref).abs().max()) < 0.03
