@@ -396,6 +396,7 @@ def run_b200(args):
         from oracle import cport
 
         cport.build()
+        cport.use_all_host_threads()
         sec, done = cpu_arm(bits, inv_h, sc.tree, q_host.numpy(), TOP_K, 40, 2)
         cpu = {"value": (1.0 / sec) * (sample / n_rows), "unit": UNIT, "cores": cport.fast_threads(), "kind": "port",
                "sample": f"{done} batch-1 queries over the first {sample} of {n_rows} rows ({sec * 1e3:.1f} ms each), "
@@ -445,6 +446,7 @@ def run_reference(args):
     from tensor_truth_b200.synth import SynthCorpus
 
     cport.build()
+    cport.use_all_host_threads()  # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is the all-cores baseline
     n_rows = args.rows
     sample = min(args.cpu_sample_rows, n_rows)
     dev = "cuda" if torch.cuda.is_available() else "cpu"

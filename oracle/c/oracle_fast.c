@@ -49,6 +49,16 @@ int oracle_fast_threads(void) {
 #endif
 }
 
+/* The timed CPU arm is meant to use every host thread it can; launchers such as torchrun export OMP_NUM_THREADS=1
+ * to their workers, which the OpenMP runtime has already read by the time this library loads. */
+void oracle_fast_set_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 #define QB 4 /* queries scored per pass over a row */
 
 #if defined(__AVX2__) && defined(__FMA__)

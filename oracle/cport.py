@@ -36,6 +36,8 @@ def lib():
         L.oracle_fast_scan_topk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         L.oracle_fast_threads.restype = C.c_int
+        L.oracle_fast_set_threads.restype = None
+        L.oracle_fast_set_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -79,6 +81,19 @@ def auto_merge(pairs, parent_of, child_count, prev_id, next_id, ratio_thresh=0.5
 
 def fast_threads() -> int:
     return int(lib().oracle_fast_threads())
+
+
+def use_all_host_threads() -> int:
+    """Give the fast CPU arm every CPU this process may run on, whatever OMP_NUM_THREADS a launcher exported
+    (torchrun sets it to 1 for its workers).  Returns the thread count now in use."""
+    import os
+
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        n = os.cpu_count() or 1
+    lib().oracle_fast_set_threads(int(n))
+    return fast_threads()
 
 
 def fast_scan_topk(corpus_bits: np.ndarray, inv_norm: np.ndarray, queries: np.ndarray, k: int, id_base: int = 0):

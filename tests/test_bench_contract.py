@@ -27,6 +27,17 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert "workload" in d["config"] and d["data"] == "synthetic" and d["gpu_launches"] == 0
 
 
+def test_reference_arm_uses_every_host_thread_even_under_a_launcher():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is the all-cores baseline regardless."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--rows", "131072",
+                        "--steps", "3", "--warmup", "3", "--cpu-sample-rows", "65536"], capture_output=True, text=True, cwd=ROOT,
+                       env=env, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads(p.stdout.strip().splitlines()[-1])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0)) and d["n_gpus"] == 2
+
+
 def test_reference_arm_other_ranks_exit_quietly():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
