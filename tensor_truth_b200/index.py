@@ -33,7 +33,8 @@ from .tree import NodeTree
 EPS_BF16_CORPUS = 2.5e-4   # corpus stored in bf16: hi/lo split residual + fp32 accumulation + inv_norm rounding
 EPS_F32_CORPUS = 4.2e-3    # fp32 master scanned through a bf16 shadow: + 2^-8 corpus rounding
 EPS_HI_ONLY = 3.95e-3      # added when the query travels as bf16 hi only (|q - bf16(q)| <= 2^-8 |q|)
-HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first (64 queries per corpus pass)
+HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first.  (17-32 queries hi-only through the GEMM-shaped scan were
+                           # measured at 3.4 ms against 3.56 ms hi+lo: not worth giving up the tight certificate bound by default)
 MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist workspace: 148 * K' * 12 B per query)
 GEMM_ABOVE = 33            # hi-only batches at least this large take the GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass
                            # per 4096 queries, one list per query (64 queries: 3.04 ms at 10M rows vs 3.35 ms for the pair kernel)

@@ -250,9 +250,9 @@ def test_c1_batch64_hi_only_single_pass(c1, stage1, monkeypatch):
     torch.cuda.synchronize()
     assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
     assert idx.retries == int((~proven).sum())
-    # 20 and 32 queries: hi+lo with N = 64 columns
+    # 20 and 32 queries, hi+lo on request: N = 64 columns of the batch kernel
     for b in (20, 32):
-        r = idx.search(qd[:b], 10)
+        r = idx.search(qd[:b], 10, hi_only=False)
         torch.cuda.synchronize()
         assert r.eps == idx.eps and (_np(r.margin) > r.eps).all()
         assert (_np(r.ids) == ids_o[:b]).all() and (_np(r.scores) == sc_o[:b]).all()
