@@ -14,7 +14,6 @@ import torch
 from oracle.multi_index import MultiIndexRetriever  # the caller restatement (pinned against the reference's class)
 from tensor_truth_b200.index import DeviceIndex
 from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200MultiIndexRetriever, B200VectorIndexRetriever
-from tensor_truth_b200.schema import QueryBundle
 from tensor_truth_b200.segmented import SegmentedIndex
 from tensor_truth_b200.synth import SynthCorpus
 

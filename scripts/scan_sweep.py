@@ -1,7 +1,6 @@
 """Times the stage-1 launch alone for several batch sizes / modes (tuning aid; run on the GPU box)."""
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
