@@ -136,13 +136,14 @@ def build_shard(n_rows, rank, world, device, levels=None):
     return sc, corpus, inv, lo, hi
 
 
-def make_queries(sc, corpus, lo, hi, n_q, world):
+def make_queries(sc, corpus, lo, hi, n_q, world, first=0, lookup=None):
     import torch.distributed as dist
 
-    def lookup(t):
-        return corpus[t - lo] if lo <= t < hi else None
+    if lookup is None:
+        def lookup(t):
+            return corpus[t - lo] if lo <= t < hi else None
 
-    q = sc.queries(n_q, lookup=lookup)
+    q = sc.queries(n_q, first=first, lookup=lookup)
     if world > 1:
         qd = q.cuda()
         dist.all_reduce(qd)  # every target row is owned by exactly one rank; the other ranks contribute zeros
@@ -152,7 +153,7 @@ def make_queries(sc, corpus, lo, hi, n_q, world):
 
 def cpu_arm(bits, inv_norm, tree, queries, k, n_steps, n_warm, budget_s=25.0):
     """The CPU restatement in its fast mode on every host thread (oracle/c/oracle_fast.c + oracle/automerge.py):
-    one step = one batch-1 query over the sample rows + auto-merge.  Returns (seconds per step, steps run)."""
+    one step = one batch-1 query over the rows given + auto-merge.  Returns (seconds per step, steps run)."""
     import oracle
     from oracle import cport
 
@@ -174,95 +175,162 @@ def cpu_arm(bits, inv_norm, tree, queries, k, n_steps, n_warm, budget_s=25.0):
     return (time.perf_counter() - t0) / done, done
 
 
+def host_can_hold(n_bytes: int) -> bool:
+    """Whether the CPU arm may keep ``n_bytes`` of corpus in host memory (with the same again as slack)."""
+    try:
+        import psutil
+
+        return psutil.virtual_memory().available > 2 * n_bytes + (8 << 30)
+    except Exception:
+        return False
+
+
+def to_host_bits(corpus: torch.Tensor) -> np.ndarray:
+    """bf16 device rows -> uint16 host array, copied in 1 GB slices through a pinned bounce buffer."""
+    n, d = int(corpus.shape[0]), int(corpus.shape[1])
+    out = np.empty((n, d), dtype=np.uint16)
+    step = max(1, (1 << 30) // (2 * d))
+    pin = torch.empty((step, d), dtype=torch.int16).pin_memory()
+    view = corpus.view(torch.int16)
+    for a in range(0, n, step):
+        m = min(step, n - a)
+        pin[:m].copy_(view[a:a + m])
+        out[a:a + m] = pin[:m].numpy().view(np.uint16)
+    return out
+
+
 # --------------------------------------------------------------------------- this repo's arm
-def run_b200(args):
-    import torch.distributed as dist
+class Bench:
+    """One corpus resident on this rank + the timing loops over it.  ``run_b200`` builds one per section."""
 
-    from tensor_truth_b200 import _lib
-    from tensor_truth_b200.index import DeviceIndex
-    from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200VectorIndexRetriever
-    from tensor_truth_b200.schema import QueryBundle
-    from tensor_truth_b200.sharded import ShardedIndex
+    def __init__(self, ctx, n_rows, levels, k, kprime, variant, n_pool=QUERY_POOL, master_f32=False):
+        from tensor_truth_b200.index import DeviceIndex
+        from tensor_truth_b200.sharded import ShardedIndex
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
-    torch.cuda.set_device(local_rank)
-    device = torch.device(f"cuda:{local_rank}")
-    if world > 1:
-        # NCCL writes its version banner (any NCCL_DEBUG level >= VERSION, which this image sets) and its logs to stdout;
-        # rank 0 must print ONE line there
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
-            os.environ["NCCL_DEBUG"] = "NONE"
-        dist.init_process_group("nccl", device_id=device)
-    _lib.lib()  # fail loudly if the CUDA library is missing
+        self.ctx = ctx
+        self.k = k
+        self.n_rows = n_rows
+        self.sc, corpus, inv, self.lo, self.hi = build_shard(n_rows, ctx.rank, ctx.world, ctx.device, levels)
+        self.queries = make_queries(self.sc, corpus, self.lo, self.hi, n_pool, ctx.world).to(ctx.device)
+        self.corpus_bf16, self.inv = corpus, inv
+        if master_f32:
+            # an fp32 store (what a real bge-m3 index holds, indexing/builder.py:437-442): the canonical bf16 rows plus
+            # low-order mantissa bits the bf16 shadow cannot represent (deterministic, relative size ~2^-9)
+            master = torch.empty((self.hi - self.lo, DIM), dtype=torch.float32, device=ctx.device)
+            step = 1 << 20
+            for a in range(0, self.hi - self.lo, step):
+                c = corpus[a:a + step].float()
+                g = torch.Generator(device=ctx.device)
+                g.manual_seed(SEED * 31 + (self.lo + a) // step)
+                master[a:a + step] = c * (1.0 + (2.0 ** -9) * (torch.rand(c.shape, generator=g, device=ctx.device) - 0.5))
+            self.idx = DeviceIndex(master, self.sc.tree, id_base=self.lo, device=ctx.device, kprime=kprime, variant=variant)
+            del master
+        else:
+            self.idx = DeviceIndex(corpus, self.sc.tree, inv_norm=inv, id_base=self.lo, device=ctx.device, kprime=kprime,
+                                   variant=variant)
+        self.sharded = ShardedIndex(self.idx) if ctx.world > 1 else None
+        self.rows_local = self.hi - self.lo
 
-    n_rows = args.rows
-    sc, corpus, inv, lo, hi = build_shard(n_rows, rank, world, device)
-    queries = make_queries(sc, corpus, lo, hi, QUERY_POOL, world).to(device)
-    variant = {"auto": _lib.SCAN_AUTO, "simt": _lib.SCAN_SIMT, "tcgen05": _lib.SCAN_TCGEN05}[args.variant]
-    idx = DeviceIndex(corpus, sc.tree, inv_norm=inv, id_base=lo, device=device, kprime=args.kprime, variant=variant)
-    sharded = ShardedIndex(idx) if world > 1 else None
-    peak, peak_src = measured_peaks()
+    @classmethod
+    def head_of(cls, parent: "Bench", n_head: int, k: int, variant):
+        """A Bench over the first ``n_head`` rows of every rank's shard of ``parent`` (shared memory, own index): how the
+        C4 section gets 6.25M rows per GPU out of the C3 corpus without generating another one."""
+        from tensor_truth_b200.index import DeviceIndex
+        from tensor_truth_b200.sharded import ShardedIndex
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        ctx = parent.ctx
+        w = cls.__new__(cls)
+        w.ctx, w.k, w.sc = ctx, k, parent.sc
+        w.lo, w.hi, w.rows_local, w.n_rows = parent.lo, parent.lo + n_head, n_head, n_head * ctx.world
+        w.corpus_bf16, w.inv = parent.corpus_bf16[:n_head], parent.inv[:n_head]
+        w.idx = DeviceIndex(w.corpus_bf16, parent.sc.tree, inv_norm=w.inv, id_base=parent.lo, device=ctx.device, variant=variant)
+        w.sharded = ShardedIndex(w.idx) if ctx.world > 1 else None
+        w.queries = parent.queries
+        # a query's target row t of the parent corpus is answered by its owner with row (t - lo) % n_head of the head
+        p_lo, p_hi, head = parent.lo, parent.hi, w.corpus_bf16
+        w.query_lookup = lambda t: head[(t - p_lo) % n_head] if p_lo <= t < p_hi else None
+        return w
 
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    query_lookup = None
 
-    from tensor_truth_b200.index import MergeResult
+    def close(self):
+        if self.sharded is not None:
+            self.sharded.close()
+        else:
+            self.idx.close()
+        self.corpus_bf16 = self.inv = self.queries = None
+        torch.cuda.empty_cache()
 
-    def timed(batch: int, steps: int, warm: int, sample_clocks: bool, depth: int, k: int = 0, pool=None):
-        """K steps of the device pipeline.  depth = 1: strictly serial, with CUDA events around every stage-1
-        launch (the roofline numbers).  depth = 2: steps alternate between two streams, so step i+1's scan
-        overlaps step i's re-score / select / (all-gather, merge) / auto-merge -- the throughput configuration."""
-        margins = torch.full((steps + warm, batch), float("inf"), dtype=torch.float32, device=device)
-        k = k or TOP_K
-        pool = queries if pool is None else pool
+    # ---- one step, eager (serial loop: per-kernel events) and as a graph (pipelined loop)
+    def step_graph(self, batch, k, lane):
+        if self.sharded is not None and self.sharded.transport == "peer":
+            return self.sharded.step_graph(batch, k, 0.5, lane)
+        if self.sharded is None:
+            return self.idx.step_graph(batch, k, 0.5, lane)
+        return None  # NCCL transport: eager steps
+
+    def timed(self, batch: int, steps: int, warm: int, sample_clocks: bool, depth: int, k: int = 0, pool=None):
+        """K steps of the device pipeline, queries resident in HBM.
+        depth = 1: strictly serial on one stream, eager launches with CUDA events around every stage-1 launch (the
+        roofline numbers; the host stays ahead of the GPU, so the events see device time only).
+        depth = 2: the throughput configuration -- every lane (stream) replays the CUDA graph of the whole step
+        (prepare -> scan -> re-score+select(+push) -> (flag-wait+merge+)auto-merge), steps alternate between the lanes, so
+        step i+1's scan overlaps step i's tail.  Both loops start behind a device-side rendezvous of all ranks."""
+        from tensor_truth_b200.index import MergeResult
+
+        ctx, idx, sharded = self.ctx, self.idx, self.sharded
+        device = ctx.device
+        k = k or self.k
+        pool = self.queries if pool is None else pool
         n_pool = max(1, int(pool.shape[0]) // batch)
+        margins = torch.full((steps + warm, batch), float("inf"), dtype=torch.float32, device=device)
         streams = [torch.cuda.Stream(device) for _ in range(depth)]
-        bufs = [idx._buffers(batch, k, slot=s) for s in range(depth)]
-        mouts = [MergeResult(torch.empty((batch, 2 * k), dtype=torch.int64, device=device),
-                             torch.empty((batch, 2 * k), dtype=torch.float64, device=device),
-                             torch.empty((batch,), dtype=torch.int32, device=device)) for _ in range(depth)]
         eps = [idx.eps]
+        graphs = [self.step_graph(batch, k, s) for s in range(depth)] if depth > 1 else [None]
+        use_graph = graphs[0] is not None
+        launches = [0]
+        if not use_graph:
+            bufs = [idx._buffers(batch, k, slot=s) for s in range(depth)]
+            mouts = [MergeResult(torch.empty((batch, 2 * k), dtype=torch.int64, device=device),
+                                 torch.empty((batch, 2 * k), dtype=torch.float64, device=device),
+                                 torch.empty((batch,), dtype=torch.int32, device=device)) for _ in range(depth)]
 
         def one(i):
             s = i % depth
+            q = pool[(i % n_pool) * batch:(i % n_pool) * batch + batch]
             with torch.cuda.stream(streams[s]):
-                q = pool[(i % n_pool) * batch:(i % n_pool) * batch + batch]
+                if use_graph:
+                    g = graphs[s]
+                    g.q.copy_(q, non_blocking=True)
+                    g.replay()
+                    margins[i].copy_(g.result.margin, non_blocking=True)
+                    eps[0] = g.eps
+                    return g.merged
                 if sharded is None:
                     w = dict(bufs[s])
                     w["margin"] = margins[i]
-                    r = idx.search(q, k, out=w)
+                    r = idx.search(q, k, out=w, am=idx._am_args(0.5, mouts[s]))
                     eps[0] = r.eps
-                    return idx.automerge(r.ids, r.scores, out=mouts[s])
-                scores, ids = sharded.search(q, k, margins=margins[i], slot=s)
+                    return mouts[s]
+                sharded.search(q, k, margins=margins[i], slot=s, merged_out=mouts[s])
                 eps[0] = sharded.last.eps
-                return idx.automerge(ids, scores, out=mouts[s])
+                return mouts[s]
 
         cur = torch.cuda.current_stream()
+        for st in streams:
+            st.wait_stream(cur)
         for i in range(warm):
             one(i)
         for st in streams:
             cur.wait_stream(st)
-        barrier()
+        ctx.barrier()
         idx.scan_events = [] if depth == 1 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(physical_index(local_rank)) if sample_clocks else None
+        sampler = ClockSampler(physical_index(ctx.local_rank)) if sample_clocks else None
         if sampler:
             sampler.__enter__()
+        if sharded is not None:
+            sharded.barrier(batch, k)  # device-side rendezvous: rank skew stays outside the timed region
         e0.record()
         for st in streams:
             st.wait_stream(cur)
@@ -271,170 +339,481 @@ def run_b200(args):
         for st in streams:
             cur.wait_stream(st)
         e1.record()
-        barrier()
+        ctx.barrier()
         if sampler:
             sampler.__exit__()
-        ms = max_over_ranks(e0.elapsed_time(e1))
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1))
         ev = idx.scan_events
         idx.scan_events = None
         scan_ms, n_scan_launches = None, None
         if ev:
-            scan_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])))
+            scan_ms = ctx.max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in ev])))
             n_scan_launches = len(ev) // steps
+        from tensor_truth_b200 import _lib
+
+        _lib.check_status(idx._dev_index)
         mt = margins[warm:]
         bad = int((~(mt > eps[0])).sum().item())
         return {"ms": ms, "scan_ms": scan_ms, "scan_calls_per_step": n_scan_launches, "bad": bad, "last": last,
-                "clocks": sampler.summary() if sampler else None, "min_margin": float(mt.min().item()), "eps": eps[0]}
+                "clocks": sampler.summary() if sampler else None, "min_margin": float(mt.min().item()), "eps": eps[0],
+                "graph": use_graph}
 
-    # ---- headline: batch-1.  Serial loop first (per-kernel events -> roofline), then the pipelined loop (-> value).
-    ser1 = timed(1, args.steps, args.warmup, False, depth=1)
-    pip1 = timed(1, args.steps, args.warmup, True, depth=2)
-    ms1, scan1_ms, nl1, bad1, clocks = pip1["ms"], ser1["scan_ms"], ser1["scan_calls_per_step"], ser1["bad"] + pip1["bad"], pip1["clocks"]
-    value = args.steps * 1 / (ms1 / 1e3)
-    local_bytes = float(hi - lo) * DIM * 2
-    achieved = local_bytes / (scan1_ms / 1e3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
-            tj = json.load(f)
-        if tj.get("rows") == hi - lo and tj.get("batch") == 1:
-            traffic = tj.get("dram_bytes_per_launch")
-    except Exception:
-        pass
+    def hbm_section(self, steps, warm, peak, peak_src, batch=1, sample_clocks=False, label=""):
+        """Serial loop (roofline of the stage-1 kernel) + pipelined loop (throughput) at one batch size."""
+        ser = self.timed(batch, steps, warm, False, depth=1)
+        pip = self.timed(batch, steps, warm, sample_clocks, depth=2)
+        local_bytes = float(self.rows_local) * DIM * 2
+        achieved = local_bytes / (ser["scan_ms"] / 1e3) / 1e9
+        return {
+            "value": steps * batch / (pip["ms"] / 1e3), "unit": UNIT, "ms_per_step": pip["ms"] / steps, "steps": steps,
+            "warmup": warm, "batch": batch, "k": self.k, "rows_total": self.n_rows, "rows_per_gpu": self.rows_local,
+            "serial": {"value": steps * batch / (ser["ms"] / 1e3), "ms_per_step": ser["ms"] / steps},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "scan_tc_kernel", "bytes_per_launch": local_bytes,
+                         "kernel_ms": ser["scan_ms"], "peak_source": peak_src,
+                         "step_share": ser["scan_ms"] * ser["scan_calls_per_step"] / (ser["ms"] / steps),
+                         "measured_in": "serial loop, CUDA events around each stage-1 launch"},
+            "hbm_frac_of_step": local_bytes / (pip["ms"] / steps / 1e3) / 1e9 / peak,
+            "certificate_failures": ser["bad"] + pip["bad"], "min_margin": pip["min_margin"], "eps": pip["eps"],
+            "pipelined_with_cuda_graphs": pip["graph"],
+        }, ser, pip
 
-    # ---- batch-64 (same corpus, one pass of 64 hi-only queries; tensor work rises, HBM bytes per pass do not)
-    skip = set(x for x in args.skip.split(",") if x)
-    batch64 = None
-    if "batch64" not in skip:
-        steps64 = max(3, min(args.steps, 40))
-        ser64 = timed(64, steps64, 3, False, depth=1)
-        pip64 = timed(64, steps64, 3, False, depth=2)
-        batch64 = {"value": steps64 * 64 / (pip64["ms"] / 1e3), "unit": UNIT, "ms_per_step": pip64["ms"] / steps64,
-                   "steps": steps64, "serial_value": steps64 * 64 / (ser64["ms"] / 1e3), "scan_ms_per_step": ser64["scan_ms"],
-                   "hbm_frac": float(hi - lo) * DIM * 2 / (ser64["scan_ms"] / 1e3) / 1e9 / peak,
-                   "certificate_failures": ser64["bad"] + pip64["bad"], "min_margin": pip64["min_margin"],
-                   "eps": pip64["eps"], "mode": "hi-only bf16 queries, 64 per corpus pass",
-                   "kernel": "scan_gemm_kernel<64,2>" if idx._use_gemm(64) else "scan_tc2_kernel<64,2>"}
+    def wide_section(self, bw, kw, steps):
+        """BASELINE configs[3]'s shape: `bw` concurrent queries, top-`kw` + auto-merge, through the GEMM-shaped stage 1."""
+        ctx, idx = self.ctx, self.idx
+        qw = make_queries(self.sc, self.corpus_bf16, self.lo, self.hi, bw, ctx.world, lookup=self.query_lookup).to(ctx.device)
+        tpeak, tpeak_src = measured_tensor_peak()
+        serw = self.timed(bw, steps, 1, False, depth=1, k=kw, pool=qw)
+        flops = 2.0 * bw * float(self.rows_local) * DIM
+        tfl = flops / (serw["scan_ms"] / 1e3) / 1e12
+        # spot check: the first 4 queries against the exact fp64 scan of the local shard
+        rw = idx.search(qw, kw, out=dict(idx._buffers(bw, kw, slot=0)))
+        exw = idx.search_exact(qw[:4], kw)
+        wide_ok = bool(torch.equal(rw.ids[:4], exw.ids) and torch.equal(rw.scores[:4], exw.scores))
+        out = {"value": steps * bw / (serw["ms"] / 1e3), "unit": UNIT, "batch": bw, "k": kw,
+               "ms_per_step": serw["ms"] / steps, "steps": steps, "rows_total": self.n_rows, "rows_per_gpu": self.rows_local,
+               "stage1_ms_per_step": serw["scan_ms"], "gemm_path": bool(idx._use_gemm(bw)),
+               "roofline": {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
+                            "traffic": None, "kernel": "scan_gemm_kernel (+ gemm_cut_kernel between phases)",
+                            "flops_per_step": flops, "peak_source": tpeak_src,
+                            "measured_in": "CUDA events around the whole stage 1 of each step (all phases and cuts)"},
+               "certificate_failures": serw["bad"], "min_margin": serw["min_margin"], "eps": serw["eps"],
+               "parity_vs_gpu_exact_scan_local_shard": wide_ok,
+               "mode": "hi-only bf16 queries, 256 x 256 tcgen05 pair tiles, data-driven thresholds in phases"}
+        del qw, rw, exw
+        idx._ws = {kk: v for kk, v in idx._ws.items() if not (isinstance(kk, tuple) and kk and kk[0] == bw)}
+        if self.sharded is not None:
+            self.sharded._peers.pop((bw, kw), None)
+            self.sharded._out.clear()
+        torch.cuda.empty_cache()
+        return out
 
-    # ---- wide batch (BASELINE configs[3] shape: 16k concurrent queries, top-100): the tensor-bound regime, served by
-    #      the GEMM-shaped stage 1 (scan_gemm.cu).  Roofline: dense bf16 tensor throughput.
-    wide = None
-    if args.wide_batch > 0 and "wide" not in skip:
-        try:
-            bw, kw = args.wide_batch, args.wide_k
-            qw = make_queries(sc, corpus, lo, hi, bw, world).to(device)
-            tpeak, tpeak_src = measured_tensor_peak()
-            serw = timed(bw, args.wide_steps, 1, False, depth=1, k=kw, pool=qw)
-            flops = 2.0 * bw * float(hi - lo) * DIM
-            tfl = flops / (serw["scan_ms"] / 1e3) / 1e12
-            # spot check: the first 4 queries against the exact fp64 scan of the local shard
-            rw = idx.search(qw, kw, out=dict(idx._buffers(bw, kw, slot=0)))
-            exw = idx.search_exact(qw[:4], kw)
-            wide_ok = bool(torch.equal(rw.ids[:4], exw.ids) and torch.equal(rw.scores[:4], exw.scores))
-            wide = {"value": args.wide_steps * bw / (serw["ms"] / 1e3), "unit": UNIT, "batch": bw, "k": kw,
-                    "ms_per_step": serw["ms"] / args.wide_steps, "steps": args.wide_steps,
-                    "stage1_ms_per_step": serw["scan_ms"], "gemm_path": bool(idx._use_gemm(bw)),
-                    "roofline": {"bound": "tensor", "achieved": tfl, "peak": tpeak, "unit": "TFLOP/s", "frac": tfl / tpeak,
-                                 "traffic": None, "kernel": "scan_gemm_kernel (+ gemm_cut_kernel between phases)",
-                                 "flops_per_step": flops, "peak_source": tpeak_src,
-                                 "measured_in": "CUDA events around the whole stage 1 of each step (all phases and cuts)"},
-                    "certificate_failures": serw["bad"], "min_margin": serw["min_margin"], "eps": serw["eps"],
-                    "parity_vs_gpu_exact_scan_local_shard": wide_ok,
-                    "mode": "hi-only bf16 queries, 256 x 256 tcgen05 pair tiles, data-driven thresholds in phases"}
-            del qw, rw, exw
-            idx._ws = {kk: v for kk, v in idx._ws.items() if not (isinstance(kk, tuple) and kk and kk[0] == bw)}
-            torch.cuda.empty_cache()
-        except Exception as exc:  # never lose the headline line to the secondary section
-            wide = {"error": f"{type(exc).__name__}: {exc}"}
+    def retriever(self):
+        from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200VectorIndexRetriever
 
-    # ---- parity spot check inside the bench: the timed path vs the on-GPU exact fp64 scan of the same shard(s)
-    qs = queries[:4]
-    if sharded is None:
-        r = idx.search(qs, TOP_K)
-        got_ids, got_sc = r.ids.clone(), r.scores.clone()
-        ex = idx.search_exact(qs, TOP_K)
-        parity_ok = bool(torch.equal(got_ids, ex.ids) and torch.equal(got_sc, ex.scores))
-    else:
-        scores, ids = sharded.search(qs, TOP_K)
-        got_ids, got_sc = ids.clone(), scores.clone()
-        ex = idx.search_exact(qs, TOP_K)
-        sharded.plumbing.local_search = lambda q, k, ko, io, slot=0: (ko.copy_(ex.keys), io.copy_(ex.ids))
-        s2, i2 = sharded.plumbing.search(qs, TOP_K)
-        parity_ok = bool(torch.equal(got_ids, i2) and torch.equal(got_sc, s2))
-        sharded.plumbing.local_search = sharded._local_search
-    torch.cuda.synchronize()
-    last = pip1["last"]
+        base_r = B200VectorIndexRetriever(self.idx if self.sharded is None else self.sharded, similarity_top_k=self.k)
+        return B200AutoMergingRetriever(base_r, None)  # over a ShardedIndex every rank makes the same call (SPMD)
 
-    # ---- end to end through the public retriever API: host query in, NodeWithScore list out
-    e2e_steps = max(5, min(args.steps, 100))
-    q_host = queries.cpu()
-    q_lists = [row.tolist() for row in q_host]  # host input as an embed model hands it over: a Python list of floats
-    base_r = B200VectorIndexRetriever(idx if sharded is None else sharded, similarity_top_k=TOP_K)
-    am = B200AutoMergingRetriever(base_r, None)  # over a ShardedIndex every rank makes the same call (SPMD)
-    call = lambda i: am.retrieve(QueryBundle(query_str=f"q{i}", embedding=q_lists[i % QUERY_POOL]))  # noqa: E731
-    e2e_warm = 8  # past DeviceIndex's GRAPH_AFTER: the one-off CUDA-graph capture of the pipeline belongs to the warm-up
-    for i in range(e2e_warm):
-        out = call(i)
-    barrier()
+    def e2e_section(self, steps, q_host=None, warm=8):
+        """End to end through the public retriever API: host query embedding in, List[NodeWithScore] out; H2D of the
+        query and D2H of the result record inside the timed region (wall clock, max over ranks)."""
+        from tensor_truth_b200.schema import QueryBundle
+
+        ctx = self.ctx
+        q_host = self.queries.cpu() if q_host is None else q_host
+        q_lists = [row.tolist() for row in q_host]  # host input as an embed model hands it over: a Python list of floats
+        am = self.retriever()
+        n = len(q_lists)
+        call = lambda i: am.retrieve(QueryBundle(query_str=f"q{i}", embedding=q_lists[i % n]))  # noqa: E731
+        for i in range(warm):  # past GRAPH_AFTER: the one-off CUDA-graph capture of the pipeline belongs to the warm-up
+            out = call(i)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            out = call(warm + i)
+        ctx.barrier()
+        e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+        idx = self.idx
+        d2h = idx._record(1, self.k, True, extra_f32=ctx.world if (self.sharded is not None and self.sharded.transport == "peer") else 0)["bytes"]
+        return {"value": steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": DIM * 4, "d2h_bytes_per_step": d2h,
+                "steps": steps, "warmup": warm,
+                "api": "B200AutoMergingRetriever.retrieve(QueryBundle)" + ("" if self.sharded is None else " over ShardedIndex, every rank"),
+                "retries": idx.retries, "deep_rescans": idx.deep_rescans, "fallbacks": idx.fallbacks,
+                "second_rounds": getattr(self.sharded, "second_rounds", 0) if self.sharded is not None else 0,
+                "nodes_returned_last": len(out)}
+
+
+class Ctx:
+    def __init__(self):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device(f"cuda:{self.local_rank}")
+        if self.world > 1:
+            # NCCL writes its version banner (any NCCL_DEBUG level >= VERSION, which this image sets) and its logs to
+            # stdout; rank 0 must print ONE line there
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+                os.environ["NCCL_DEBUG"] = "NONE"
+            dist.init_process_group("nccl", device_id=self.device)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def guarded(name, fn, log):
+    """Secondary sections never cost the headline line: an exception becomes {"error": ...}."""
     t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        out = call(e2e_warm + i)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    n_out = len(out)
-    e2e = {"value": e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": DIM * 4,
-           "d2h_bytes_per_step": idx._record(1, TOP_K, True)["bytes"], "steps": e2e_steps, "warmup": e2e_warm,
-           "api": "B200AutoMergingRetriever.retrieve(QueryBundle)" + ("" if sharded is None else " over ShardedIndex, every rank"),
-           "fallbacks": idx.fallbacks, "nodes_returned_last": n_out}
+    try:
+        out = fn()
+    except Exception as exc:
+        import traceback
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same corpus bytes
-    cpu = None
-    if world == 1 and not args.no_cpu and "cpu" not in skip:
-        sample = min(args.cpu_sample_rows, hi - lo)
-        bits = corpus[:sample].view(torch.int16).cpu().numpy().view(np.uint16)
-        inv_h = inv[:sample].cpu().numpy()
+        traceback.print_exc(file=sys.stderr)
+        out = {"error": f"{type(exc).__name__}: {exc}"}
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+    if isinstance(out, dict):
+        out["section_seconds"] = round(time.perf_counter() - t0, 2)
+    print(f"[bench] section {name}: {time.perf_counter() - t0:.1f} s", file=log, flush=True)
+    return out
+
+
+def oracle_parity_c1(ctx, kprime, variant):
+    """BASELINE configs[0] (C1: 100k rows, 64 queries, top-10 + auto-merge, 3 levels) through the SAME path the timed
+    loops use -- row-sharded over all ranks when N > 1 -- checked on rank 0 against the CPU oracle (strict fp64 C
+    restatement + oracle/automerge.py) on the whole corpus: ids and scores bit-equal."""
+    from tensor_truth_b200.index import MergeResult
+
+    n, nq, k = 100_000, 64, 10
+    w = Bench(ctx, n, 3, k, kprime, variant, n_pool=nq)
+    dev = ctx.device
+    got = []
+    for a in range(0, nq, 8):
+        q = w.queries[a:a + 8]
+        mo = MergeResult(torch.empty((8, 2 * k), dtype=torch.int64, device=dev), torch.empty((8, 2 * k), dtype=torch.float64, device=dev),
+                         torch.empty((8,), dtype=torch.int32, device=dev))
+        if w.sharded is not None:
+            scores, ids = w.sharded.search(q, k, merged_out=mo)
+        else:
+            r = w.idx.search(q, k, am=w.idx._am_args(0.5, mo))
+            scores, ids = r.scores, r.ids
+        torch.cuda.synchronize()
+        got.append((ids.cpu().numpy().copy(), scores.cpu().numpy().copy(), mo.ids.cpu().numpy().copy(),
+                    mo.scores.cpu().numpy().copy(), mo.lens.cpu().numpy().copy()))
+    # the whole corpus on rank 0's host: every rank generates its shard, rank 0 gathers the bits
+    bits_local = w.corpus_bf16.view(torch.int16)
+    if ctx.world > 1:
+        parts = [torch.empty((shard_rows(n, ctx.world, r), DIM), dtype=torch.int16, device=dev) for r in range(ctx.world)]
+        for r in range(ctx.world):  # broadcast each shard in turn (shards may differ in size)
+            if r == ctx.rank:
+                parts[r].copy_(bits_local)
+            ctx.dist.broadcast(parts[r], src=r)
+        bits_all = torch.cat(parts, dim=0)
+    else:
+        bits_all = bits_local
+    ok, checked = True, 0
+    if ctx.rank == 0:
+        import oracle
         from oracle import cport
 
         cport.build()
-        cport.use_all_host_threads()
-        sec, done = cpu_arm(bits, inv_h, sc.tree, q_host.numpy(), TOP_K, 40, 2)
-        cpu = {"value": (1.0 / sec) * (sample / n_rows), "unit": UNIT, "cores": cport.fast_threads(), "kind": "port",
-               "sample": f"{done} batch-1 queries over the first {sample} of {n_rows} rows ({sec * 1e3:.1f} ms each), "
-                         f"q/s scaled by {sample}/{n_rows} (the scan is linear in rows); oracle/c/oracle_fast.c "
-                         f"fp32 AVX2 + OpenMP, auto-merge in oracle/automerge.py",
-               "host_cpus": os.cpu_count()}
+        bits = bits_all.cpu().numpy().view(np.uint16)
+        qh = w.queries.cpu().numpy()
+        ids_o, sc_o, _ = cport.scan_topk(bits, qh, k)
+        tree = w.sc.tree
+        for bi, a in enumerate(range(0, nq, 8)):
+            ids, scores, mids, msc, mlens = got[bi]
+            ok = ok and bool((ids == ids_o[a:a + 8]).all() and (scores == sc_o[a:a + 8]).all())
+            for j in range(8):
+                exp = oracle.auto_merge([(int(o), float(s)) for o, s in zip(ids_o[a + j], sc_o[a + j]) if o >= 0],
+                                        tree.parent_of, tree.child_count, tree.prev_id, tree.next_id)
+                gl = [(int(o), float(s)) for o, s in zip(mids[j, :mlens[j]], msc[j, :mlens[j]])]
+                ok = ok and gl == exp
+                checked += 1
+    w.close()
+    return {"ok": bool(ok), "queries_checked": checked, "rows": n, "k": k,
+            "what": "C1 through the timed path (sharded over all ranks when N > 1) vs the CPU oracle on rank 0: ids, fp32 scores, merged ids, fp64 merged scores bit-equal"}
+
+
+def shard_rows(n, world, r):
+    from tensor_truth_b200.sharded import shard_bounds
+
+    lo, hi = shard_bounds(n, world, r)
+    return hi - lo
+
+
+def hard_section(w, n_dup_per_cta, steps):
+    """Queries aimed at near-duplicate rows: `n_dup_per_cta` x 148 rows of the shard are overwritten with copies of one
+    base vector perturbed by ~1e-3 (relative), spread over the whole shard so that every CTA's share holds about that
+    many; the query is the base vector.  More near-ties of the k-th score than a CTA's shortlist is deep defeats the
+    certificate, and the repair ladder has to answer: hi+lo re-scan with K' = 128 shortlists, then the exact fp64 scan.
+    Timed through retrieve_host (the path that enforces the certificate), wall clock."""
+    ctx, idx = w.ctx, w.idx
+    dev = ctx.device
+    g = torch.Generator(device="cpu")
+    g.manual_seed(SEED + 4242)
+    base = torch.randn(DIM, generator=g)
+    base = base / base.norm()
+    n_dup_global = n_dup_per_cta * 148 * ctx.world
+    stride = max(1, w.n_rows // n_dup_global)
+    rows = torch.arange(0, n_dup_global, dtype=torch.int64) * stride
+    rows = rows[(rows >= w.lo) & (rows < w.hi)] - w.lo
+    gd = torch.Generator(device=dev)
+    gd.manual_seed(SEED + 99 + ctx.rank)
+    saved = idx.corpus[rows.to(dev)].clone()
+    saved_inv = idx.inv_norm[rows.to(dev)].clone()
+    dup = (base.to(dev)[None, :] * (1.0 + 1e-3 * torch.randn((rows.numel(), DIM), generator=gd, device=dev))).to(torch.bfloat16)
+    idx.corpus[rows.to(dev)] = dup
+    idx.inv_norm[rows.to(dev)] = dup.float().pow(2).sum(dim=1).clamp_min(1e-30).rsqrt()
+    before = (idx.retries, idx.deep_rescans, idx.fallbacks)
+    target = w.sharded if w.sharded is not None else idx
+    qh = (base[None, :] * (1.0 + 1e-3 * torch.randn((8, DIM), generator=g))).float()
+    qh = qh / qh.norm(dim=1, keepdim=True)
+    ok = True
+    for i in range(4):  # past GRAPH_AFTER: the one-off graph capture of this call shape stays outside the timed region
+        target.retrieve_host(qh[i:i + 1], w.k, merge=False)
+    ctx.barrier()
+    t0 = time.perf_counter()
+    for i in range(steps):
+        ids, scores, lens = target.retrieve_host(qh[i % 8:i % 8 + 1], w.k, merge=False)
+    ctx.barrier()
+    sec = ctx.max_over_ranks(time.perf_counter() - t0)
+    # the answer must still be the exact one: compare the last query with the exact fp64 scan of every shard
+    ex = idx.search_exact(qh[(steps - 1) % 8:(steps - 1) % 8 + 1].to(dev), w.k)
+    if w.sharded is None:
+        ok = bool((ex.ids.cpu().numpy() == ids).all())
+    out = {"value": steps / sec, "unit": UNIT, "steps": steps, "near_duplicates_per_cta": n_dup_per_cta,
+           "near_duplicates_total": int(n_dup_global), "retries": idx.retries - before[0],
+           "deep_rescans_kprime128": idx.deep_rescans - before[1], "exact_fp64_fallbacks": idx.fallbacks - before[2],
+           "second_rounds": getattr(w.sharded, "second_rounds", 0) if w.sharded is not None else 0,
+           "matches_exact_scan": ok if w.sharded is None else None}
+    idx.corpus[rows.to(dev)] = saved
+    idx.inv_norm[rows.to(dev)] = saved_inv
+    return out
+
+
+def run_b200(args):
+    from tensor_truth_b200 import _lib
+
+    ctx = Ctx()
+    world, rank = ctx.world, ctx.rank
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
+    _lib.lib()  # fail loudly if the CUDA library is missing
+    log = sys.stderr
+    variant = {"auto": _lib.SCAN_AUTO, "simt": _lib.SCAN_SIMT, "tcgen05": _lib.SCAN_TCGEN05}[args.variant]
+    peak, peak_src = measured_peaks()
+    skip = set(x for x in args.skip.split(",") if x)
+    t_start = time.perf_counter()
+
+    # ================= headline: BASELINE configs[1] (C2), batch-1, the same rows at every N (strong scaling)
+    w = Bench(ctx, args.rows, LEVELS, TOP_K, args.kprime, variant)
+    print(f"[bench] corpus {args.rows} rows built in {time.perf_counter() - t_start:.1f} s", file=log, flush=True)
+    head, ser1, pip1 = w.hbm_section(args.steps, args.warmup, peak, peak_src, batch=1, sample_clocks=True)
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "scan_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("rows") == w.rows_local and tj.get("batch") == 1:
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "ncu --set full capture: " + str(tj.get("source"))
+    except Exception:
+        pass
+    head["roofline"]["traffic"] = traffic
+    head["roofline"]["traffic_source"] = traffic_src or "no ncu capture for this shard size (profiles/scan_traffic.json is for the 1-GPU shard)"
+    nl1 = ser1["scan_calls_per_step"]
+
+    # ---- batch-64 (same corpus, one pass of 64 hi-only queries; tensor work rises, HBM bytes per pass do not)
+    batch64 = None
+    if "batch64" not in skip:
+        def f64():
+            steps64 = max(3, min(args.steps, 40))
+            ser64 = w.timed(64, steps64, 3, False, depth=1)
+            pip64 = w.timed(64, steps64, 3, False, depth=2)
+            return {"value": steps64 * 64 / (pip64["ms"] / 1e3), "unit": UNIT, "ms_per_step": pip64["ms"] / steps64,
+                    "steps": steps64, "serial_value": steps64 * 64 / (ser64["ms"] / 1e3), "scan_ms_per_step": ser64["scan_ms"],
+                    "hbm_frac": float(w.rows_local) * DIM * 2 / (ser64["scan_ms"] / 1e3) / 1e9 / peak,
+                    "certificate_failures": ser64["bad"] + pip64["bad"], "min_margin": pip64["min_margin"],
+                    "eps": pip64["eps"], "mode": "hi-only bf16 queries, 64 per corpus pass",
+                    "pipelined_with_cuda_graphs": pip64["graph"],
+                    "kernel": "scan_gemm_kernel<64,2>" if w.idx._use_gemm(64) else "scan_tc2_kernel<64,2>"}
+        batch64 = guarded("batch64", f64, log)
+
+    # ---- wide batch on the headline corpus (BASELINE configs[3]'s shape: 16k concurrent queries, top-100)
+    wide = None
+    if args.wide_batch > 0 and "wide" not in skip:
+        wide = guarded("wide", lambda: w.wide_section(args.wide_batch, args.wide_k, args.wide_steps), log)
+
+    # ---- parity spot check inside the bench: the timed path vs the on-GPU exact fp64 scan of the same shard(s)
+    qs = w.queries[:4]
+    if w.sharded is None:
+        r = w.idx.search(qs, TOP_K)
+        got_ids, got_sc = r.ids.clone(), r.scores.clone()
+        ex = w.idx.search_exact(qs, TOP_K)
+        parity_ok = bool(torch.equal(got_ids, ex.ids) and torch.equal(got_sc, ex.scores))
+    else:
+        scores, ids = w.sharded.search(qs, TOP_K)
+        got_ids, got_sc = ids.clone(), scores.clone()
+        ex = w.idx.search_exact(qs, TOP_K)
+        w.sharded.plumbing.local_search = lambda q, k, ko, io, slot=0: (ko.copy_(ex.keys), io.copy_(ex.ids))
+        s2, i2 = w.sharded.plumbing.search(qs, TOP_K)
+        parity_ok = bool(torch.equal(got_ids, i2) and torch.equal(got_sc, s2))
+        w.sharded.plumbing.local_search = w.sharded._local_search
+    torch.cuda.synchronize()
+
+    # ---- end to end through the public retriever API
+    e2e = None
+    if "e2e" not in skip:
+        e2e = guarded("e2e", lambda: w.e2e_section(max(5, min(args.steps, 100))), log)
+
+    # ---- CPU baseline (rank 0, N=1 only): the SAME corpus bytes on the host cores, all rows when host memory allows
+    cpu = None
+    if world == 1 and not args.no_cpu and "cpu" not in skip:
+        def fcpu():
+            from oracle import cport
+
+            cport.build()
+            cport.use_all_host_threads()
+            full = host_can_hold(w.rows_local * DIM * 2) and not args.cpu_sample_rows
+            sample = w.rows_local if full else min(args.cpu_sample_rows or 1_048_576, w.rows_local)
+            bits = to_host_bits(w.corpus_bf16[:sample])
+            inv_h = w.inv[:sample].cpu().numpy()
+            sec, done = cpu_arm(bits, inv_h, w.sc.tree, w.queries.cpu().numpy(), TOP_K, 20, 2, budget_s=20.0)
+            scale = sample / w.n_rows
+            return {"value": (1.0 / sec) * scale, "unit": UNIT, "cores": cport.fast_threads(), "kind": "port",
+                    "sample": (f"{done} batch-1 queries over " + (f"ALL {sample} rows" if full else f"the first {sample} of {w.n_rows} rows, q/s scaled by {scale:.4f}")
+                               + f" ({sec * 1e3:.1f} ms each); oracle/c/oracle_fast.c fp32 AVX2 + OpenMP, auto-merge in oracle/automerge.py"),
+                    "full_corpus": bool(full), "host_cpus": os.cpu_count()}
+        cpu = guarded("cpu_baseline", fcpu, log)
+
+    # ---- hard queries: near-duplicate rows defeat the certificate, the repair ladder answers (mutates rows, restores them)
+    hard = None
+    if "hard" not in skip:
+        def fhard():
+            return {"deep_rung": hard_section(w, 64, 10), "exact_fallback": hard_section(w, 200, 6),
+                    "what": "queries aimed at 64 / 200 near-duplicate rows per CTA share (K' = 32 lists): K' = 128 re-scan, then exact fp64 scan"}
+        hard = guarded("hard", fhard, log)
+    w.close()
+    del w
+
+    # ================= fp32 store at the headline size (what a real bge-m3 index holds): bf16 shadow scanned, fp32 master re-scored
+    fp32_store = None
+    if "fp32" not in skip:
+        def ffp32():
+            wf = Bench(ctx, args.rows, LEVELS, TOP_K, args.kprime, variant, master_f32=True)
+            sec, _s, _p = wf.hbm_section(max(5, min(args.steps, 40)), 3, peak, peak_src, batch=1)
+            e = wf.e2e_section(max(5, min(args.steps, 40)))
+            sec["e2e"] = e
+            sec["store"] = "fp32 master [rows, 1024] (re-scored in fp64) + bf16 shadow (scanned); eps = 4.2e-3"
+            sec["retries"], sec["deep_rescans"], sec["fallbacks"] = wf.idx.retries, wf.idx.deep_rescans, wf.idx.fallbacks
+            wf.close()
+            return sec
+        fp32_store = guarded("fp32_store", ffp32, log)
+
+    # ================= BASELINE configs[2] (C3): 12.5M rows per GPU (100M over 8), batch-1 -- weak scaling
+    c3 = c4 = None
+    if "c3" not in skip or "c4" not in skip:
+        def fc3():
+            rows3 = args.c3_rows_per_gpu * world
+            w3 = Bench(ctx, rows3, 3, 10, 32, variant)
+            out = {}
+            if "c3" not in skip:
+                sec, _s, _p = w3.hbm_section(max(5, min(args.steps, 40)), 3, peak, peak_src, batch=1)
+                sec["scaling"] = "weak"
+                sec["config"] = f"C3: {rows3} x {DIM} rows over {world} GPU(s) ({args.c3_rows_per_gpu} per GPU), batch-1, top-10 + auto-merge"
+                sec["aggregate_hbm_frac"] = sec["hbm_frac_of_step"]
+                sec["e2e"] = w3.e2e_section(max(5, min(args.steps, 40)))
+                out["c3"] = sec
+            if "c4" not in skip:
+                # BASELINE configs[3] (C4): 50M rows over 8 GPUs = 6.25M per GPU, 16 384 queries, top-100.  The first
+                # c4_rows_per_gpu rows of each rank's C3 shard stand for it (same generator, same bytes per GPU).
+                n4 = min(args.c4_rows_per_gpu, w3.rows_local)
+                w3.idx._ws.clear()
+                w4 = Bench.head_of(w3, n4, args.wide_k, variant)
+                sec4 = w4.wide_section(args.wide_batch, args.wide_k, args.wide_steps)
+                sec4["scaling"] = "weak"
+                sec4["config"] = (f"C4: {n4 * world} x {DIM} rows over {world} GPU(s) ({n4} per GPU: the head of each rank's C3 shard), "
+                                  f"{args.wide_batch} queries per step, top-{args.wide_k} + auto-merge")
+                out["c4"] = sec4
+            w3.close()
+            return out
+        r34 = guarded("c3+c4", fc3, log)
+        c3, c4 = r34.get("c3"), r34.get("c4")
+        if "error" in r34:
+            c3 = c3 or {"error": r34["error"]}
+
+    # ================= BASELINE configs[4] (C5): 20M leaves, 4 levels, top-200, the same rows at every N
+    c5 = None
+    if "c5" not in skip:
+        def fc5():
+            w5 = Bench(ctx, args.c5_rows, 4, 200, 128, variant)
+            sec, _s, _p = w5.hbm_section(max(5, min(args.steps, 20)), 3, peak, peak_src, batch=1)
+            sec["scaling"] = "strong"
+            sec["config"] = f"C5: {args.c5_rows} leaves, 4-level tree, top-200 + auto-merge, batch-1, over {world} GPU(s)"
+            sec["e2e"] = w5.e2e_section(max(5, min(args.steps, 20)))
+            # merges must actually fire on this workload: report the last merged list's length against k
+            sec["merged_len_last"] = int(_p["last"].lens[0].item()) if _p.get("last") is not None else None
+            w5.close()
+            return sec
+        c5 = guarded("c5", fc5, log)
+
+    # ================= oracle-anchored parity of the timed path (C1, sharded over all ranks when N > 1)
+    parity_cpu = None
+    if "parity" not in skip:
+        parity_cpu = guarded("parity_vs_cpu_oracle", lambda: oracle_parity_c1(ctx, 32, variant), log)
 
     if rank == 0:
+        steps = args.steps
+        launches_per_step = 3 + nl1 - 1 + (1 if world > 1 else 0)  # prepare, scan(s), re-score+select(+push|+auto-merge), (merge+auto-merge)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms1 / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "serial": {"value": args.steps / (ser1["ms"] / 1e3), "ms_per_step": ser1["ms"] / args.steps,
-                       "note": "same K steps with no overlap between consecutive steps (one stream)"},
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "serial": dict(head["serial"], note="same K steps with no overlap between consecutive steps (one stream, eager launches)"),
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{args.tag}: exact cosine top-{TOP_K} + auto-merge, {n_rows} x {DIM} bf16 leaf embeddings, "
+            "config": {"workload": f"{args.tag}: exact cosine top-{TOP_K} + auto-merge, {args.rows} x {DIM} bf16 leaf embeddings, "
                                    f"{LEVELS}-level tree, batch-1 queries, corpus row-sharded over {world} GPU(s)",
-                       "rows_per_gpu": hi - lo, "batch": 1, "k": TOP_K, "kprime": args.kprime, "variant": args.variant,
+                       "rows_per_gpu": head["rows_per_gpu"], "batch": 1, "k": TOP_K, "kprime": args.kprime, "variant": args.variant,
                        "l2": "no flush: every step streams the whole shard (>= 2.5 GB) through a 126 MB L2",
-                       "pipeline": "2 streams: step i+1's scan overlaps step i's re-score/select/merge/auto-merge",
+                       "pipeline": "2 lanes (streams), one CUDA graph of the whole step per lane: step i+1's scan overlaps step i's "
+                                   "tail (and the drain of scan i overlaps the ramp of scan i+1, so ms_per_step can sit a hair below kernel_ms)",
+                       "timing": "CUDA events on the launching stream, after a device-side rendezvous of all ranks (tt_peer_barrier); max over ranks",
                        "seed": SEED},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "scan_tc_kernel" if args.variant != "simt" else "scan_simt_kernel",
-                         "bytes_per_launch": local_bytes, "kernel_ms": scan1_ms, "peak_source": peak_src,
-                         "step_share": scan1_ms * nl1 / (ser1["ms"] / args.steps),
-                         "measured_in": "serial loop, CUDA events around each stage-1 launch"},
+            "roofline": head["roofline"],
             "cpu_baseline": cpu,
             "e2e": e2e,
-            "gpu_launches": args.steps * (4 + nl1 + (1 if world > 1 else 0)),
-            "clocks": clocks,
+            "gpu_launches": steps * launches_per_step,
+            "kernels_per_step": launches_per_step,
+            "clocks": pip1["clocks"],
             "batch64": batch64,
             "wide": wide,
-            "certificate_failures": bad1, "min_margin": pip1["min_margin"], "eps": pip1["eps"],
-            "exchange": (sharded.transport + (" (fused into the select / merge kernels over peer memory)" if sharded.transport == "peer" else " all-gather")) if sharded is not None else None,
+            "fp32_store": fp32_store,
+            "hard_queries": hard,
+            "c3": c3, "c4": c4, "c5": c5,
+            "certificate_failures": head["certificate_failures"], "min_margin": head["min_margin"], "eps": head["eps"],
+            "exchange": None if world == 1 else ("peer: fused into the select / merge kernels over symmetric memory, device-resident epochs, CUDA-graph replay"
+                                                 if os.environ.get("TT_EXCHANGE", "peer") != "nccl" else "nccl all-gather"),
             "parity_vs_gpu_exact_scan": parity_ok,
+            "parity_vs_cpu_oracle": parity_cpu,
+            "bench_seconds": round(time.perf_counter() - t_start, 1),
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------- the CPU arm
@@ -448,40 +827,48 @@ def run_reference(args):
     cport.build()
     cport.use_all_host_threads()  # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is the all-cores baseline
     n_rows = args.rows
-    sample = min(args.cpu_sample_rows, n_rows)
+    full = host_can_hold(n_rows * DIM * 2) and not args.cpu_sample_rows
+    sample = n_rows if full else min(args.cpu_sample_rows or 1_048_576, n_rows)
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     sc = SynthCorpus(n_rows, DIM, LEVELS, SEED, device=dev)
     corpus, inv = sc.rows(0, sample)
-    tgt = sc.query_targets(QUERY_POOL) % sample  # keep the targets inside the sample
-    q = torch.zeros((QUERY_POOL, DIM))
-    for j in range(QUERY_POOL):
-        g = torch.Generator(device="cpu")
-        g.manual_seed(SEED * 7_368_787 + 11 + j)
-        q[j] = corpus[int(tgt[j])].float().cpu() + (0.3 / DIM ** 0.5) * torch.randn(DIM, generator=g)
-    q = sc.finish_queries(q).numpy()
-    bits = corpus.view(torch.int16).cpu().numpy().view(np.uint16)
+    if full:  # the same 64 queries the GPU arm draws
+        q = sc.finish_queries(sc.queries(QUERY_POOL, lookup=lambda t: corpus[t])).numpy()
+    else:     # keep the targets inside the sample
+        tgt = sc.query_targets(QUERY_POOL) % sample
+        q = torch.zeros((QUERY_POOL, DIM))
+        for j in range(QUERY_POOL):
+            g = torch.Generator(device="cpu")
+            g.manual_seed(SEED * 7_368_787 + 11 + j)
+            q[j] = corpus[int(tgt[j])].float().cpu() + (0.3 / DIM ** 0.5) * torch.randn(DIM, generator=g)
+        q = sc.finish_queries(q).numpy()
+    bits = to_host_bits(corpus) if corpus.is_cuda else corpus.view(torch.int16).numpy().view(np.uint16)
     inv_h = inv.cpu().numpy()
     del corpus
+    if dev == "cuda":
+        torch.cuda.empty_cache()
     # calibrate so that warmup + steps stay within a few minutes
     sec, _ = cpu_arm(bits, inv_h, sc.tree, q, TOP_K, 1, 1)
     budget = 150.0
     if sec * (args.steps + args.warmup) > budget:
         sample = max(65536, int(sample * budget / (sec * (args.steps + args.warmup))) // 1024 * 1024)
         bits, inv_h = bits[:sample], inv_h[:sample]
+        full = False
     sec, done = cpu_arm(bits, inv_h, sc.tree, q, TOP_K, args.steps, args.warmup, budget_s=budget)
-    value = (1.0 / sec) * (sample / n_rows)
+    scale = sample / n_rows
+    value = (1.0 / sec) * scale
     cores = cport.fast_threads()
-    desc = (f"{done} batch-1 queries over the first {sample} of {n_rows} rows ({sec * 1e3:.1f} ms each), q/s scaled by "
-            f"{sample}/{n_rows} (the scan is linear in rows); oracle/c/oracle_fast.c fp32 AVX2 + OpenMP on {cores} threads, "
+    desc = (f"{done} batch-1 queries over " + (f"ALL {sample} rows" if full else f"the first {sample} of {n_rows} rows, q/s scaled by {scale:.4f} (the scan is linear in rows)")
+            + f" ({sec * 1e3:.1f} ms each); oracle/c/oracle_fast.c fp32 AVX2 + OpenMP on {cores} threads, "
             f"auto-merge in oracle/automerge.py.  The reference's own stack (llama-index + chromadb) is not installable here.")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3 * (n_rows / sample), "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": sec * 1e3 / scale, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C2: exact cosine top-{TOP_K} + auto-merge, {n_rows} x {DIM} bf16 leaf embeddings, "
-                                   f"{LEVELS}-level tree, batch-1 queries (CPU arm on a {sample}-row sample)",
-                       "batch": 1, "k": TOP_K, "seed": SEED},
+                                   f"{LEVELS}-level tree, batch-1 queries" + ("" if full else f" (CPU arm on a {sample}-row sample)"),
+                       "batch": 1, "k": TOP_K, "seed": SEED, "full_corpus": bool(full)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
-                             "host_cpus": os.cpu_count()},
+                             "full_corpus": bool(full), "host_cpus": os.cpu_count()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -497,9 +884,14 @@ def main():
     ap.add_argument("--kprime", type=int, default=0, help="per-CTA shortlist length (0 = by k)")
     ap.add_argument("--k", type=int, default=10, help="similarity_top_k (BASELINE: 10; C5: 200)")
     ap.add_argument("--levels", type=int, default=3, help="levels of the node tree (C5: 4)")
-    ap.add_argument("--skip", default="", help="comma list of secondary sections to skip: batch64,wide,e2e,cpu")
+    ap.add_argument("--skip", default="", help="comma list of secondary sections to skip: batch64,wide,e2e,cpu,hard,fp32,c3,c4,c5,parity")
+    ap.add_argument("--only-headline", action="store_true", help="skip every secondary section")
+    ap.add_argument("--c3-rows-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--c4-rows-per-gpu", type=int, default=6_250_000)
+    ap.add_argument("--c5-rows", type=int, default=20_000_000)
     ap.add_argument("--variant", default="auto", choices=["auto", "simt", "tcgen05"])
-    ap.add_argument("--cpu-sample-rows", type=int, default=1_048_576)
+    ap.add_argument("--cpu-sample-rows", type=int, default=0,
+                    help="CPU arm: 0 = the whole corpus when host memory allows (else 1,048,576 rows); N = the first N rows, q/s scaled")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="label only: 'strong' = --rows is the total (default: the same 10M rows at every N); 'weak' when the "
@@ -511,6 +903,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.only_headline:
+        args.skip = "batch64,wide,e2e,cpu,hard,fp32,c3,c4,c5,parity"
     global TOP_K, LEVELS, METRIC
     TOP_K, LEVELS = args.k, args.levels
     if args.kprime <= 0:  # per-CTA shortlist length: deeper for larger k (clustered hits share a tile, hence a CTA)

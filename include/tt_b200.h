@@ -36,6 +36,27 @@ extern "C" {
 #define TT_ERR_CUDA (-2)        /* a CUDA runtime/driver call failed */
 #define TT_ERR_UNSUPPORTED (-3) /* shape/alignment this build has no kernel for */
 #define TT_ERR_WORKSPACE (-4)   /* workspace too small */
+#define TT_ERR_TIMEOUT (-5)     /* a device-side wait ran out of time (tt_status_read says which) */
+
+/*
+ * Device-side status.  No kernel of this library traps or hangs: a wait that runs out of time -- an mbarrier of a
+ * TMA/MMA ring (a protocol bug or a lost copy), a peer's exchange flag (a rank that died, raised or never made the
+ * matching call) -- records a code and lets the launch finish on whatever it has, so the CUDA context, the other
+ * indexes of the process and the peers' mappings of this GPU stay usable.  The results of such a launch are
+ * garbage: a caller must look at the status before it trusts them (the Python binding does, and raises TTError
+ * with TT_ERR_TIMEOUT on every rank concerned; errors past MultiIndexRetriever are logged and skipped per index
+ * by the reference, rag_engine.py:453-455, and must never take the process down).
+ *
+ *   tt_status_configure(mapped_word_host, timeout_ms)   for the CURRENT device: `mapped_word_host` is an optional
+ *       uint32 in pinned (device-mapped) HOST memory that the kernels OR the code into as well, so that the caller
+ *       can poll it after its usual stream synchronisation without an extra device read; timeout_ms bounds one
+ *       ring wait (exchange waits get four times that).  0 = keep the default (about 4 s).
+ *   tt_status_read(out_host, clear)   synchronous read of the device-resident words (OR of all of them).
+ */
+#define TT_STATUS_RING_TIMEOUT 1u
+#define TT_STATUS_EXCHANGE_TIMEOUT 2u /* bits 8..15: the source rank that was waited for */
+int tt_status_configure(uint32_t* mapped_word_host, int timeout_ms);
+int tt_status_read(uint32_t* out_host, int clear);
 
 #define TT_DTYPE_BF16 0
 #define TT_DTYPE_F32 1
@@ -209,8 +230,20 @@ typedef struct tt_exchange {
     uint64_t ids_off_bytes;
     void* peer_recv[TT_MAX_PEERS];      /* peer p: base of ITS receive region for this slot, as mapped here */
     uint32_t* peer_flags[TT_MAX_PEERS]; /* peer p: ITS flag array for this slot, as mapped here             */
-    uint32_t* ticket;                   /* local device word, zero between calls (one per slot)             */
+    uint32_t* ticket;                   /* local device word, zero between calls (one per lane)             */
     uint64_t margins_off_bytes;         /* 0: margins are not exchanged                                     */
+    /* Device-resident epoch (NULL: `epoch` above is used and peer_recv / peer_flags address the slot directly).
+     * *epoch_dev counts the pushes this LANE (one stream of a pipelined caller) has completed; a pushing launch
+     * opens epoch *epoch_dev + 1 and stores it back when its flags go up, the waiting launch that follows it in
+     * stream order reads it.  The slot of the receive ring is epoch % n_slots: peer_recv[p] + slot *
+     * slot_stride_bytes, peer_flags[p] + slot * flag_slot_stride.  Nothing in the descriptor changes from step to
+     * step, so a captured CUDA graph of the step replays as it is.  All ranks must push in lockstep per lane;
+     * 2 slots per lane suffice (slot e % 2 is rewritten at e + 2, after this rank merged e + 1, which needed every
+     * peer's push of e + 1, which that peer issued after ITS merge of e). */
+    uint32_t* epoch_dev;
+    uint32_t n_slots;                   /* 0 or 1: a single slot                                            */
+    uint64_t slot_stride_bytes;
+    uint64_t flag_slot_stride;          /* in uint32 elements, >= world                                     */
 } tt_exchange_t;
 
 /*
@@ -232,6 +265,9 @@ int tt_rescore_topk_push(const void* corpus, int corpus_dtype, int64_t n_rows, i
                          void* ws, size_t ws_bytes, const tt_exchange_t* xchg, const tt_l2_cert_t* l2_cert,
                          void* stream);
 int tt_exchange_push(const void* record, size_t nbytes, const tt_exchange_t* xchg, void* stream);
+/* Device-side rendezvous of all ranks over the flags of `xchg` (its own descriptor: flags + epoch_dev, no receive
+ * region needed -- peer_recv may repeat peer_flags): returns, in stream order, once every rank has reached it. */
+int tt_peer_barrier(const tt_exchange_t* xchg, void* stream);
 int tt_merge_topk_pulled(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
                          int64_t ids_list_stride, int n_q, int k_in, int k_out, int score_mode,
                          float* out_scores, int64_t* out_ids, const tt_exchange_t* xchg, void* stream);
@@ -252,6 +288,46 @@ int tt_automerge(const int64_t* ids, const float* scores, int n_q, int k,
                  const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
                  double ratio_thresh, int max_rounds,
                  int64_t* out_ids, double* out_scores, int32_t* out_len, int max_out, void* stream);
+
+/*
+ * Fused tails: the same arithmetic in fewer launches on the latency chain of a query.
+ *
+ *   tt_rescore_topk_fused   = tt_rescore_topk_push in ONE launch: the blocks of a query re-score its candidates, the
+ *                             block that finishes last (per-query ticket) selects -- and then either pushes the
+ *                             record to the peers (xchg != NULL) or runs stage 3 on it (am != NULL, xchg == NULL).
+ *                             ws: tt_rescore_fused_workspace_bytes(n_q, n_cand) bytes, ZEROED ONCE by the caller
+ *                             when it allocates them (the tickets; the kernel leaves them zero).
+ *   tt_merge_topk_fused     = tt_merge_topk_pulled + (optionally) the certificate margins every source pushed,
+ *                             copied out of the receive region into out_all_margins float [n_lists, n_q], +
+ *                             (optionally) stage 3 on the merged list in the same block.  out_scores / out_ids
+ *                             are required when am != NULL (stage 3 reads the merged list back from them).
+ */
+typedef struct tt_automerge_args {
+    const int32_t* parent_of;
+    const int32_t* child_count;
+    const int32_t* prev_id;
+    const int32_t* next_id;
+    int64_t n_nodes;
+    double ratio_thresh;
+    int max_rounds;
+    int64_t* out_ids;    /* [n_q, max_out] */
+    double* out_scores;  /* [n_q, max_out] */
+    int32_t* out_len;    /* [n_q] */
+    int max_out;
+} tt_automerge_args_t;
+
+size_t tt_rescore_fused_workspace_bytes(int n_q, int n_cand);
+int tt_rescore_topk_fused(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                          int64_t id_base, const float* q_f32, int n_q,
+                          const int64_t* cand_ids, int n_cand, const float* cand_thresh, int n_lists,
+                          int k, int score_mode,
+                          float* out_keys, float* out_scores, int64_t* out_ids, float* out_margin,
+                          void* ws, size_t ws_bytes, const tt_exchange_t* xchg, const tt_l2_cert_t* l2_cert,
+                          const tt_automerge_args_t* am, void* stream);
+int tt_merge_topk_fused(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
+                        int64_t ids_list_stride, int n_q, int k_in, int k_out, int score_mode,
+                        float* out_scores, int64_t* out_ids, const tt_exchange_t* xchg, float* out_all_margins,
+                        const tt_automerge_args_t* am, void* stream);
 
 /*
  * The stage AFTER the retrieval path: the dense layers of the cross-encoder reranker

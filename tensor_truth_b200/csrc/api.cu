@@ -39,11 +39,29 @@ int launch_layernorm(const void* x, int64_t n_rows, int dim, const float* gamma,
 int launch_rescore(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
                    const float* q, int n_q, const int64_t* cand_ids, int n_cand, int mode, uint64_t* packed,
                    cudaStream_t st);
+struct RescoreSrc;
 int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const int64_t* in_ids, int n_lists,
                   int64_t keys_stride, int64_t ids_stride, int n_q, int k_in, int k, int mode, const float* thresh, int n_thresh, float* out_keys, float* out_scores,
                   int64_t* out_ids, float* out_margin, cudaStream_t st, const tt_exchange_t* xh = nullptr, bool push = false,
-                  bool wait = false, const tt_l2_cert_t* l2 = nullptr, const float* q_f32 = nullptr, int dim = 0);
+                  bool wait = false, const tt_l2_cert_t* l2 = nullptr, const float* q_f32 = nullptr, int dim = 0,
+                  const tt_automerge_args_t* amh = nullptr, float* out_all_margins = nullptr, const RescoreSrc* rs = nullptr);
+int launch_rescore_select(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
+                          const float* q, int n_q, const int64_t* cand_ids, int n_cand, const float* thresh, int n_thresh,
+                          int k, int mode, float* out_keys, float* out_scores, int64_t* out_ids, float* out_margin,
+                          uint64_t* packed, unsigned* tickets, const tt_exchange_t* xh, const tt_l2_cert_t* l2,
+                          const tt_automerge_args_t* amh, cudaStream_t st);
 int launch_exchange_push(const void* rec, size_t nbytes, const tt_exchange_t* h, cudaStream_t st);
+int launch_peer_barrier(const tt_exchange_t* h, cudaStream_t st);
+// per-translation-unit status words (tt_common.cuh)
+#define TT_STATUS_TU(tu)                                       \
+    int tu##_status_configure(unsigned* mapped, long long cycles); \
+    int tu##_status_read(unsigned* out, bool clear);
+TT_STATUS_TU(rescore)
+TT_STATUS_TU(scan_tc)
+TT_STATUS_TU(scan_tc2)
+TT_STATUS_TU(scan_gemm)
+TT_STATUS_TU(linear)
+#undef TT_STATUS_TU
 int launch_automerge(const int64_t* ids, const float* scores, int n_q, int k, const int32_t* parent_of,
                      const int32_t* child_count, const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
                      double ratio_thresh, int max_rounds, int64_t* out_ids, double* out_scores, int32_t* out_len,
@@ -97,9 +115,49 @@ using namespace tt;
 
 extern "C" {
 
-int tt_version(void) { return 100; }
+int tt_version(void) { return 200; }
 
 const char* tt_last_error(void) { return g_err; }
+
+int tt_status_configure(uint32_t* mapped_word_host, int timeout_ms) {
+    TT_CHECK_ARG(timeout_ms >= 0, "tt_status_configure: timeout_ms=%d", timeout_ms);
+    int khz = 0;
+    if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, current_device()) != cudaSuccess || khz <= 0) {
+        cudaGetLastError();
+        khz = 1965000;
+    }
+    const long long cycles = timeout_ms > 0 ? (long long)timeout_ms * khz : 8000000000ll;  // clock64 ticks at the SM clock
+    unsigned* dev_view = nullptr;
+    if (mapped_word_host) {
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, mapped_word_host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("tt_status_configure: the status word must live in pinned (device-mapped) host memory");
+            return TT_ERR_INVALID;
+        }
+        dev_view = reinterpret_cast<unsigned*>(d);
+    }
+    if (rescore_status_configure(dev_view, cycles) || scan_tc_status_configure(dev_view, cycles) ||
+        scan_tc2_status_configure(dev_view, cycles) || scan_gemm_status_configure(dev_view, cycles) ||
+        linear_status_configure(dev_view, cycles)) {
+        set_error("tt_status_configure: %s", cudaGetErrorString(cudaGetLastError()));
+        return TT_ERR_CUDA;
+    }
+    return TT_OK;
+}
+
+int tt_status_read(uint32_t* out_host, int clear) {
+    TT_CHECK_ARG(out_host != nullptr, "tt_status_read: null pointer");
+    unsigned v = 0u;
+    const bool c = clear != 0;
+    if (rescore_status_read(&v, c) || scan_tc_status_read(&v, c) || scan_tc2_status_read(&v, c) ||
+        scan_gemm_status_read(&v, c) || linear_status_read(&v, c)) {
+        set_error("tt_status_read: %s", cudaGetErrorString(cudaGetLastError()));
+        return TT_ERR_CUDA;
+    }
+    *out_host = v;
+    return TT_OK;
+}
 
 int tt_scan_num_lists(int device) { return sm_count(device); }
 
@@ -273,6 +331,46 @@ int tt_exchange_push(const void* record, size_t nbytes, const tt_exchange_t* xch
     return launch_exchange_push(record, nbytes, xchg, TT_STREAM(stream));
 }
 
+int tt_peer_barrier(const tt_exchange_t* xchg, void* stream) {
+    TT_CHECK_ARG(xchg != nullptr, "tt_peer_barrier: null pointer");
+    return launch_peer_barrier(xchg, TT_STREAM(stream));
+}
+
+size_t tt_rescore_fused_workspace_bytes(int n_q, int n_cand) {
+    if (n_q <= 0 || n_cand < 0) return 0;
+    return size_t(n_q) * size_t(n_cand) * sizeof(uint64_t) + size_t(n_q) * sizeof(uint32_t);
+}
+
+int tt_rescore_topk_fused(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                          int64_t id_base, const float* q_f32, int n_q, const int64_t* cand_ids, int n_cand,
+                          const float* cand_thresh, int n_lists, int k, int score_mode, float* out_keys, float* out_scores,
+                          int64_t* out_ids, float* out_margin, void* ws, size_t ws_bytes, const tt_exchange_t* xchg,
+                          const tt_l2_cert_t* l2_cert, const tt_automerge_args_t* am, void* stream) {
+    TT_CHECK_ARG(!l2_cert || (l2_cert->row_norm_min >= 0.f && l2_cert->row_norm_max >= l2_cert->row_norm_min &&
+                              l2_cert->eps >= 0.f),
+                 "tt_rescore_topk_fused: bad L2 certificate bounds");
+    TT_CHECK_ARG(corpus_dtype == TT_DTYPE_BF16 || corpus_dtype == TT_DTYPE_F32, "tt_rescore_topk_fused: dtype %d", corpus_dtype);
+    TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_rescore_topk_fused: score_mode %d",
+                 score_mode);
+    TT_CHECK_ARG(dim > 0 && dim % 8 == 0 && row_stride_elems >= dim && row_stride_elems % 8 == 0,
+                 "tt_rescore_topk_fused: dim=%d stride=%lld", dim, (long long)row_stride_elems);
+    TT_CHECK_ARG(n_q >= 0 && n_q <= 65535 && n_cand >= 0 && k >= 1, "tt_rescore_topk_fused: n_q=%d n_cand=%d k=%d", n_q, n_cand, k);
+    TT_CHECK_ARG(id_base >= 0 && id_base + n_rows <= (int64_t(1) << 32), "tt_rescore_topk_fused: ids must stay below 2^32");
+    TT_CHECK_ARG(!(xchg && am), "tt_rescore_topk_fused: a pushed record is merged before stage 3 (tt_merge_topk_fused)");
+    if (n_q == 0) return TT_OK;
+    TT_CHECK_ARG(q_f32 && (out_ids || xchg) && (n_cand == 0 || cand_ids), "tt_rescore_topk_fused: null pointer");
+    const size_t need = tt_rescore_fused_workspace_bytes(n_q, n_cand);
+    if (ws_bytes < need || !ws) {
+        set_error("tt_rescore_topk_fused: workspace %zu < %zu bytes", ws_bytes, need);
+        return TT_ERR_WORKSPACE;
+    }
+    uint64_t* packed = reinterpret_cast<uint64_t*>(ws);
+    unsigned* tickets = reinterpret_cast<unsigned*>(packed + size_t(n_q) * n_cand);
+    return launch_rescore_select(corpus, corpus_dtype, n_rows, dim, row_stride_elems, id_base, q_f32, n_q, cand_ids, n_cand,
+                                 cand_thresh, cand_thresh ? n_lists : 0, k, score_mode, out_keys, out_scores, out_ids,
+                                 out_margin, packed, tickets, xchg, l2_cert, am, TT_STREAM(stream));
+}
+
 size_t tt_scan_exact_workspace_bytes(int device, int n_q, int k) {
     const int kp = exact_kprime(k);
     const int n_lists = sm_count(device);
@@ -323,7 +421,17 @@ int tt_merge_topk(const float* keys, const int64_t* ids, int n_lists, int64_t ke
 int tt_merge_topk_pulled(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
                          int64_t ids_list_stride, int n_q, int k_in, int k_out, int score_mode, float* out_scores,
                          int64_t* out_ids, const tt_exchange_t* xchg, void* stream) {
+    return tt_merge_topk_fused(keys, ids, n_lists, keys_list_stride, ids_list_stride, n_q, k_in, k_out, score_mode, out_scores,
+                               out_ids, xchg, nullptr, nullptr, stream);
+}
+
+int tt_merge_topk_fused(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
+                        int64_t ids_list_stride, int n_q, int k_in, int k_out, int score_mode, float* out_scores,
+                        int64_t* out_ids, const tt_exchange_t* xchg, float* out_all_margins,
+                        const tt_automerge_args_t* am, void* stream) {
     TT_CHECK_ARG(keys_list_stride >= 0 && ids_list_stride >= 0, "tt_merge_topk: negative list stride");
+    TT_CHECK_ARG(!out_all_margins || (xchg && xchg->margins_off_bytes && n_lists == xchg->world),
+                 "tt_merge_topk_fused: margins are gathered from an exchange that carries them, one list per rank");
     TT_CHECK_ARG(n_lists >= 1 && n_q >= 0 && k_in >= 1 && k_out >= 1, "tt_merge_topk: n_lists=%d n_q=%d k_in=%d k_out=%d",
                  n_lists, n_q, k_in, k_out);
     TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_merge_topk: score_mode %d",
@@ -331,7 +439,8 @@ int tt_merge_topk_pulled(const float* keys, const int64_t* ids, int n_lists, int
     if (n_q == 0) return TT_OK;
     TT_CHECK_ARG(keys && ids && out_ids, "tt_merge_topk: null pointer");
     return launch_select(nullptr, 0, keys, ids, n_lists, keys_list_stride, ids_list_stride, n_q, k_in, k_out, score_mode,
-                         nullptr, 0, nullptr, out_scores, out_ids, nullptr, TT_STREAM(stream), xchg, false, xchg != nullptr);
+                         nullptr, 0, nullptr, out_scores, out_ids, nullptr, TT_STREAM(stream), xchg, false, xchg != nullptr,
+                         nullptr, nullptr, 0, am, out_all_margins);
 }
 
 

@@ -10,6 +10,8 @@
 #include "tc_ptx.cuh"
 
 namespace tt {
+
+TT_DEFINE_STATUS_HOOKS(linear)
 namespace lin {
 
 using namespace tc;

@@ -22,6 +22,8 @@
 #include "tc_ptx.cuh"
 
 namespace tt {
+
+TT_DEFINE_STATUS_HOOKS(scan_gemm)
 namespace tc3 {
 
 using namespace tc;

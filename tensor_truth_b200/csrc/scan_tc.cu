@@ -20,6 +20,8 @@
 
 namespace tt {
 
+TT_DEFINE_STATUS_HOOKS(scan_tc)
+
 namespace tc {
 
 constexpr int MAX_SEGMENTS = 16;
@@ -261,8 +263,38 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
 // Shared-memory budget: the resident query block, then the candidate lists, the rest is the TMA ring.
 // Lists hold K' + spare entries; spare = 128 never needs a retry (a tile pushes at most 128 rows per query);
 // with many queries per pass the spare shrinks so that the ring keeps enough bytes in flight.
+// CO_RESIDENT_RESERVE bytes of the SM's shared memory are left to other kernels when that costs no ring stage worth
+// having: in a two-lane pipeline the tail of step i (re-score/select, merge/auto-merge: <= 18 KB, 512 threads) has to
+// become resident NEXT TO the persistent scan CTAs of step i + 1, or it would wait for the whole scan to drain.
+constexpr size_t CO_RESIDENT_RESERVE = 20 * 1024;
+
+template <int N, int CH, bool HILO>
+static bool plan_within(size_t limit, int dim, int kprime, int* spare_out, int* stages_out, size_t* smem_out, int n_seg);
+
 template <int N, int CH, bool HILO>
 static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* smem_out, int n_seg = 1) {
+    int sp_full = 0, st_full = 0;
+    size_t sm_full = 0;
+    if (!plan_within<N, CH, HILO>(size_t(SMEM_LIMIT), dim, kprime, &sp_full, &st_full, &sm_full, n_seg)) return false;
+    int sp = 0, st_n = 0;
+    size_t sm = 0;
+    // keep the reserve if the ring stays >= 128 KB, or loses nothing at all
+    if (!getenv("TT_SCAN_NO_RESERVE") &&
+        plan_within<N, CH, HILO>(size_t(SMEM_LIMIT) - CO_RESIDENT_RESERVE, dim, kprime, &sp, &st_n, &sm, n_seg) &&
+        (st_n == st_full || size_t(st_n) * CH * CHUNK_BYTES >= 128 * 1024) && sp == sp_full) {
+        *spare_out = sp;
+        *stages_out = st_n;
+        *smem_out = sm;
+        return true;
+    }
+    *spare_out = sp_full;
+    *stages_out = st_full;
+    *smem_out = sm_full;
+    return true;
+}
+
+template <int N, int CH, bool HILO>
+static bool plan_within(size_t limit, int dim, int kprime, int* spare_out, int* stages_out, size_t* smem_out, int n_seg) {
     const int NQ = (HILO ? N / 2 : N) * n_seg;  // shortlists per CTA
     const size_t q_bytes = size_t(dim / CHUNK_COLS) * N * 128;
     const size_t base = 1024 /*align slack*/ + q_bytes + size_t(NQ) * 8 + 160;
@@ -271,8 +303,8 @@ static bool plan(int dim, int kprime, int* spare_out, int* stages_out, size_t* s
     auto try_spare = [&](int sp, size_t want_ring) {
         if (kprime + sp > 256) return false;
         const size_t fixed = base + size_t(NQ) * (kprime + sp) * 8;
-        if (fixed + 2 * per_stage > size_t(SMEM_LIMIT)) return false;
-        const int st_n = int((size_t(SMEM_LIMIT) - fixed) / per_stage);
+        if (fixed + 2 * per_stage > limit) return false;
+        const int st_n = int((limit - fixed) / per_stage);
         if (size_t(st_n) * CH * CHUNK_BYTES < want_ring) return false;
         spare = sp;
         stages = st_n;

@@ -19,6 +19,8 @@
 #include "tc_ptx.cuh"
 
 namespace tt {
+
+TT_DEFINE_STATUS_HOOKS(scan_tc2)
 namespace tc2 {
 
 using namespace tc;

@@ -32,8 +32,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Spin on the phase parity.  A wait that lasts ~seconds can only be a protocol bug: trap instead of
-// hanging the device.
+// Spin on the phase parity.  A wait that lasts ~seconds can only be a protocol bug or a lost TMA: it records
+// TT_STATUS_RING_TIMEOUT and gives up (status_report, tt_common.cuh) -- the kernel then runs to its end on garbage,
+// every later wait of the launch gives up after its first slow-path check, and the host raises TTError.  Neither a
+// hung device nor a trapped context.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done = 0;
     long long t0 = 0;
@@ -47,12 +49,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (done) return;
         if ((spins & 0xfffu) == 0xfffu) {
+            if (status_raised()) return;
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 8000000000ll) {
-                printf("tt_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                       threadIdx.x, bar, parity);
-                __trap();
+            else if (now - t0 > status_timeout_cycles()) {
+                status_report(TT_STATUS_RING_TIMEOUT);
+                return;
             }
         }
     }

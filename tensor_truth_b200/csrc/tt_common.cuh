@@ -73,6 +73,47 @@ __host__ __device__ __forceinline__ float entry_key(uint64_t e) { return key_of_
 __host__ __device__ __forceinline__ uint32_t entry_id(uint64_t e) { return ~uint32_t(e); }
 
 #ifdef __CUDACC__
+// ------------------------------------------------------------------ device-side status (bounded waits never trap)
+// A wait that runs out of time (an mbarrier of a TMA/MMA ring, a peer's exchange flag) records a TT_STATUS_* code
+// and lets the kernel run to its end with whatever it has: the CUDA context -- and with it every other index and
+// every peer rank's mapping of this GPU -- stays alive, and the host turns the code into a TTError
+// (tt_status_configure / tt_status_read in the header).  The words are per translation unit (no relocatable
+// device code in this build) and per device, like every __device__ variable; api.cu fans configure/read out.
+struct StatusCfg {
+    unsigned* mapped;          // optional host-mapped (pinned) word the host can poll without a device read
+    long long timeout_cycles;  // bound on one wait
+};
+static __device__ unsigned g_status_word = 0u;
+static __device__ StatusCfg g_status_cfg = {nullptr, 8000000000ll};
+
+__device__ __forceinline__ void status_report(unsigned code) {
+    atomicOr(&g_status_word, code);
+    unsigned* m = g_status_cfg.mapped;
+    if (m) {
+        atomicOr_system(m, code);
+        __threadfence_system();
+    }
+}
+__device__ __forceinline__ bool status_raised() { return *reinterpret_cast<volatile unsigned*>(&g_status_word) != 0u; }
+__device__ __forceinline__ long long status_timeout_cycles() { return g_status_cfg.timeout_cycles; }
+
+static inline int status_configure_tu(unsigned* mapped, long long cycles) {
+    StatusCfg c{mapped, cycles};
+    return cudaMemcpyToSymbol(g_status_cfg, &c, sizeof(c)) == cudaSuccess ? 0 : -1;
+}
+static inline int status_read_tu(unsigned* out, bool clear) {
+    unsigned v = 0u, z = 0u;
+    if (cudaMemcpyFromSymbol(&v, g_status_word, sizeof(v)) != cudaSuccess) return -1;
+    if (clear && v && cudaMemcpyToSymbol(g_status_word, &z, sizeof(z)) != cudaSuccess) return -1;
+    *out |= v;
+    return 0;
+}
+
+// every translation unit whose kernels can wait defines its pair of hooks with this (api.cu calls them all)
+#define TT_DEFINE_STATUS_HOOKS(tu)                                                                        \
+    int tu##_status_configure(unsigned* mapped, long long cycles) { return status_configure_tu(mapped, cycles); } \
+    int tu##_status_read(unsigned* out, bool clear) { return status_read_tu(out, clear); }
+
 // ------------------------------------------------------------------ warp helpers
 __device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
     uint32_t lo = __shfl_xor_sync(0xffffffffu, uint32_t(v), m);

@@ -38,8 +38,10 @@ def relations_from_docstore(docs: Dict[str, Any]):
 
 def flatten_index(leaf_ids: Sequence[str], embeddings, docs: Dict[str, Any]) -> Tuple[np.ndarray, NodeTree, List[Any]]:
     """Host-side half of the import: ``(corpus fp32 [N, D] in leaf order, NodeTree, node objects by ordinal)``.
-    Leaves the vector store knows but the docstore does not (or the reverse) are an error, as they would make
-    ordinals and corpus rows disagree."""
+    An embedded id the docstore does not know is an error (the auto-merge could not place it).  A childless docstore
+    node WITHOUT an embedding is kept and warned about: the reference would still serve such an index -- the node can
+    never be retrieved, but it keeps counting in its parent's ``len(child_nodes)`` -- so it gets an ordinal after the
+    leaves (no corpus row) and the engine load goes through."""
     leaf_ids = list(leaf_ids)
     missing = [i for i in leaf_ids if i not in docs]
     if missing:
@@ -48,7 +50,9 @@ def flatten_index(leaf_ids: Sequence[str], embeddings, docs: Dict[str, Any]) -> 
     embedded = set(leaf_ids)
     stray = [i for i, n in docs.items() if not children[i] and i not in embedded]
     if stray:
-        raise ValueError(f"{len(stray)} leaf nodes of the docstore have no embedding (first: {stray[0]!r})")
+        import warnings
+
+        warnings.warn(f"{len(stray)} childless docstore nodes have no embedding and cannot be retrieved (first: {stray[0]!r})")
     tree = tree_from_relations(list(docs), parent, children, prev, nxt, leaf_ids)
     corpus = np.ascontiguousarray(np.asarray(embeddings, dtype=np.float32))
     if corpus.ndim != 2 or corpus.shape[0] != len(leaf_ids):
@@ -57,11 +61,36 @@ def flatten_index(leaf_ids: Sequence[str], embeddings, docs: Dict[str, Any]) -> 
     return corpus, tree, nodes
 
 
-def load_device_index(collection: Any, docstore: Any, device=None, **index_kw):
+def collection_score_mode(collection: Any) -> int:
+    """The score the reference surfaces for this collection.  It opens Chroma with ``get_or_create_collection("data")``
+    (rag_engine.py:628-630, builder.py:424-426) and never sets ``hnsw:space``, so the space is Chroma's default,
+    squared L2, and ``ChromaVectorStore`` reports ``exp(-distance)`` -> ``SCORE_CHROMA_L2_EXP``.  The auto-merge averages
+    children's scores, and a mean is not invariant under that transform: only this mode reproduces the reference's
+    merged-parent scores (and with them its order and the per-index truncation of ``_balance_top_k_per_index``).
+    A collection created with another space is refused rather than silently scored differently."""
+    from ._lib import SCORE_CHROMA_L2_EXP
+
+    meta = getattr(collection, "metadata", None) or {}
+    space = meta.get("hnsw:space", "l2") if isinstance(meta, dict) else "l2"
+    cfg = getattr(collection, "configuration_json", None)
+    if isinstance(cfg, dict):
+        space = (cfg.get("hnsw") or {}).get("space", space) or space
+    if space != "l2":
+        raise ValueError(f"collection space {space!r}: only Chroma's default squared-L2 space is reproduced; "
+                         "pass score_mode explicitly to override")
+    return SCORE_CHROMA_L2_EXP
+
+
+def load_device_index(collection: Any, docstore: Any, device=None, score_mode: Optional[int] = None, **index_kw):
     """Snapshot a loaded reference index into HBM.  Returns ``(DeviceIndex, nodes_by_ordinal)``.
-    The stored embeddings are fp32: they become the fp32 master, scanned through a bf16 shadow (index.py)."""
+    The stored embeddings are fp32: they become the fp32 master, scanned through a bf16 shadow (index.py).
+    ``score_mode`` defaults to what the reference reports for the collection (``collection_score_mode``:
+    ``exp(-squared L2)``); ``SCORE_COSINE`` is the explicit choice of the synthetic benchmark."""
     from .index import DeviceIndex
 
+    if score_mode is None:
+        score_mode = collection_score_mode(collection)
+    index_kw["score_mode"] = score_mode
     got = collection.get(include=["embeddings"])
     docs = docstore.docs if hasattr(docstore, "docs") else dict(docstore)
     corpus, tree, nodes = flatten_index(got["ids"], got["embeddings"], docs)

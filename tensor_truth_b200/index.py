@@ -69,6 +69,34 @@ class MergeResult:
     lens: torch.Tensor      # int32   [B]
 
 
+class StepGraph:
+    """One query batch through the whole device pipeline, captured as a CUDA graph.  Inputs and outputs are
+    device-resident and fixed: write the batch into ``q`` (stream-ordered, e.g. ``q.copy_(...)``), ``replay()``, read
+    ``result`` (leaf top-k + certificate margins) / ``merged`` (auto-merged lists).  Produced by
+    ``DeviceIndex.step_graph`` and ``ShardedIndex.step_graph``; replays go to the current stream."""
+
+    def __init__(self, graph, q, result, merged, eps, extra=None):
+        self.graph, self.q, self.result, self.merged, self.eps, self.extra = graph, q, result, merged, eps, extra
+
+    def replay(self) -> None:
+        self.graph.replay()
+
+
+def capture_on_side_stream(device, fn):
+    """``fn()`` once eagerly on the current stream (lazy initialisation; for a sharded index one real exchange, which
+    every rank makes), then once more under capture on a side stream.  Returns ``(graph, fn's captured return value)``."""
+    with _CAPTURE_LOCK:
+        cur = torch.cuda.current_stream(device)
+        fn()
+        side = torch.cuda.Stream(device)
+        side.wait_stream(cur)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+            out = fn()
+        cur.wait_stream(side)
+    return graph, out
+
+
 def _as_device_corpus(corpus, device):
     if isinstance(corpus, np.ndarray):
         if corpus.dtype == np.uint16:  # bf16 bit patterns
@@ -132,15 +160,28 @@ class DeviceIndex:
                 nrm = 1.0 / self.inv_norm.double()
                 lo_v, hi_v = float(nrm.min()), float(nrm.max())
             self.norm_lo, self.norm_hi = max(0.0, lo_v * (1 - 1e-5)), hi_v * (1 + 1e-5)
-        self.set_tree(tree)
         self._ws: dict = {}
         self._lock = threading.Lock()  # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420)
+        self.set_tree(tree)
+        _lib.status_word(self._dev_index)  # device-side timeouts surface as TTError after the next host synchronisation
         self.fallbacks = 0             # queries whose certificate failed and were re-run through the exact scan
         self.retries = 0               # queries of a hi-only batch re-run through the hi+lo scan
+        self.deep_rescans = 0          # queries re-run hi+lo with K' = 128 shortlists before the exact scan is tried
         self.scan_events = None        # bench hook: a list collects (start, end) CUDA events around every stage-1 launch
 
     # ------------------------------------------------------------------ tree
     def set_tree(self, tree: Optional[NodeTree]) -> None:
+        """Install (or drop) the node tree.  Captured pipelines bake the old tree arrays' addresses in, so every cached
+        graph / step graph is dropped with them."""
+        lock = getattr(self, "_lock", None) or contextlib.nullcontext()
+        with lock:
+            ws = getattr(self, "_ws", None)
+            if ws:
+                for key in [key for key in ws if isinstance(key, tuple) and key and key[0] in ("graph", "step")]:
+                    del ws[key]
+            self._set_tree_locked(tree)
+
+    def _set_tree_locked(self, tree: Optional[NodeTree]) -> None:
         self.tree = tree
         if tree is None:
             self.parent_of = self.child_count = self.prev_id = self.next_id = None
@@ -158,10 +199,12 @@ class DeviceIndex:
         return (hi_only and b >= int(os.environ.get("TT_GEMM_ABOVE", GEMM_ABOVE)) and self.variant in (SCAN_AUTO, _lib.SCAN_TCGEN05) and self.dim % 64 == 0
                 and self.n_rows > 0 and not os.environ.get("TT_NO_GEMM"))
 
-    def _buffers(self, b: int, k: int, slot: int = 0, hi_only: Optional[bool] = None):
-        """Workspace set for a (batch, k) shape; ``slot`` separates sets used concurrently on different streams."""
-        gemm = self._use_gemm(b, b > HI_ONLY_ABOVE if hi_only is None else hi_only)
-        key = (b, k, slot, gemm)
+    def _buffers(self, b: int, k: int, slot: int = 0, hi_only: Optional[bool] = None, kprime: Optional[int] = None):
+        """Workspace set for a (batch, k) shape; ``slot`` separates sets used concurrently on different streams;
+        ``kprime`` overrides the per-CTA shortlist length (the repair ladder's deeper re-scan)."""
+        gemm = self._use_gemm(b, b > HI_ONLY_ABOVE if hi_only is None else hi_only) and kprime is None
+        kprime = int(kprime or self.kprime)
+        key = (b, k, slot, gemm, kprime)
         w = self._ws.get(key)
         if w is None and gemm:
             dev, kp = self.device, gemm_kprime(k)
@@ -173,7 +216,7 @@ class DeviceIndex:
                 "cand_ids": torch.empty((b, kp), dtype=torch.int64, device=dev),
                 "cand_approx": torch.empty((b, kp), dtype=torch.float32, device=dev),
                 "cand_thresh": torch.empty((b, 1), dtype=torch.float32, device=dev),
-                "ws": torch.empty(max(1, int(self.lib.tt_rescore_workspace_bytes(b, kp))), dtype=torch.uint8, device=dev),
+                "ws": torch.zeros(max(8, int(self.lib.tt_rescore_fused_workspace_bytes(b, kp))), dtype=torch.uint8, device=dev),
                 "gemm_ws": torch.empty(int(self.lib.tt_scan_gemm_workspace_bytes(sl, kp)), dtype=torch.uint8, device=dev),
                 "keys": torch.empty((b, k), dtype=torch.float32, device=dev),
                 "scores": torch.empty((b, k), dtype=torch.float32, device=dev),
@@ -182,14 +225,15 @@ class DeviceIndex:
             }
             self._ws[key] = w
         if w is None:
-            dev, n_cand = self.device, self.n_lists * self.kprime
+            dev, n_cand = self.device, self.n_lists * kprime
             w = {
+                "kprime": kprime,
                 "q_hi": torch.empty((b, self.dim), dtype=torch.bfloat16, device=dev),
                 "q_lo": torch.empty((b, self.dim), dtype=torch.bfloat16, device=dev),
                 "cand_ids": torch.empty((b, n_cand), dtype=torch.int64, device=dev),
                 "cand_approx": torch.empty((b, n_cand), dtype=torch.float32, device=dev),
                 "cand_thresh": torch.empty((b, self.n_lists), dtype=torch.float32, device=dev),
-                "ws": torch.empty(max(1, int(self.lib.tt_rescore_workspace_bytes(b, n_cand))), dtype=torch.uint8, device=dev),
+                "ws": torch.zeros(max(8, int(self.lib.tt_rescore_fused_workspace_bytes(b, n_cand))), dtype=torch.uint8, device=dev),
                 "keys": torch.empty((b, k), dtype=torch.float32, device=dev),
                 "scores": torch.empty((b, k), dtype=torch.float32, device=dev),
                 "ids": torch.empty((b, k), dtype=torch.int64, device=dev),
@@ -225,14 +269,36 @@ class DeviceIndex:
         return q
 
     # ------------------------------------------------------------------ stage 1 + 2
+    def _am_args(self, ratio_thresh: float, out: "MergeResult", max_rounds: int = 64):
+        """``tt_automerge_args_t`` for the kernels that run stage 3 as their tail (tree arrays + the outputs in ``out``)."""
+        if self.tree is None:
+            raise RuntimeError("this index has no node tree: auto-merge is not available")
+        return _lib.AutomergeArgs(ptr(self.parent_of), ptr(self.child_count), ptr(self.prev_id), ptr(self.next_id),
+                                  self.n_nodes, float(ratio_thresh), int(max_rounds), ptr(out.ids), ptr(out.scores),
+                                  ptr(out.lens), int(out.ids.shape[1]))
+
+    def _stage2(self, q, b, w, n_cand, n_lists, k, xchg=None, cert=None, am=None):
+        """Exact re-score of the shortlist + top-k selection in ONE launch (``tt_rescore_topk_fused``): the block that
+        finishes a query's re-scoring last selects, then pushes the record to the peer ranks (``xchg``) or runs the
+        auto-merge on it (``am``)."""
+        src = self.master if self.master is not None else self.corpus
+        check(self.lib.tt_rescore_topk_fused(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
+                                             self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q), b,
+                                             ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), n_lists, k, self.score_mode,
+                                             ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
+                                             ptr(w["ws"]), w["ws"].numel(), C.byref(xchg) if xchg is not None else None,
+                                             C.byref(cert) if cert is not None else None,
+                                             C.byref(am) if am is not None else None, self._stream()))
+
     def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None, hi_only: Optional[bool] = None,
-               xchg=None) -> SearchResult:
+               xchg=None, am=None) -> SearchResult:
         """Shortlist scan + exact re-score.  Asynchronous on the current stream; ``margin[b] > result.eps``
         certifies that query b's top-k is the exact one (``search_certified`` acts on it).
         ``hi_only``: send the queries through the tensor cores as bf16 hi halves only (twice the queries per
         corpus pass, wider certificate); default: batches above ``HI_ONLY_ABOVE``.
         ``xchg`` (``_lib.Exchange``): row-sharded corpus -- the selecting kernel also pushes this shard's top-k
-        record to every peer rank (sharded.py)."""
+        record to every peer rank (sharded.py).
+        ``am`` (``_am_args``): single shard -- the selecting kernel also auto-merges the list it selected."""
         q = self._check_queries(q)
         b = int(q.shape[0])
         if hi_only is None:
@@ -244,6 +310,12 @@ class DeviceIndex:
             # certificate below would refuse every query -- let the exact fp64 scan answer directly.
             ex = self.search_exact(q, k, out=w)
             w["margin"].fill_(float("inf"))
+            if xchg is not None:
+                raise ValueError("chroma_l2_exp over a row-sharded corpus needs (near-)equal row norms")
+            if am is not None:
+                check(self.lib.tt_automerge(ptr(ex.ids), ptr(ex.scores), b, k, am.parent_of, am.child_count, am.prev_id,
+                                            am.next_id, am.n_nodes, am.ratio_thresh, am.max_rounds, am.out_ids,
+                                            am.out_scores, am.out_len, am.max_out, self._stream()))
             return SearchResult(ex.keys, ex.scores, ex.ids, w["margin"], 0.0)
         eps = self.eps + (EPS_HI_ONLY if hi_only else 0.0)
         cert = None
@@ -251,7 +323,8 @@ class DeviceIndex:
             cert = _lib.L2Cert(self.norm_lo, self.norm_hi, eps)
         L, st = self.lib, self._stream()
         gemm = bool(w.get("gemm")) and hi_only
-        n_cand, n_lists = (w["kprime"], 1) if gemm else (self.n_lists * self.kprime, self.n_lists)
+        kprime = w.get("kprime", self.kprime)
+        n_cand, n_lists = (kprime, 1) if gemm else (self.n_lists * kprime, self.n_lists)
         with self._on_device():
             check(L.tt_prepare_queries(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), st))
             if self.scan_events is not None:
@@ -266,20 +339,14 @@ class DeviceIndex:
                                                    ptr(w["gemm_ws"]), w["gemm_ws"].numel(), st))
             else:
                 check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus), ptr(self.inv_norm),
-                                          ptr(w["q_hi"]), None if hi_only else ptr(w["q_lo"]), b, self.kprime, self.id_base,
+                                          ptr(w["q_hi"]), None if hi_only else ptr(w["q_lo"]), b, kprime, self.id_base,
                                           self.variant,
                                           ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]),
                                           ptr(w["scan_ws"]), w["scan_ws"].numel(), st))
             if self.scan_events is not None:
                 e1.record()
                 self.scan_events.append((e0, e1))
-            src = self.master if self.master is not None else self.corpus
-            check(L.tt_rescore_topk_push(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
-                                         self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q), b,
-                                         ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), n_lists, k, self.score_mode,
-                                         ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
-                                         ptr(w["ws"]), w["ws"].numel(), C.byref(xchg) if xchg is not None else None,
-                                         C.byref(cert) if cert is not None else None, st))
+            self._stage2(q, b, w, n_cand, n_lists, k, xchg, cert, am)
         # cosine: proven iff margin > eps;  L2: the bound already contains eps, proven iff margin > 0
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if l2 else eps, bool(hi_only))
 
@@ -316,19 +383,34 @@ class DeviceIndex:
             self._repair(q, k, r, bad, hi_lo_first=r.hi_only)
         return r
 
+    def _rescan(self, q, k, r: SearchResult, bad: torch.Tensor, kprime: Optional[int]) -> torch.Tensor:
+        """Re-run the queries ``bad`` hi+lo (optionally with deeper per-CTA shortlists), copy the ones that are now proven
+        into ``r`` and return the indices still unproven.  The sub-batch is padded to a power of two (repeating its
+        last query) so that a long-lived service keeps a handful of repair workspaces, not one per failure count."""
+        n_bad = int(bad.numel())
+        n_pad = 1 << max(0, n_bad - 1).bit_length()
+        sel = bad if n_pad == n_bad else torch.cat([bad, bad[-1:].expand(n_pad - n_bad)])
+        sub = q.index_select(0, sel)
+        r2 = self.search(sub, k, out=dict(self._buffers(n_pad, k, slot=-1, hi_only=False, kprime=kprime)), hi_only=False)
+        ok = (r2.margin > r2.eps)[:n_bad]
+        good = bad[ok]
+        if good.numel():
+            r.keys.index_copy_(0, good, r2.keys[:n_bad][ok])
+            r.scores.index_copy_(0, good, r2.scores[:n_bad][ok])
+            r.ids.index_copy_(0, good, r2.ids[:n_bad][ok])
+        return bad[~ok]
+
     def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool) -> None:
-        """Queries whose certificate failed: (a hi-only batch first gets the tighter hi+lo scan,) then the exact fp64 scan."""
-        if hi_lo_first:
-            sub = q.index_select(0, bad)
-            r2 = self.search(sub, k, out=dict(self._buffers(int(sub.shape[0]), k, slot=-1, hi_only=False)), hi_only=False)
-            ok = r2.margin > r2.eps
-            good = bad[ok]
-            if good.numel():
-                r.keys.index_copy_(0, good, r2.keys[ok])
-                r.scores.index_copy_(0, good, r2.scores[ok])
-                r.ids.index_copy_(0, good, r2.ids[ok])
+        """Queries whose certificate failed climb a ladder: (a hi-only batch first gets the tighter hi+lo scan,) then a
+        hi+lo re-scan with the deepest per-CTA shortlists the kernel has (K' = 128: many near-ties of the k-th score
+        inside one CTA's share of the corpus are what defeats a short list), then the exact fp64 scan."""
+        if hi_lo_first and bad.numel():
             self.retries += int(bad.numel())
-            bad = bad[~ok]
+            bad = self._rescan(q, k, r, bad, None)
+        deep = int(self.lib.tt_scan_max_kprime())
+        if bad.numel() and self.kprime < deep and not os.environ.get("TT_NO_DEEP_RUNG"):
+            self.deep_rescans += int(bad.numel())
+            bad = self._rescan(q, k, r, bad, deep)
         if bad.numel():
             self.fallbacks += int(bad.numel())
             ex = self.search_exact(q.index_select(0, bad), k)
@@ -354,24 +436,49 @@ class DeviceIndex:
                                         int(out.ids.shape[1]), self._stream()))
         return out
 
+    def step_graph(self, b: int, k: int, ratio_thresh: float = 0.5, lane: int = 0, merged: bool = True) -> StepGraph:
+        """The device pipeline of one (batch, k) shape as ONE CUDA graph over device-resident buffers: prepare ->
+        stage 1 -> re-score + select + auto-merge (3 kernel nodes for batch <= 32).  ``lane`` picks an independent
+        workspace set, so that graphs of different lanes may be in flight on different streams at once."""
+        key = ("step", b, k, float(ratio_thresh), lane, merged)
+        g = self._ws.get(key)
+        if g is None:
+            dev = self.device
+            q = torch.zeros((b, self.dim), dtype=torch.float32, device=dev)
+            w = dict(self._buffers(b, k, slot=("step", lane)))
+            w["margin"] = torch.empty((b,), dtype=torch.float32, device=dev)
+            mo = None
+            if merged:
+                mo = MergeResult(torch.empty((b, max(2 * k, 1)), dtype=torch.int64, device=dev),
+                                 torch.empty((b, max(2 * k, 1)), dtype=torch.float64, device=dev),
+                                 torch.empty((b,), dtype=torch.int32, device=dev))
+            am = self._am_args(ratio_thresh, mo) if merged else None
+            with self._on_device():
+                graph, r = capture_on_side_stream(dev, lambda: self.search(q, k, out=w, am=am))
+            g = self._ws[key] = StepGraph(graph, q, r, mo, r.eps)
+        return g
+
     # ------------------------------------------------------------------ whole path, host in / host out
-    def _record(self, b: int, k: int, merged: bool):
+    def _record(self, b: int, k: int, merged: bool, extra_f32: int = 0):
         """One contiguous result record per query batch, so the whole answer (and the certificate margins)
         comes back in ONE device->host copy into pinned memory:
-        ``[ lens i32 B | margin f32 B | ids i64 B*w | scores (f64 merged / f32 leaves) B*w ]``."""
-        key = ("rec", b, k, merged)
+        ``[ lens i32 B | margin f32 B | ids i64 B*w | scores (f64 merged / f32 leaves) B*w | extra f32 ]``
+        (``extra``: the row-sharded path's margins of every rank, [world, B])."""
+        key = ("rec", b, k, merged, extra_f32)
         r = self._ws.get(key)
         if r is None:
             w = max(2 * k, 1) if merged else k
             ssz = 8 if merged else 4
             off_ids = 8 * b
             off_sc = off_ids + 8 * b * w
-            total = off_sc + ssz * b * w
+            off_ex = off_sc + ssz * b * w
+            total = off_ex + 4 * extra_f32
 
             def views(base):
                 return {"lens": base[0:4 * b].view(torch.int32), "margin": base[4 * b:8 * b].view(torch.float32),
                         "ids": base[off_ids:off_sc].view(torch.int64).view(b, w),
-                        "scores": base[off_sc:total].view(torch.float64 if merged else torch.float32).view(b, w)}
+                        "scores": base[off_sc:off_ex].view(torch.float64 if merged else torch.float32).view(b, w),
+                        "extra": base[off_ex:total].view(torch.float32)}
 
             dev = torch.zeros(total, dtype=torch.uint8, device=self.device)
             host = torch.zeros(total, dtype=torch.uint8).pin_memory()
@@ -411,9 +518,8 @@ class DeviceIndex:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
                 q_dev.copy_(q_pin, non_blocking=True)
-                r = self.search(q_dev, k, out=w)
-                if merged:
-                    self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+                am = self._am_args(ratio_thresh, MergeResult(d["ids"], d["scores"], d["lens"])) if merged else None
+                r = self.search(q_dev, k, out=w, am=am)  # prepare -> scan -> re-score + select + auto-merge: 3 kernels
                 rec["host"].copy_(rec["dev"], non_blocking=True)
             torch.cuda.current_stream(self.device).wait_stream(side)
             g.update(graph=graph, q_pin=q_pin, q_dev=q_dev, result=r, rec=rec)
@@ -461,12 +567,12 @@ class DeviceIndex:
                 w["margin"] = d["margin"]
                 if not merged:
                     w["ids"], w["scores"] = d["ids"], d["scores"]
-                r = self.search(q, k, out=w)
-                if merged:
-                    self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+                am = self._am_args(ratio_thresh, MergeResult(d["ids"], d["scores"], d["lens"])) if merged else None
+                r = self.search(q, k, out=w, am=am)
                 rec["host"].copy_(rec["dev"], non_blocking=True)
             rec["event"].record()
             rec["event"].synchronize()
+            _lib.check_status(self._dev_index)
             bad = np.nonzero(~(h["margin"].numpy() > r.eps))[0]
             if bad.size:  # not proven exact: re-run those queries (tighter scan, then the exact fp64 scan)
                 self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only)
@@ -475,6 +581,7 @@ class DeviceIndex:
                 rec["host"].copy_(rec["dev"], non_blocking=True)
                 rec["event"].record()
                 rec["event"].synchronize()
+                _lib.check_status(self._dev_index)
             ids, scores = h["ids"].numpy().copy(), h["scores"].numpy().astype(np.float64)
             lens = h["lens"].numpy().copy() if merged else (ids >= 0).sum(axis=1).astype(np.int32)
             return ids, scores, lens

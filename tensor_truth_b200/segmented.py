@@ -72,7 +72,7 @@ class SegmentedIndex(DeviceIndex):
 
     # ------------------------------------------------------------------ stage 1 + 2 over virtual queries
     def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None, hi_only: Optional[bool] = None,
-               xchg=None) -> SearchResult:
+               xchg=None, am=None) -> SearchResult:
         """Exact top-k of every segment for every query: rows v = s * B + b of the result belong to (segment s,
         query b); ids are rows of the concatenated corpus.  Asynchronous on the current stream."""
         if xchg is not None or hi_only:
@@ -98,12 +98,7 @@ class SegmentedIndex(DeviceIndex):
                                                 self.id_base, self._seg_end, self.n_seg, ptr(w["cand_ids"]),
                                                 ptr(w["cand_approx"]), ptr(w["cand_thresh"]), ptr(w["scan_ws"]),
                                                 w["scan_ws"].numel(), st))
-            src = self.master if self.master is not None else self.corpus
-            check(L.tt_rescore_topk_push(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
-                                         self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q_rep), vb,
-                                         ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), self.n_lists, k, self.score_mode,
-                                         ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
-                                         ptr(w["ws"]), w["ws"].numel(), None, C.byref(cert) if cert is not None else None, st))
+            self._stage2(q_rep, vb, w, n_cand, self.n_lists, k, None, cert, am)
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if cert is not None else self.eps, False)
 
     def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool) -> None:

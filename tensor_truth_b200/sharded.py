@@ -74,60 +74,100 @@ class ShardedSearch:
 class PeerBuffers:
     """Symmetric (peer-mapped) receive regions + flags for one (batch, k) shape: what lets the selecting kernel push
     its record straight into every rank's memory and the merging kernel wait on flags (include/tt_b200.h,
-    ``tt_exchange_t``).  A ring of ``DEPTH`` slots: with steps alternating between two streams, slot e % 4 is only
-    rewritten (epoch e+4) after this rank merged epoch e+2, which needed every peer's push of e+2, which on that peer
-    is stream-ordered after ITS merge of epoch e -- so nobody is still reading the slot."""
+    ``tt_exchange_t``).
 
-    DEPTH = 4
+    ``lanes`` independent lanes (one per stream of a pipelined caller), each a ring of ``SLOTS`` = 2 receive regions
+    and its own device-resident epoch counter: the kernels read the epoch -- and with it the slot -- from device
+    memory, so the descriptor of a lane never changes and a captured CUDA graph of the step replays as it is.  Two
+    slots per lane suffice: slot e % 2 is rewritten at epoch e + 2, after this rank merged e + 1, which needed every
+    peer's push of e + 1, which that peer issued (stream order) after ITS merge of e -- nobody still reads the slot.
+    All ranks must issue the same sequence of pushes per lane.  One extra flag array serves ``barrier()``."""
 
-    def __init__(self, b: int, k: int, device: torch.device, group=None):
-        import torch.distributed._symmetric_memory as symm_mem
+    SLOTS = 2
 
-        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        self.b, self.k = b, k
+    def __init__(self, b: int, k: int, device: torch.device, group=None, lanes: int = 2, _local=None):
+        self.b, self.k, self.lanes, self.device = b, k, lanes, device
+        if _local is not None:  # (world, rank, [buffers of all simulated ranks]): see local_group()
+            self.world, self.rank, bufs = _local
+        else:
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         rec, self.ids_off, _ = record_layout(b, k)
         self.margins_off = rec               # [keys | ids | margins float32 B]: the source's certificate margins ride along
         self.rec_bytes = rec + 4 * b         # what one source writes (and what tt_exchange_push copies)
         self.rec_stride = (self.rec_bytes + 15) // 16 * 16
-        self.region = self.world * self.rec_stride
-        self.flags_off = (self.DEPTH * self.region + 127) // 128 * 128
-        total = self.flags_off + (self.DEPTH * self.world * 4 + 127) // 128 * 128
-        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
-        self.buf.zero_()
-        self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
-        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        self.tickets = torch.zeros(self.DEPTH, dtype=torch.int32, device=device)
-        self.epoch = 0
+        self.region = self.world * self.rec_stride                      # one slot
+        self.flag_stride = (self.world + 31) // 32 * 32                 # uint32 elements per slot
+        self.flags_off = (lanes * self.SLOTS * self.region + 127) // 128 * 128
+        n_flag_arrays = lanes * self.SLOTS + 1                          # + the barrier's
+        self.total_bytes = self.flags_off + n_flag_arrays * self.flag_stride * 4
+        if _local is not None:
+            self.buf = bufs[self.rank]
+            self.ptrs = [int(t.data_ptr()) for t in bufs]
+        else:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            self.buf = symm_mem.empty(self.total_bytes, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.hdl = symm_mem.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+            self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._bind()
+        torch.cuda.synchronize(device)
+        if _local is None:
+            dist.barrier(group)  # every rank's zero-fill has landed before anyone pushes
+
+    @classmethod
+    def local_group(cls, world: int, b: int, k: int, device: torch.device, lanes: int = 2):
+        """``world`` simulated ranks inside ONE process on ONE device: plain device buffers stand in for the peer
+        mappings (a rank's "peer pointer" is just the other rank's buffer).  The kernels cannot tell the difference --
+        same descriptors, same stores, same flags -- which is what lets a single-GPU box exercise the exchange
+        protocol (tests/test_gpu_exchange_one_device.py).  The caller must run the ranks on different streams."""
+        stride = (record_layout(b, k)[0] + 4 * b + 15) // 16 * 16
+        flags_off = (lanes * cls.SLOTS * world * stride + 127) // 128 * 128
+        total = flags_off + (lanes * cls.SLOTS + 1) * ((world + 31) // 32 * 32) * 4
+        bufs = [torch.zeros(total, dtype=torch.uint8, device=device) for _ in range(world)]
+        return [cls(b, k, device, lanes=lanes, _local=(world, r, bufs)) for r in range(world)]
+
+    def _bind(self) -> None:
         from ._lib import Exchange
 
+        lanes, device = self.lanes, self.device
+        self.epochs = torch.zeros(lanes + 1, dtype=torch.int32, device=device)   # device-resident epoch per lane (+ barrier)
+        self.tickets = torch.zeros(lanes + 1, dtype=torch.int32, device=device)
+        self.all_margins = torch.zeros((lanes, self.world, self.b), dtype=torch.float32, device=device)
         self._x = []
-        for slot in range(self.DEPTH):  # one descriptor per slot; only the epoch changes from step to step
+        for lane in range(lanes + 1):
             x = Exchange()
-            x.world, x.rank = self.world, self.rank
+            x.world, x.rank, x.epoch = self.world, self.rank, 0
             x.rec_stride_bytes, x.ids_off_bytes = self.rec_stride, self.ids_off
             x.margins_off_bytes = self.margins_off
+            barrier = lane == lanes
             for p in range(self.world):
-                x.peer_recv[p] = self.ptrs[p] + slot * self.region
-                x.peer_flags[p] = self.ptrs[p] + self.flags_off + slot * self.world * 4
-            x.ticket = self.tickets.data_ptr() + 4 * slot
+                flags = self.ptrs[p] + self.flags_off + lane * self.SLOTS * self.flag_stride * 4
+                x.peer_flags[p] = flags
+                x.peer_recv[p] = flags if barrier else self.ptrs[p] + lane * self.SLOTS * self.region
+            x.ticket = self.tickets.data_ptr() + 4 * lane
+            x.epoch_dev = self.epochs.data_ptr() + 4 * lane
+            x.n_slots = 1 if barrier else self.SLOTS
+            x.slot_stride_bytes = 0 if barrier else self.region
+            x.flag_slot_stride = self.flag_stride
             self._x.append(x)
-        torch.cuda.synchronize(device)
-        dist.barrier(group)  # every rank's zero-fill has landed before anyone pushes
 
-    def next(self):
-        """The exchange descriptor of the next step (all ranks call this in lockstep) and the local addresses the merge reads."""
-        self.epoch += 1
-        slot = (self.epoch - 1) % self.DEPTH
-        x = self._x[slot]  # the library copies it into the kernel parameters at launch, so reuse is safe
-        x.epoch = self.epoch
-        self.last_slot = slot
-        return x, self.ptrs[self.rank] + slot * self.region
+    def desc(self, lane: int = 0):
+        """The (constant) exchange descriptor of a lane; the library copies it into the kernel parameters at launch."""
+        return self._x[lane]
 
-    def margins_view(self, slot: int) -> torch.Tensor:
-        """float32 [world, B] view of the margins every source pushed into this rank's receive region of ``slot``."""
-        base = slot * self.region
-        recs = self.buf[base: base + self.world * self.rec_stride].view(self.world, self.rec_stride)
-        return recs[:, self.margins_off: self.margins_off + 4 * self.b].view(torch.float32)
+    def region_ptr(self, lane: int = 0) -> int:
+        """Local address of the lane's receive ring (slot 0); the kernels add the slot offset themselves."""
+        return self.ptrs[self.rank] + lane * self.SLOTS * self.region
+
+    def barrier(self, lib, stream) -> None:
+        """Device-side rendezvous of all ranks, enqueued on ``stream`` (``tt_peer_barrier``): no host involved, so what
+        follows it in stream order starts within an NVLink round trip of the slowest rank."""
+        import ctypes as C
+
+        from ._lib import check
+
+        check(lib.tt_peer_barrier(C.byref(self._x[self.lanes]), stream))
 
     def send_record(self):
         """A local record in the layout of one source's slice of a receive region (for tt_exchange_push): the uint8
@@ -142,7 +182,9 @@ class PeerBuffers:
 
 
 class ShardedIndex:
-    """``DeviceIndex`` shards + NCCL all-gather + the CUDA merge and auto-merge kernels."""
+    """``DeviceIndex`` shards + the fused peer exchange (or an NCCL all-gather) + the CUDA merge and auto-merge kernels."""
+
+    LANES = 2
 
     def __init__(self, local_index, group=None):
         from . import _lib
@@ -156,6 +198,8 @@ class ShardedIndex:
         self.group = group
         self._peers: dict = {}
         self._host_bufs: dict = {}
+        self._graphs: dict = {}
+        self.second_rounds = 0
         # peer pushes need symmetric memory (NVLink peer mappings); without it the exchange is an NCCL all-gather
         self.transport = "nccl" if os.environ.get("TT_EXCHANGE", "peer") == "nccl" or self.plumbing.world == 1 else "peer"
 
@@ -165,7 +209,7 @@ class ShardedIndex:
         pb = self._peers.get((b, k))
         if pb is None:
             try:
-                pb = self._peers[(b, k)] = PeerBuffers(b, k, self.device, self.group)
+                pb = self._peers[(b, k)] = PeerBuffers(b, k, self.device, self.group, lanes=self.LANES)
             except Exception as exc:  # every rank fails alike (same node, same driver): fall back together
                 import warnings
 
@@ -181,16 +225,21 @@ class ShardedIndex:
                                                torch.empty((b, k_out), dtype=torch.int64, device=self.device))
         return o
 
-    def _merge_pulled(self, x, region_ptr, b, k, k_out, slot):
-        """Merge straight out of this rank's receive region once every source's flag has reached the epoch."""
+    def _merge_pulled(self, pb, lane, b, k, k_out, slot, am=None, all_margins=None):
+        """Merge straight out of this rank's receive ring once every source's flag has reached the lane's epoch
+        (``tt_merge_topk_fused``); the same kernel copies out the margins every source pushed (``all_margins``
+        float32 [world, B]) and runs the auto-merge on the merged list (``am``)."""
         import ctypes as C
 
         L, ptr, check = self._lib.lib(), self._lib.ptr, self._lib.check
         o = self._outputs(b, k_out, slot)
+        x = pb.desc(lane)
+        region = pb.region_ptr(lane)
         with self.local._on_device():
-            check(L.tt_merge_topk_pulled(region_ptr, region_ptr + x.ids_off_bytes, x.world, x.rec_stride_bytes // 4,
-                                         x.rec_stride_bytes // 8, b, k, k_out, self.local.score_mode, ptr(o[0]), ptr(o[1]),
-                                         C.byref(x), self.local._stream()))
+            check(L.tt_merge_topk_fused(region, region + pb.ids_off, pb.world, pb.rec_stride // 4, pb.rec_stride // 8, b, k,
+                                        k_out, self.local.score_mode, ptr(o[0]), ptr(o[1]), C.byref(x),
+                                        ptr(all_margins) if all_margins is not None else None,
+                                        C.byref(am) if am is not None else None, self.local._stream()))
         return o
 
     def _local_search(self, q, k, keys_out, ids_out, slot=0):
@@ -211,28 +260,80 @@ class ShardedIndex:
                                   self.local.score_mode, ptr(o[0]), ptr(o[1]), self.local._stream()))
         return o
 
-    def search(self, q, k, margins: Optional[torch.Tensor] = None, slot: int = 0):
+    def search(self, q, k, margins: Optional[torch.Tensor] = None, slot: int = 0, merged_out=None, ratio_thresh: float = 0.5):
         """Merged exact top-k, identical on every rank: ``(scores [B,k], ids [B,k])``.  ``margins`` (float32 [B])
-        receives this rank's certificate margins (compare with ``self.last.eps``)."""
+        receives this rank's certificate margins (compare with ``self.last.eps``).  ``slot``: the lane (stream) of a
+        pipelined caller, < ``LANES``.  ``merged_out`` (``MergeResult``): also auto-merge the merged list into it -- on
+        the peer transport inside the merging kernel."""
         self._margins = margins
         q = self.local._check_queries(q)
         b = int(q.shape[0])
         pb = self.peers(b, k)
         if pb is None:
-            return self.plumbing.search(q, k, slot=slot)
+            scores, ids = self.plumbing.search(q, k, slot=slot)
+            if merged_out is not None:
+                self.local.automerge(ids, scores, ratio_thresh, out=merged_out)
+            return scores, ids
         # fused exchange: the selecting kernel pushes to every peer, the merging kernel waits on the flags
-        x, region = pb.next()
         w = dict(self.local._buffers(b, k, slot))
         if margins is not None:
             w["margin"] = margins
-        self.last = self.local.search(q, k, out=w, xchg=x)
-        return self._merge_pulled(x, region, b, k, k, slot)
+        self.last = self.local.search(q, k, out=w, xchg=pb.desc(slot))
+        am = self.local._am_args(ratio_thresh, merged_out) if merged_out is not None else None
+        return self._merge_pulled(pb, slot, b, k, k, slot, am=am)
+
+    def step_graph(self, b: int, k: int, ratio_thresh: float = 0.5, lane: int = 0, merged: bool = True):
+        """The sharded step over device-resident buffers as ONE CUDA graph: prepare -> scan -> re-score + select + push
+        -> flag-wait + merge + auto-merge (4 kernel nodes for batch <= 32; the exchange lives inside the last two).
+        Every rank must create and replay its graphs in the same order per lane.  Peer transport only."""
+        from .index import MergeResult, StepGraph, capture_on_side_stream
+
+        key = (b, k, float(ratio_thresh), lane, merged)
+        g = self._graphs.get(key)
+        if g is None:
+            pb = self.peers(b, k)
+            if pb is None:
+                raise RuntimeError("ShardedIndex.step_graph needs the peer transport (symmetric memory)")
+            dev = self.device
+            q = torch.zeros((b, self.local.dim), dtype=torch.float32, device=dev)
+            margins = torch.empty((b,), dtype=torch.float32, device=dev)
+            mo = None
+            if merged:
+                mo = MergeResult(torch.empty((b, max(2 * k, 1)), dtype=torch.int64, device=dev),
+                                 torch.empty((b, max(2 * k, 1)), dtype=torch.float64, device=dev),
+                                 torch.empty((b,), dtype=torch.int32, device=dev))
+            out = {}
+
+            def fn():
+                scores, ids = self.search(q, k, margins=margins, slot=lane, merged_out=mo, ratio_thresh=ratio_thresh)
+                out["r"] = (scores, ids)
+                return self.last
+
+            with self.local._on_device():
+                graph, last = capture_on_side_stream(dev, fn)
+            from .index import SearchResult
+
+            scores, ids = out["r"]
+            r = SearchResult(scores, scores, ids, margins, last.eps, last.hi_only)  # merged keys are reported as scores
+            g = self._graphs[key] = StepGraph(graph, q, r, mo, last.eps)
+        return g
+
+    def barrier(self, b: int = 1, k: int = 10) -> None:
+        """Device-side rendezvous of all ranks on the current stream (peer transport); a host barrier otherwise."""
+        pb = self.peers(b, k)
+        if pb is None:
+            if self.plumbing.world > 1:
+                dist.barrier(self.group)
+            return
+        with self.local._on_device():
+            pb.barrier(self._lib.lib(), self.local._stream())
 
     @property
     def tree(self):
         return self.local.tree
 
     def close(self) -> None:
+        self._graphs.clear()
         self._peers.clear()
         self._out.clear()
         self._host_bufs.clear()
@@ -265,28 +366,91 @@ class ShardedIndex:
         lens = h["lens"].numpy().copy() if merged else (ids_h >= 0).sum(axis=1).astype("int32")
         return ids_h, scores_h, lens
 
-    def _retrieve_host_peer(self, pb, q, b, k, ratio_thresh, merged):
+    # ------------------------------------------------------------------ host in / host out, peer transport
+    def _host_round(self, pb, q, rec, b, k, ratio_thresh, merged):
+        """First round of a host query batch on lane 0, enqueued on the current stream: local scan + re-score + select
+        + push, then flag-wait + merge (+ auto-merge), everything landing in the result record ``rec`` -- merged lists,
+        this rank's margins and the margins EVERY rank pushed (``extra``: [world, B])."""
+        from .index import MergeResult
+
+        local = self.local
+        d = rec["d"]
+        w = dict(local._buffers(b, k, slot=("host", 0)))
+        w["margin"] = d["margin"]
+        r = local.search(q, k, out=w, xchg=pb.desc(0))
+        L, ptr, check = self._lib.lib(), self._lib.ptr, self._lib.check
+        import ctypes as C
+
+        region = pb.region_ptr(0)
+        if merged:
+            o = self._outputs(b, k, ("host", 0))
+            am = local._am_args(ratio_thresh, MergeResult(d["ids"], d["scores"], d["lens"]))
+        else:
+            o, am = (d["scores"], d["ids"]), None
+        with local._on_device():
+            check(L.tt_merge_topk_fused(region, region + pb.ids_off, pb.world, pb.rec_stride // 4, pb.rec_stride // 8, b, k,
+                                        k, local.score_mode, ptr(o[0]), ptr(o[1]), C.byref(pb.desc(0)), ptr(d["extra"]),
+                                        C.byref(am) if am is not None else None, local._stream()))
+        return r
+
+    def _host_graph(self, pb, b, k, ratio_thresh, merged):
+        """The first round of ``retrieve_host`` as ONE CUDA graph: H2D of the queries from a pinned staging buffer ->
+        the four kernels of ``_host_round`` -> D2H of the result record.  Captured after ``GRAPH_AFTER`` eager calls of
+        the shape (every rank counts alike, so all ranks switch on the same call)."""
+        from .index import GRAPH_AFTER, capture_on_side_stream
+
+        key = ("host", b, k, float(ratio_thresh), merged)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = {"calls": 0, "graph": None, "dead": bool(os.environ.get("TT_NO_GRAPH"))}
+        if g["graph"] is not None:
+            return g
+        g["calls"] += 1
+        if g["dead"] or g["calls"] <= GRAPH_AFTER:
+            return None
+        local = self.local
+        rec = local._record(b, k, merged, extra_f32=pb.world * b)
+        q_pin = torch.zeros((b, local.dim), dtype=torch.float32).pin_memory()
+        q_dev = torch.zeros((b, local.dim), dtype=torch.float32, device=self.device)
+        out = {}
+
+        def fn():
+            q_dev.copy_(q_pin, non_blocking=True)
+            out["r"] = self._host_round(pb, q_dev, rec, b, k, ratio_thresh, merged)
+            rec["host"].copy_(rec["dev"], non_blocking=True)
+
+        # the eager run inside capture_on_side_stream is a real exchange round (with whatever q_pin holds: zeros);
+        # every rank makes it, so the lane's epochs stay in lockstep
+        with local._on_device():
+            graph, _ = capture_on_side_stream(self.device, fn)
+        g.update(graph=graph, q_pin=q_pin, q_dev=q_dev, result=out["r"], rec=rec)
+        return g
+
+    def _retrieve_host_peer(self, pb, q_host, b, k, ratio_thresh, merged):
         """Peer transport, ONE host synchronisation per query batch: the selecting kernel pushes this rank's record AND
-        its certificate margins to every peer, so after the merge every rank finds all ranks' margins in its own
-        receive region and they come back with the result.  Only if some rank's top-k was not proven (every rank sees
-        that, from identical data) do all ranks take a second round: local repair, plain push, merge again."""
+        its certificate margins to every peer, the merging kernel copies all ranks' margins into the result record, so
+        they come back with the answer.  Only if some rank's top-k was not proven (every rank sees that, from identical
+        data) do all ranks take a second round: local repair, plain push, merge again."""
         import ctypes as C
 
         local = self.local
-        hb = self._host_bufs.get(("all", b))
-        if hb is None:
-            hb = self._host_bufs[("all", b)] = (torch.empty((b,), dtype=torch.float32, device=self.device),
-                                                torch.empty((pb.world, b), dtype=torch.float32).pin_memory())
-        margins, all_h = hb
-        x, region = pb.next()
-        slot = pb.last_slot
-        w = dict(local._buffers(b, k))
-        w["margin"] = margins
-        r = self.last = local.search(q, k, out=w, xchg=x)
-        scores, mids = self._merge_pulled(x, region, b, k, k, 0)
-        rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged, extra=(pb.margins_view(slot), all_h))
+        g = self._host_graph(pb, b, k, ratio_thresh, merged)
+        if g is not None:
+            g["q_pin"].copy_(q_host)
+            q, r, rec = g["q_dev"], g["result"], g["rec"]
+            with local._on_device():
+                g["graph"].replay()
+        else:
+            q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
+            rec = local._record(b, k, merged, extra_f32=pb.world * b)
+            r = self._host_round(pb, q, rec, b, k, ratio_thresh, merged)
+            rec["host"].copy_(rec["dev"], non_blocking=True)
+        self.last = r
+        rec["event"].record()
         rec["event"].synchronize()
-        proven = all_h.numpy() > r.eps           # [world, B], the same on every rank
+        self._lib.check_status(local._dev_index)
+        all_h = rec["h"]["extra"].numpy().reshape(pb.world, b)
+        proven = all_h > r.eps                    # [world, B], the same on every rank
         if not proven.all():
             mine = (~proven[pb.rank]).nonzero()[0]
             if mine.size:
@@ -295,28 +459,29 @@ class ShardedIndex:
             s_keys.copy_(r.keys)
             s_ids.copy_(r.ids)
             s_margins.fill_(float("inf"))         # what is sent now is exact (proven before, or repaired)
-            x2, region2 = pb.next()
             with local._on_device():
-                self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), pb.rec_bytes // 4 * 4, C.byref(x2),
+                self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), pb.rec_bytes // 4 * 4, C.byref(pb.desc(0)),
                                                                  local._stream()))
-            scores, mids = self._merge_pulled(x2, region2, b, k, k, 0)
+            scores, mids = self._merge_pulled(pb, 0, b, k, k, ("host", 1))
             rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged)
             rec["event"].synchronize()
-            self.second_rounds = getattr(self, "second_rounds", 0) + 1
+            self._lib.check_status(local._dev_index)
+            self.second_rounds += 1
         return self._unpack_host(rec, merged)
 
     def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True):
         """Host queries in, merged (+ auto-merged) lists out (numpy), with the certificate enforced per rank.
         Same contract as ``DeviceIndex.retrieve_host``, so the retriever classes take either; every rank must call it."""
         merged = bool(merge and self.local.tree is not None)
+        if q_host.dim() != 2 or q_host.shape[1] != self.local.dim:
+            raise ValueError(f"queries must be [B, {self.local.dim}], got {tuple(q_host.shape)}")
+        b = int(q_host.shape[0])
         if self.transport == "peer":
-            q0 = self.local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
-            pb0 = self.peers(int(q0.shape[0]), k)
+            pb0 = self.peers(b, k)
             if pb0 is not None:
-                return self._retrieve_host_peer(pb0, q0, int(q0.shape[0]), k, ratio_thresh, merged)
+                return self._retrieve_host_peer(pb0, q_host, b, k, ratio_thresh, merged)
         local = self.local
         q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
-        b = int(q.shape[0])
         hb = self._host_bufs.get(b)
         if hb is None:  # margins on the device + a pinned host mirror + the event the certificate check waits on
             hb = self._host_bufs[b] = (torch.empty((b,), dtype=torch.float32, device=self.device),
@@ -328,6 +493,7 @@ class ShardedIndex:
         margins_h.copy_(margins, non_blocking=True)
         ev.record()
         ev.synchronize()
+        self._lib.check_status(local._dev_index)
         bad = (~(margins_h > r.eps)).nonzero().flatten()
         if bad.numel():  # rank-local repair (writes into the send record); the exchange below is reached by every rank
             local._repair(q, k, r, bad.to(self.device), hi_lo_first=r.hi_only)

@@ -543,9 +543,12 @@ def test_c5_shape_four_levels_top200():
         assert any(o >= tree.level_offsets[2] for o, _ in got)  # merges cascade at least two levels up
 
 
-def test_importer_end_to_end_fp32_store():
+@pytest.mark.parametrize("mode", ["default_l2_exp", "cosine"])
+def test_importer_end_to_end_fp32_store(mode):
     """a (duck-typed) Chroma collection + docstore snapshot -> DeviceIndex -> retriever; the stored
-    embeddings are fp32, so the scan runs on the bf16 shadow and the exact answer comes from the fp32 master."""
+    embeddings are fp32, so the scan runs on the bf16 shadow and the exact answer comes from the fp32 master.
+    By default the importer scores like the reference's Chroma collection (exp(-squared L2)): the merged parents' mean
+    scores -- and so their positions -- are those of that mode; cosine is the explicit override."""
     from tensor_truth_b200.importer import load_device_index
     from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200VectorIndexRetriever, NodeTable
     from tensor_truth_b200.schema import QueryBundle
@@ -561,14 +564,20 @@ def test_importer_end_to_end_fp32_store():
             assert include == ["embeddings"]
             return {"ids": [f"uuid-{o:05d}" for o in order], "embeddings": emb[order]}
 
-    idx, nodes = load_device_index(Collection(), type("DS", (), {"docs": docs})(), device=torch.device("cuda:0"))
+    kw = {} if mode == "default_l2_exp" else {"score_mode": _lib.SCORE_COSINE}
+    idx, nodes = load_device_index(Collection(), type("DS", (), {"docs": docs})(), device=torch.device("cuda:0"), **kw)
+    smode = _lib.SCORE_CHROMA_L2_EXP if mode == "default_l2_exp" else _lib.SCORE_COSINE
+    assert idx.score_mode == smode
     am = B200AutoMergingRetriever(B200VectorIndexRetriever(idx, 10, None, NodeTable(nodes=nodes)), None)
+    merged_any = False
     for b in range(q.shape[0]):
         out = am.retrieve(QueryBundle(query_str="x", embedding=q[b].tolist()))
         # oracle on the same fp32 values in the ORIGINAL leaf order, ids compared through the node ids
-        exp = oracle.retrieve(emb, q[b], 10, tree)
+        exp = oracle.retrieve(emb, q[b], 10, tree, score_mode=smode)
+        merged_any = merged_any or any(o >= tree.n_leaf for o, _ in exp)
         assert [n.node.id_ for n in out] == [f"uuid-{o:05d}" for o, _ in exp]
         assert [n.score for n in out] == [s for _, s in exp]
+    assert merged_any  # the auto-merge (mean of transformed scores) was exercised in this mode
 
 
 def test_near_duplicate_corpus_walks_the_repair_ladder():

@@ -167,8 +167,32 @@ def test_importer_flattens_docstore_and_collection():
         assert tree.child_count[o2] == len(n.child_ids)
     with pytest.raises(ValueError):
         flatten_index(leaf_ids + ["ghost"], emb.tolist() + [[0.0] * 16], docs)
+    # a docstore leaf WITHOUT an embedding does not fail the load (the reference would still serve the index): it is
+    # warned about, gets an ordinal after the embedded leaves and still counts among its parent's children
+    with pytest.warns(UserWarning, match="no embedding"):
+        corpus2, tree2, nodes2 = flatten_index(leaf_ids[:-1], emb[:-1].tolist(), docs)
+    assert corpus2.shape[0] == 299 and tree2.n_leaf == 299 and tree2.n_nodes == t.n_nodes
+    stray = [o for o in range(tree2.n_leaf, tree2.n_nodes) if nodes2[o].id_ == leaf_ids[-1]]
+    assert len(stray) == 1 and tree2.child_count[stray[0]] == 0
+    assert tree2.child_count[tree2.parent_of[stray[0]]] == len(nodes2[tree2.parent_of[stray[0]]].child_ids)
+
+
+def test_importer_defaults_to_the_score_the_reference_reports():
+    """the reference opens Chroma with the default (squared-L2) space, ChromaVectorStore reports
+    exp(-distance); the importer must default to that, refuse other spaces, and let the caller override."""
+    from tensor_truth_b200 import _lib
+    from tensor_truth_b200.importer import collection_score_mode
+
+    class Default:
+        metadata = None
+
+    class Cosine:
+        metadata = {"hnsw:space": "cosine"}
+
+    assert collection_score_mode(Default()) == _lib.SCORE_CHROMA_L2_EXP
+    assert collection_score_mode(object()) == _lib.SCORE_CHROMA_L2_EXP
     with pytest.raises(ValueError):
-        flatten_index(leaf_ids[:-1], emb[:-1].tolist(), docs)
+        collection_score_mode(Cosine())
 
 
 def test_query_is_embedded_once_across_per_index_retrievers():
