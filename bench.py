@@ -224,7 +224,9 @@ class Bench:
                 g.manual_seed(SEED * 31 + (self.lo + a) // step)
                 master[a:a + step] = c * (1.0 + (2.0 ** -9) * (torch.rand(c.shape, generator=g, device=ctx.device) - 0.5))
             self.idx = DeviceIndex(master, self.sc.tree, id_base=self.lo, device=ctx.device, kprime=kprime, variant=variant)
-            del master
+            del master, corpus, inv
+            self.corpus_bf16, self.inv = self.idx.corpus, self.idx.inv_norm  # the shadow the index derived from the master
+            torch.cuda.empty_cache()
         else:
             self.idx = DeviceIndex(corpus, self.sc.tree, inv_norm=inv, id_base=self.lo, device=ctx.device, kprime=kprime,
                                    variant=variant)

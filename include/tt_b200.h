@@ -332,7 +332,7 @@ int tt_merge_topk_fused(const float* keys, const int64_t* ids, int n_lists, int6
 /*
  * The stage AFTER the retrieval path: the dense layers of the cross-encoder reranker
  * (SentenceTransformerRerank.postprocess_nodes; services/model_manager.py:333-337, services/rag_service.py:343-346).
- * tensor_truth_b200/rerank.py strings them into an XLM-RoBERTa encoder; attention itself is a library call there.
+ * tensor_truth_b200/rerank.py strings them into an XLM-RoBERTa encoder.
  *
  * tt_linear_bf16:  y[T, n_out] = act(x[T, k_in] W[n_out, k_in]^T + bias) (+ residual[T, n_out]), all bf16 except
  *                  bias (fp32, nullable); fp32 accumulation on tcgen05 (256 x 256 tiles per CTA pair), the layer tail
@@ -350,6 +350,22 @@ int tt_layernorm_bf16(const void* x_bf16, int64_t n_rows, int dim, const float* 
 int tt_embed_layernorm_bf16(const int32_t* word_ids, const int32_t* pos_ids, int64_t n_rows, int dim,
                             const void* word_emb_bf16, const void* pos_emb_bf16, const void* type_emb_bf16,
                             const float* gamma, const float* beta, float eps, void* y_bf16, void* stream);
+
+/*
+ * tt_attention_varlen_bf16: bidirectional multi-head self-attention over PACKED sequences (no padding), the attention
+ *                  of every encoder layer.  qkv bf16 [n_tokens, 3 * n_heads * head_dim] as one fused Q|K|V projection
+ *                  writes it; cu_seqlens int32 [n_seq + 1] token offsets; out bf16 [n_tokens, n_heads * head_dim].
+ *                  One CTA per (128-row query tile, head): S = Q K^T and O += P V on tcgen05 (accumulators in TMEM),
+ *                  softmax in registers, V consumed as an MN-major operand as it lies in memory.  head_dim == 64,
+ *                  every sequence <= max_len <= 512; max_tiles >= sum_i ceil(len_i / 128) sizes the grid (surplus
+ *                  CTAs exit), e.g. n_tokens / 128 + n_seq.  scale: softmax scale (1 / sqrt(head_dim)).
+ * tt_cls_head_f32: logits[i] = w2 . tanh(W1 x[cu_seqlens[i]] + b1) + b2 on the first (<s>) token of every sequence --
+ *                  RobertaClassificationHead with one output unit; x bf16 [n_tokens, hidden], fp32 weights.
+ */
+int tt_attention_varlen_bf16(const void* qkv_bf16, int64_t n_tokens, int n_heads, int head_dim, const int32_t* cu_seqlens,
+                             int n_seq, int max_len, int max_tiles, float scale, void* out_bf16, void* stream);
+int tt_cls_head_f32(const void* x_bf16, const int32_t* cu_seqlens, int n_seq, int hidden, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* logits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,8 @@ SIGNATURES = {
     "tt_linear_bf16": (_I, [_P, _L, _I, _P, _I, _P, _P, _I, _P, _P]),
     "tt_layernorm_bf16": (_I, [_P, _L, _I, _P, _P, C.c_float, _P, _P]),
     "tt_embed_layernorm_bf16": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _P, C.c_float, _P, _P]),
+    "tt_attention_varlen_bf16": (_I, [_P, _L, _I, _I, _P, _I, _I, _I, C.c_float, _P, _P]),
+    "tt_cls_head_f32": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "tt_automerge_max_k": (_I, []),
     "tt_automerge": (_I, [_P, _P, _I, _I, _P, _P, _P, _P, _L, _D, _I, _P, _P, _P, _I, _P]),
 }

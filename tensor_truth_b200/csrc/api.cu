@@ -61,7 +61,12 @@ TT_STATUS_TU(scan_tc)
 TT_STATUS_TU(scan_tc2)
 TT_STATUS_TU(scan_gemm)
 TT_STATUS_TU(linear)
+TT_STATUS_TU(attention)
 #undef TT_STATUS_TU
+int launch_attention_varlen(const void* qkv, int64_t n_tokens, int n_heads, const int* cu_seqlens, int n_seq, int max_len,
+                            int max_tiles, float scale, void* out, cudaStream_t st);
+int launch_cls_head(const void* x, const int* cu_seqlens, int n_seq, int hidden, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* logits, cudaStream_t st);
 int launch_automerge(const int64_t* ids, const float* scores, int n_q, int k, const int32_t* parent_of,
                      const int32_t* child_count, const int32_t* prev_id, const int32_t* next_id, int64_t n_nodes,
                      double ratio_thresh, int max_rounds, int64_t* out_ids, double* out_scores, int32_t* out_len,
@@ -139,7 +144,7 @@ int tt_status_configure(uint32_t* mapped_word_host, int timeout_ms) {
     }
     if (rescore_status_configure(dev_view, cycles) || scan_tc_status_configure(dev_view, cycles) ||
         scan_tc2_status_configure(dev_view, cycles) || scan_gemm_status_configure(dev_view, cycles) ||
-        linear_status_configure(dev_view, cycles)) {
+        linear_status_configure(dev_view, cycles) || attention_status_configure(dev_view, cycles)) {
         set_error("tt_status_configure: %s", cudaGetErrorString(cudaGetLastError()));
         return TT_ERR_CUDA;
     }
@@ -151,7 +156,7 @@ int tt_status_read(uint32_t* out_host, int clear) {
     unsigned v = 0u;
     const bool c = clear != 0;
     if (rescore_status_read(&v, c) || scan_tc_status_read(&v, c) || scan_tc2_status_read(&v, c) ||
-        scan_gemm_status_read(&v, c) || linear_status_read(&v, c)) {
+        scan_gemm_status_read(&v, c) || linear_status_read(&v, c) || attention_status_read(&v, c)) {
         set_error("tt_status_read: %s", cudaGetErrorString(cudaGetLastError()));
         return TT_ERR_CUDA;
     }
@@ -485,6 +490,28 @@ int tt_embed_layernorm_bf16(const int32_t* word_ids, const int32_t* pos_ids, int
                  "tt_embed_layernorm_bf16: bad pointer");
     return launch_layernorm(nullptr, n_rows, dim, gamma, beta, eps, y_bf16, word_ids, pos_ids, word_emb_bf16, pos_emb_bf16,
                             type_emb_bf16, TT_STREAM(stream));
+}
+
+int tt_attention_varlen_bf16(const void* qkv_bf16, int64_t n_tokens, int n_heads, int head_dim, const int32_t* cu_seqlens,
+                             int n_seq, int max_len, int max_tiles, float scale, void* out_bf16, void* stream) {
+    TT_CHECK_ARG(n_tokens >= 0 && n_tokens < (int64_t(1) << 31) && n_seq >= 0 && n_heads >= 1, "tt_attention_varlen_bf16: n_tokens=%lld n_seq=%d n_heads=%d",
+                 (long long)n_tokens, n_seq, n_heads);
+    if (head_dim != 64 || max_len > 512) {
+        set_error("tt_attention_varlen_bf16: head_dim=%d max_len=%d (this build: head_dim 64, sequences of up to 512 tokens)", head_dim, max_len);
+        return TT_ERR_UNSUPPORTED;
+    }
+    TT_CHECK_ARG(max_len >= 1 && max_tiles >= 0 && max_tiles <= 65535 * 32 && n_heads <= 65535, "tt_attention_varlen_bf16: max_len=%d max_tiles=%d", max_len, max_tiles);
+    if (n_tokens == 0 || n_seq == 0 || max_tiles == 0) return TT_OK;
+    TT_CHECK_ARG(qkv_bf16 && cu_seqlens && out_bf16 && aligned16(qkv_bf16) && aligned16(out_bf16), "tt_attention_varlen_bf16: bad pointer");
+    return launch_attention_varlen(qkv_bf16, n_tokens, n_heads, cu_seqlens, n_seq, max_len, max_tiles, scale, out_bf16, TT_STREAM(stream));
+}
+
+int tt_cls_head_f32(const void* x_bf16, const int32_t* cu_seqlens, int n_seq, int hidden, const float* w1, const float* b1,
+                    const float* w2, const float* b2, float* logits, void* stream) {
+    TT_CHECK_ARG(n_seq >= 0 && hidden >= 4 && hidden % 4 == 0 && hidden <= 8192, "tt_cls_head_f32: n_seq=%d hidden=%d", n_seq, hidden);
+    if (n_seq == 0) return TT_OK;
+    TT_CHECK_ARG(x_bf16 && cu_seqlens && w1 && b1 && w2 && b2 && logits && aligned16(w1), "tt_cls_head_f32: bad pointer");
+    return launch_cls_head(x_bf16, cu_seqlens, n_seq, hidden, w1, b1, w2, b2, logits, TT_STREAM(stream));
 }
 
 int tt_automerge_max_k(void) { return automerge_max_k(); }

@@ -1,0 +1,396 @@
+// Packed variable-length self-attention + the classification head of the cross-encoder reranker: the two pieces of the
+// stage AFTER the retrieval path that round 1 still borrowed from a library (reference:
+// SentenceTransformerRerank.postprocess_nodes, wired at /root/reference/src/tensortruth/services/model_manager.py:333-337
+// and run at services/rag_service.py:343-346 on the node list the retriever returned).
+//
+// attn_varlen_kernel: one CTA per (128-row query tile of one packed sequence, head), bidirectional (encoder) attention,
+// head_dim = 64, sequences of up to 512 tokens (XLM-RoBERTa's limit), bf16 in / bf16 out, fp32 accumulation.
+//
+//   S = Q K^T     tcgen05.mma  M = 128 (query rows) x N = 128 (keys of one kv tile) x K = 64, operands K-major SW128
+//                 straight from TMA (the packed [T, 3H] QKV matrix is its own tensor map; a tile is 128 rows x 128 B)
+//   P = exp2((S - m) c)   softmax numerators in registers: thread = query row = TMEM lane, tcgen05.ld of its 128 scores
+//   O += P V      tcgen05.mma  M = 128 x N = 64 (head_dim) x K = 128 (keys): P goes back through shared memory as a
+//                 K-major SW128 A operand (bf16); V is used AS IT LIES in memory -- [keys, 64] rows of 128 B are an
+//                 MN-major B operand (instruction descriptor bit 16), so nothing is transposed
+//
+// Two passes over the (at most four) kv tiles of the sequence instead of an online softmax: pass A computes the row
+// maxima m (S tiles are recomputed in pass B -- the tensor work is negligible here, the K tiles stay resident in
+// shared memory), pass B the numerators with the FINAL maximum, so the accumulator O in TMEM never needs a
+// correction step.  S tiles are double-buffered in TMEM (pass A / B MMAs run ahead of the softmax warps), P tiles are
+// double-buffered in shared memory (the P V MMA of tile j overlaps the softmax of tile j + 1).
+// Six warps: 0-3 softmax / epilogue, 4 TMA producer, 5 TMEM alloc + MMA issue.
+#include "tc_ptx.cuh"
+
+namespace tt {
+
+TT_DEFINE_STATUS_HOOKS(attention)
+namespace attn {
+
+using namespace tc;
+
+constexpr int HD = 64;               // head_dim
+constexpr int QT = 128;              // query rows per CTA (MMA M)
+constexpr int KT = 128;              // keys per kv tile (MMA N of S, MMA K of P V)
+constexpr int MAX_KV_TILES = 4;      // sequences up to 512 tokens
+constexpr int TILE_BYTES = QT * 128; // a [128 x 64] bf16 tile: 16 KB
+constexpr int P_BYTES = 2 * TILE_BYTES;  // a [128 x 128] bf16 P tile: two 64-column chunks
+constexpr int TMEM_COLS = 512;       // S double buffer at columns 0 / 128, O at 256..319
+constexpr int A_THREADS = 192;
+
+struct Params {
+    const int* cu_seqlens;  // [n_seq + 1] token offsets of the packed sequences
+    int n_seq;
+    int n_heads;
+    int hidden;             // n_heads * 64
+    int64_t n_tokens;
+    int n_kv_max;           // kv tiles the shared-memory layout was sized for (ceil(max_len / 128))
+    float scale_log2e;      // softmax scale * log2(e)
+    __nv_bfloat16* out;     // [T, hidden]
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy)
+        : "memory");
+}
+
+// MN-major, 128-byte-swizzled B operand: [K rows][64 MN elements = 128 B], 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr & 0x3ffffu) >> 4);  // start address
+    d |= uint64_t(1) << 16;                      // leading byte offset: one 64-element MN block only (unused)
+    d |= uint64_t(1024 >> 4) << 32;              // stride byte offset: 8 K-rows x 128 B
+    d |= uint64_t(1) << 46;                      // descriptor version (sm_100)
+    d |= uint64_t(2) << 61;                      // SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, A K-major, B K-major or MN-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_bf16(int n, bool b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | (uint32_t(n >> 3) << 17) | (uint32_t(QT >> 4) << 24);
+}
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(A_THREADS, 1)
+attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* q_s = smem;
+    unsigned char* k_s = q_s + TILE_BYTES;
+    unsigned char* v_s = k_s + size_t(p.n_kv_max) * TILE_BYTES;
+    unsigned char* p_s = v_s + size_t(p.n_kv_max) * TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * P_BYTES);
+    uint64_t* q_full = bars;                       // 1
+    uint64_t* k_full = bars + 1;                   // MAX_KV_TILES
+    uint64_t* v_full = k_full + MAX_KV_TILES;      // MAX_KV_TILES
+    uint64_t* s_full = v_full + MAX_KV_TILES;      // 2
+    uint64_t* s_empty = s_full + 2;                // 2
+    uint64_t* p_full = s_empty + 2;                // 2
+    uint64_t* p_empty = p_full + 2;                // 2
+    uint64_t* o_full = p_empty + 2;                // 1
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(o_full + 1);
+    int* work_s = reinterpret_cast<int*>(tmem_base_s + 1);  // {sequence start, sequence length, first query row of this tile}
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int head = blockIdx.y;
+
+    // ---- which (sequence, query tile) is this CTA?  warp 0 walks the sequence table 32 entries at a time
+    if (warp == 0) {
+        int tile = int(blockIdx.x), found = 0, s_beg = 0, s_len = 0, row0 = 0;
+        for (int base = 0; base < p.n_seq && !found; base += 32) {
+            const int i = base + lane;
+            int beg = 0, len = 0;
+            if (i < p.n_seq) {
+                beg = __ldg(p.cu_seqlens + i);
+                len = __ldg(p.cu_seqlens + i + 1) - beg;
+            }
+            const int nt = (len + QT - 1) / QT;
+            int inc = nt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            const int before = inc - nt;
+            const uint32_t hit = __ballot_sync(0xffffffffu, nt > 0 && tile >= before && tile < inc);
+            if (hit) {
+                const int src = __ffs(hit) - 1;
+                s_beg = __shfl_sync(0xffffffffu, beg, src);
+                s_len = __shfl_sync(0xffffffffu, len, src);
+                row0 = (tile - __shfl_sync(0xffffffffu, before, src)) * QT;
+                found = 1;
+            } else {
+                tile -= __shfl_sync(0xffffffffu, inc, 31);
+            }
+        }
+        if (lane == 0) {
+            work_s[0] = s_beg;
+            work_s[1] = found ? s_len : 0;
+            work_s[2] = row0;
+        }
+    }
+    if (threadIdx.x == 32) {
+        mbar_init(smem_u32(q_full), 1);
+        for (int j = 0; j < MAX_KV_TILES; ++j) {
+            mbar_init(smem_u32(k_full + j), 1);
+            mbar_init(smem_u32(v_full + j), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(s_full + a), 1);
+            mbar_init(smem_u32(s_empty + a), QT);
+            mbar_init(smem_u32(p_full + a), QT);
+            mbar_init(smem_u32(p_empty + a), 1);
+        }
+        mbar_init(smem_u32(o_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int s_beg = work_s[0], s_len = work_s[1], row0 = work_s[2];
+    if (s_len == 0 || s_len > MAX_KV_TILES * KT) return;  // no work for this CTA (uniform: before any TMEM allocation)
+    const int n_kv = (s_len + KT - 1) / KT;
+
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
+                     "r"(uint32_t(TMEM_COLS))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 4) {
+        // ===================================================== TMA producer: Q, then every K and V tile of the sequence
+        if (lane == 0) {
+            const int qc = head * HD, kc = p.hidden + head * HD, vc = 2 * p.hidden + head * HD;
+            mbar_expect_tx(smem_u32(q_full), TILE_BYTES);
+            tma_load_2d(smem_u32(q_s), &map_qkv, qc, s_beg + row0, smem_u32(q_full), POLICY_EVICT_FIRST);
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_expect_tx(smem_u32(k_full + j), TILE_BYTES);
+                tma_load_2d(smem_u32(k_s + size_t(j) * TILE_BYTES), &map_qkv, kc, s_beg + j * KT, smem_u32(k_full + j), POLICY_EVICT_LAST);
+            }
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_expect_tx(smem_u32(v_full + j), TILE_BYTES);
+                tma_load_2d(smem_u32(v_s + size_t(j) * TILE_BYTES), &map_qkv, vc, s_beg + j * KT, smem_u32(v_full + j), POLICY_EVICT_LAST);
+            }
+        }
+    } else if (warp == 5) {
+        // ===================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = idesc_bf16(KT, false);
+            constexpr uint32_t idesc_o = idesc_bf16(HD, true);
+            const uint32_t q_base = smem_u32(q_s);
+            auto issue_s = [&](int t, int j) {  // S tile number t (over both passes) of kv tile j -> TMEM buffer t & 1
+                const int b = t & 1;
+                mbar_wait(smem_u32(s_empty + b), (uint32_t(t >> 1) & 1u) ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t k_base = smem_u32(k_s + size_t(j) * TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_bf16(tmem_base + uint32_t(b * KT), umma_desc_sw128(q_base + k * 32), umma_desc_sw128(k_base + k * 32), idesc_s,
+                              uint32_t(k != 0));
+                umma_commit(smem_u32(s_full + b));
+            };
+            mbar_wait(smem_u32(q_full), 0);
+            // pass A: row maxima
+            for (int j = 0; j < n_kv; ++j) {
+                mbar_wait(smem_u32(k_full + j), 0);
+                issue_s(j, j);
+            }
+            // pass B: S again (one tile ahead of the softmax), O += P_j V_j
+            issue_s(n_kv, 0);
+            for (int j = 0; j < n_kv; ++j) {
+                if (j + 1 < n_kv) issue_s(n_kv + j + 1, j + 1);
+                const int pb = j & 1;
+                mbar_wait(smem_u32(v_full + j), 0);
+                mbar_wait(smem_u32(p_full + pb), uint32_t(j >> 1) & 1u);
+                tcgen05_fence_after();
+                const uint32_t p_base = smem_u32(p_s + size_t(pb) * P_BYTES);
+                const uint32_t v_base = smem_u32(v_s + size_t(j) * TILE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < KT / 16; ++kk)  // 16 keys per instruction: P chunk kk / 4, V rows 16 kk ..
+                    umma_bf16(tmem_base + 2u * KT, umma_desc_sw128(p_base + (kk >> 2) * TILE_BYTES + (kk & 3) * 32),
+                              umma_desc_mn_sw128(v_base + kk * 2048), idesc_o, uint32_t((j | kk) != 0));
+                umma_commit(smem_u32(p_empty + pb));
+            }
+            umma_commit(smem_u32(o_full));
+        }
+        __syncwarp();
+    } else {
+        // ===================================================== softmax + epilogue: thread = query row = TMEM lane
+        const int r = threadIdx.x;  // 0..127
+        const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+        float m = -INFINITY;
+        // ---- pass A
+        for (int j = 0; j < n_kv; ++j) {
+            const int b = j & 1;
+            const int valid = min(KT, s_len - j * KT);
+            mbar_wait(smem_u32(s_full + b), uint32_t(j >> 1) & 1u);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < KT; c += 32) {
+                float v[32];
+                tmem_ld_x32(lane_addr + uint32_t(b * KT + c), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c + i < valid) m = fmaxf(m, v[i]);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(s_empty + b));
+        }
+        const float mc = m * p.scale_log2e;
+        float l = 0.f;
+        // ---- pass B
+        for (int j = 0; j < n_kv; ++j) {
+            const int t = n_kv + j, b = t & 1, pb = j & 1;
+            const int valid = min(KT, s_len - j * KT);
+            mbar_wait(smem_u32(p_empty + pb), (uint32_t(j >> 1) & 1u) ^ 1u);  // the P V MMA that read this buffer has retired
+            mbar_wait(smem_u32(s_full + b), uint32_t(t >> 1) & 1u);
+            tcgen05_fence_after();
+            unsigned char* prow = p_s + size_t(pb) * P_BYTES + size_t(r) * 128;
+#pragma unroll 1
+            for (int c = 0; c < KT; c += 32) {
+                float v[32];
+                tmem_ld_x32(lane_addr + uint32_t(b * KT + c), v);
+                tmem_ld_wait();
+                uint32_t w[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float e0 = (c + i < valid) ? exp2f(fmaf(v[i], p.scale_log2e, -mc)) : 0.f;
+                    const float e1 = (c + i + 1 < valid) ? exp2f(fmaf(v[i + 1], p.scale_log2e, -mc)) : 0.f;
+                    l += e0 + e1;
+                    w[i >> 1] = pack_bf16x2(e0, e1);
+                }
+                // 32 keys = four 16-byte units of this row's 128-byte line in chunk c / 64; SW128: unit ^= row % 8
+                unsigned char* chunk = prow + size_t(c >> 6) * TILE_BYTES;
+                const int u0 = (c & 63) >> 3;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+            }
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(s_empty + b));
+            fence_proxy_async_smem();  // the P tile was written by the generic proxy, the MMA reads it through the async proxy
+            mbar_arrive(smem_u32(p_full + pb));
+        }
+        // ---- epilogue: O / l -> bf16 -> out[row, head * 64 ..]
+        mbar_wait(smem_u32(o_full), 0);
+        tcgen05_fence_after();
+        const float inv_l = 1.f / l;
+        const int qrow = row0 + r;
+        float o[HD];
+        tmem_ld_x32(lane_addr + 2u * KT, o);
+        tmem_ld_x32(lane_addr + 2u * KT + 32u, o + 32);
+        tmem_ld_wait();
+        if (qrow < s_len) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(s_beg) + qrow) * p.hidden + head * HD);
+#pragma unroll
+            for (int u = 0; u < HD / 8; ++u)
+                dst[u] = make_uint4(pack_bf16x2(o[8 * u] * inv_l, o[8 * u + 1] * inv_l), pack_bf16x2(o[8 * u + 2] * inv_l, o[8 * u + 3] * inv_l),
+                                    pack_bf16x2(o[8 * u + 4] * inv_l, o[8 * u + 5] * inv_l), pack_bf16x2(o[8 * u + 6] * inv_l, o[8 * u + 7] * inv_l));
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS)) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ classification head on the <s> token of every pair
+// logit[i] = w2 . tanh(W1 x[first[i]] + b1) + b2   (RobertaClassificationHead, one output unit), fp32 weights.
+// One block per pair; thread t owns hidden units t, t + 256, ...
+__global__ void __launch_bounds__(256) cls_head_kernel(const __nv_bfloat16* __restrict__ x, const int* __restrict__ cu_seqlens,
+                                                       int hidden, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2,
+                                                       float* __restrict__ logits) {
+    extern __shared__ float xs[];  // [hidden]
+    __shared__ float red[8];
+    const int i = blockIdx.x;
+    const __nv_bfloat16* row = x + size_t(cu_seqlens[i]) * hidden;
+    for (int d = threadIdx.x; d < hidden; d += blockDim.x) xs[d] = __bfloat162float(row[d]);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.f;
+    for (int u = warp; u < hidden; u += 8) {  // one warp per hidden unit: coalesced reads of W1's row u
+        const float* wr = w1 + size_t(u) * hidden;
+        float s = 0.f;
+        for (int d = lane * 4; d < hidden; d += 128) {
+            const float4 wv = *reinterpret_cast<const float4*>(wr + d);
+            s = fmaf(wv.x, xs[d], s);
+            s = fmaf(wv.y, xs[d + 1], s);
+            s = fmaf(wv.z, xs[d + 2], s);
+            s = fmaf(wv.w, xs[d + 3], s);
+        }
+        s = warp_sum_f32(s);
+        if (lane == 0) acc = fmaf(w2[u], tanhf(s + b1[u]), acc);
+    }
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = b2[0];
+        for (int w = 0; w < 8; ++w) t += red[w];
+        logits[i] = t;
+    }
+}
+
+}  // namespace attn
+
+int launch_attention_varlen(const void* qkv, int64_t n_tokens, int n_heads, const int* cu_seqlens, int n_seq, int max_len,
+                            int max_tiles, float scale, void* out, cudaStream_t st) {
+    using namespace attn;
+    const int hidden = n_heads * HD;
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return TT_ERR_CUDA;
+    }
+    CUtensorMap map;
+    cuuint64_t dims[2] = {cuuint64_t(3 * hidden), cuuint64_t(n_tokens)};
+    cuuint64_t strides[1] = {cuuint64_t(3 * hidden) * 2};
+    cuuint32_t box[2] = {cuuint32_t(HD), cuuint32_t(QT)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(qkv), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for the packed QKV matrix (%lld tokens)", int(r), (long long)n_tokens);
+        return TT_ERR_CUDA;
+    }
+    Params p;
+    p.cu_seqlens = cu_seqlens;
+    p.n_seq = n_seq;
+    p.n_heads = n_heads;
+    p.hidden = hidden;
+    p.n_tokens = n_tokens;
+    p.n_kv_max = (max_len + KT - 1) / KT;
+    p.scale_log2e = scale * 1.4426950408889634f;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    const size_t smem = 1024 + TILE_BYTES + size_t(p.n_kv_max) * 2 * TILE_BYTES + 2 * P_BYTES + 256;
+    TT_CUDA_OK(cudaFuncSetAttribute(attn_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT)));
+    attn_varlen_kernel<<<dim3(max_tiles, n_heads), A_THREADS, smem, st>>>(map, p);
+    TT_LAUNCH_OK("attn_varlen_kernel");
+    return TT_OK;
+}
+
+int launch_cls_head(const void* x, const int* cu_seqlens, int n_seq, int hidden, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* logits, cudaStream_t st) {
+    attn::cls_head_kernel<<<n_seq, 256, size_t(hidden) * sizeof(float), st>>>(reinterpret_cast<const __nv_bfloat16*>(x), cu_seqlens, hidden,
+                                                                               w1, b1, w2, b2, logits);
+    TT_LAUNCH_OK("cls_head_kernel");
+    return TT_OK;
+}
+
+}  // namespace tt

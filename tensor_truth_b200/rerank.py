@@ -14,10 +14,12 @@ and cut to ``top_n``.
 * every dense layer: ``tt_linear_bf16`` -- tcgen05 GEMM with bias / exact GELU / residual add fused in the epilogue
   (QKV as one [3H, H] GEMM, attention output + residual, FFN up + GELU, FFN down + residual);
 * LayerNorms: ``tt_layernorm_bf16``;
-* attention itself is a LIBRARY call (PyTorch's packed ``varlen_attn``; ``scaled_dot_product_attention`` on padded pairs
-  when that is missing) -- not part of this package's kernels;
-* the classification head (dense + tanh + 1-unit projection on the <s> token) is a [n_pairs, hidden] problem and runs
-  in torch fp32.
+* attention: ``tt_attention_varlen_bf16`` -- this package's packed variable-length kernel (one CTA per 128-row query
+  tile and head; S = Q K^T and O += P V on tcgen05 with the accumulators in TMEM, softmax in registers; csrc/attention.cu);
+* the classification head (dense + tanh + 1-unit projection on the <s> token): ``tt_cls_head_f32``.
+
+No library kernel is left on the forward pass.  (``TT_RERANK_LIBRARY_ATTENTION=1`` routes attention through PyTorch's
+``varlen_attn`` instead -- an A/B switch for scripts/rerank_bench.py, not a fallback: unsupported shapes raise.)
 
 Weights come from a Hugging Face ``XLMRobertaForSequenceClassification`` state dict (``CrossEncoderWeights``); the
 tokenizer is injected (``tokenize(pairs, max_length) -> List[List[int]]``: in a deployment the model's own
@@ -45,10 +47,13 @@ GRAPH_MAX_TOKENS = 4096    # calls with more packed tokens are GPU-bound: no gra
 GRAPH_TOKEN_STEP = 256     # token-count granularity of the graph buckets
 GRAPH_MAX_BUCKETS = 12     # captured graphs kept per encoder (each holds its activations: ~20 KB per token)
 
-try:  # PyTorch >= 2.10: attention over packed sequences (cu_seqlens), no padding
-    from torch.nn.attention.varlen import varlen_attn as _varlen_attn
-except Exception:  # pragma: no cover
-    _varlen_attn = None
+_LIBRARY_ATTENTION = bool(os.environ.get("TT_RERANK_LIBRARY_ATTENTION"))  # A/B switch for the bench script only
+_varlen_attn = None
+if _LIBRARY_ATTENTION:
+    try:  # PyTorch >= 2.10: attention over packed sequences (cu_seqlens), no padding
+        from torch.nn.attention.varlen import varlen_attn as _varlen_attn
+    except Exception:  # pragma: no cover
+        _varlen_attn = None
 
 
 @dataclass
@@ -149,11 +154,16 @@ class B200CrossEncoder:
                                          self._stream()))
         return y
 
-    # ---- attention: a LIBRARY call.  Packed (variable-length) attention when the installed PyTorch has it, else
-    #      scaled_dot_product_attention on the pairs padded to the longest one of the call.
+    # ---- attention: tt_attention_varlen_bf16 over the packed sequences (head_dim 64, pairs of up to 512 tokens)
     def _attention(self, qkv: torch.Tensor, cu: torch.Tensor, dest: torch.Tensor, n: int, s_max: int,
                    key_mask: torch.Tensor) -> torch.Tensor:
         h, nh = self.w.hidden, self.w.n_heads
+        if not _LIBRARY_ATTENTION:
+            total = int(qkv.shape[0])
+            out = torch.empty((total, h), dtype=torch.bfloat16, device=qkv.device)
+            check(self.lib.tt_attention_varlen_bf16(ptr(qkv), total, nh, h // nh, ptr(cu), n, int(s_max), total // 128 + n,
+                                                    float((h // nh) ** -0.5), ptr(out), self._stream()))
+            return out
         if _varlen_attn is not None:
             q, k, v = qkv.view(-1, 3, nh, h // nh).unbind(1)
             return _varlen_attn(q, k, v, cu, cu, s_max, s_max).reshape(-1, h)
@@ -168,9 +178,9 @@ class B200CrossEncoder:
         w = self.w
         dev = w.device
         ids_d, pos_d, cu_d = packed[:total], packed[total:2 * total], packed[2 * total:2 * total + n + 1]
-        first_d = cu_d[:-1].long()
         dest_d = key_mask = None
-        if _varlen_attn is None:
+        if _LIBRARY_ATTENTION and _varlen_attn is None:
+            first_d = cu_d[:-1].long()
             lens_d = (cu_d[1:] - cu_d[:-1]).long()
             within = torch.arange(total, device=dev) - torch.repeat_interleave(first_d, lens_d)
             dest_d = within + torch.repeat_interleave(torch.arange(n, device=dev) * s_max, lens_d)
@@ -184,9 +194,10 @@ class B200CrossEncoder:
             x = self._layernorm(self._linear(ctx, L.w_o, L.b_o, residual=x), L.ln1_g, L.ln1_b)
             hdn = self._linear(x, L.w_ff1, L.b_ff1, act=ACT_GELU)
             x = self._layernorm(self._linear(hdn, L.w_ff2, L.b_ff2, residual=x), L.ln2_g, L.ln2_b)
-        cls = x[first_d].float()                                  # the <s> token of every pair
-        hid = torch.tanh(cls @ w.head_w1.T + w.head_b1)
-        return (hid @ w.head_w2.T + w.head_b2).squeeze(-1)
+        logits = torch.empty((n,), dtype=torch.float32, device=dev)  # head on the <s> token of every pair
+        check(self.lib.tt_cls_head_f32(ptr(x), ptr(cu_d), n, w.hidden, ptr(w.head_w1), ptr(w.head_b1), ptr(w.head_w2),
+                                       ptr(w.head_b2), ptr(logits), self._stream()))
+        return logits
 
     @staticmethod
     def _pack(hv: np.ndarray, token_lists, lens: np.ndarray, total: int, pad_id: int) -> None:
@@ -206,7 +217,7 @@ class B200CrossEncoder:
         padded to a bucket (tokens to a multiple of GRAPH_TOKEN_STEP, pairs to a power of two) with dummy one-token-or-
         longer sequences whose outputs are ignored; a bucket is captured on its second use, at most GRAPH_MAX_BUCKETS
         are kept.  Returns None when the call is too large (GPU-bound: eager is as fast) or graphs are disabled."""
-        if _varlen_attn is None or total > GRAPH_MAX_TOKENS or os.environ.get("TT_NO_GRAPH"):
+        if (_LIBRARY_ATTENTION and _varlen_attn is None) or total > GRAPH_MAX_TOKENS or os.environ.get("TT_NO_GRAPH"):
             return None
         n_b = 2
         while n_b < n + 1:

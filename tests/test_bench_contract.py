@@ -61,7 +61,8 @@ def test_gpu_arm_prints_one_json_line_with_the_contract_keys():
 
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
-    p = _run("--rows", "300000", "--steps", "20", "--warmup", "3", "--wide-batch", "512", "--wide-k", "10", "--cpu-sample-rows", "65536")
+    p = _run("--rows", "300000", "--steps", "20", "--warmup", "3", "--wide-batch", "512", "--wide-k", "10", "--cpu-sample-rows", "65536",
+             "--c3-rows-per-gpu", "200000", "--c4-rows-per-gpu", "100000", "--c5-rows", "300000")
     assert p.returncode == 0, p.stderr[-3000:]
     lines = [l for l in p.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, lines
@@ -77,11 +78,21 @@ def test_gpu_arm_prints_one_json_line_with_the_contract_keys():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 and e["d2h_bytes_per_step"] > 0
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
-    assert d["gpu_launches"] == 20 * 5 and "workload" in d["config"] and "l2" in d["config"]
+    # prepare, scan, re-score + select + auto-merge: three kernels per step on one GPU
+    assert d["gpu_launches"] == 20 * 3 and d["kernels_per_step"] == 3 and "workload" in d["config"] and "l2" in d["config"]
     assert d["clocks"]["sm_max_mhz"] and isinstance(d["clocks"]["reasons"], list)
     assert d["parity_vs_gpu_exact_scan"] is True and d["certificate_failures"] == 0
     w = d["wide"]
     assert w["roofline"]["bound"] == "tensor" and w["gemm_path"] and w["parity_vs_gpu_exact_scan_local_shard"] is True
+    # the other BASELINE configs ride in the same line, each with its own roofline object
+    assert d["c3"]["roofline"]["bound"] == "hbm" and d["c3"]["scaling"] == "weak" and d["c3"]["rows_per_gpu"] == 200000
+    assert d["c4"]["roofline"]["bound"] == "tensor" and d["c4"]["rows_per_gpu"] == 100000
+    assert d["c5"]["k"] == 200 and d["c5"]["roofline"]["bound"] == "hbm" and d["c5"]["certificate_failures"] == 0
+    assert d["fp32_store"]["eps"] > 4e-3 and d["fp32_store"]["certificate_failures"] == 0
+    h = d["hard_queries"]
+    assert h["deep_rung"]["matches_exact_scan"] and h["exact_fallback"]["matches_exact_scan"]
+    assert h["deep_rung"]["deep_rescans_kprime128"] > 0 and h["exact_fallback"]["exact_fp64_fallbacks"] > 0
+    assert d["parity_vs_cpu_oracle"]["ok"] is True and d["parity_vs_cpu_oracle"]["queries_checked"] == 64
 
 
 test_gpu_arm_prints_one_json_line_with_the_contract_keys = __import__("pytest").mark.gpu(

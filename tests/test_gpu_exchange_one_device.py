@@ -94,7 +94,13 @@ def test_push_merge_automerge_matches_oracle(two_shards, b, k):
 
 
 def test_second_round_push_and_barrier(two_shards):
-    """``tt_exchange_push`` of a finished record (what follows a host-side repair) + ``tt_peer_barrier``."""
+    """``tt_exchange_push`` of a finished record (what follows a host-side repair) + ``tt_peer_barrier``.
+
+    Two simulated ranks share ONE GPU here, and two streams of one process may share a hardware queue: a kernel must
+    never wait for one that was enqueued AFTER it (on real multi-GPU runs every rank has its own device, so the mutual
+    wait of a barrier is fine there -- bench.py's timed loops start behind one).  So the barrier is exercised one
+    rank at a time, the other rank's arrival being its real kernel run earlier (or, for the very first one, the flag
+    store that kernel would have made)."""
     from oracle import cport
     from tensor_truth_b200 import _lib
     from tensor_truth_b200.sharded import PeerBuffers
@@ -109,6 +115,12 @@ def test_second_round_push_and_barrier(two_shards):
     qd = torch.from_numpy(q[:b]).to(dev)
     outs = [(torch.empty((b, k), dtype=torch.float32, device=dev), torch.empty((b, k), dtype=torch.int64, device=dev))
             for _ in range(2)]
+
+    def barrier_flags(r):  # int32 view of rank r's barrier flag array
+        pb = pbs[r]
+        off = pb.flags_off + pb.lanes * pb.SLOTS * pb.flag_stride * 4
+        return pb.buf[off: off + 4 * pb.world].view(torch.int32)
+
     for rnd in range(3):
         for r in (0, 1):
             ex = shards[r].search_exact(qd, k)  # the "repaired" local record
@@ -116,10 +128,20 @@ def test_second_round_push_and_barrier(two_shards):
             s_keys.copy_(ex.keys)
             s_ids.copy_(ex.ids)
             s_margins.fill_(float("inf"))
+        # barrier number rnd + 1: rank 1's arrival is simulated by the store its kernel makes into rank 0's flags ...
+        barrier_flags(0)[1] = rnd + 1
         torch.cuda.synchronize()
+        _lib.check(L.tt_peer_barrier(C.byref(pbs[0].desc(pbs[0].lanes)), shards[0]._stream()))
+        torch.cuda.synchronize()
+        _lib.check_status(0)
+        assert barrier_flags(0).tolist() == [rnd + 1, rnd + 1] and int(barrier_flags(1)[0]) == rnd + 1  # rank 0 told everybody
+        # ... and rank 1's real barrier kernel now finds rank 0's flag (and its own) in place
+        _lib.check(L.tt_peer_barrier(C.byref(pbs[1].desc(pbs[1].lanes)), shards[1]._stream()))
+        torch.cuda.synchronize()
+        _lib.check_status(0)
+        assert barrier_flags(1).tolist() == [rnd + 1, rnd + 1]
         for r in (1, 0):
             with torch.cuda.stream(streams[r]):
-                _lib.check(L.tt_peer_barrier(C.byref(pbs[r].desc(pbs[r].lanes)), shards[r]._stream()))
                 _lib.check(L.tt_exchange_push(pbs[r].send_record()[0].data_ptr(), pbs[r].rec_bytes // 4 * 4,
                                               C.byref(pbs[r].desc(0)), shards[r]._stream()))
         for r in (0, 1):
@@ -130,6 +152,7 @@ def test_second_round_push_and_barrier(two_shards):
         for r in (0, 1):
             assert (outs[r][1].cpu().numpy() == ids_o).all() and (outs[r][0].cpu().numpy() == sc_o).all(), (rnd, r)
     assert int(pbs[0].epochs[1]) == 3 and int(pbs[1].epochs[1]) == 3  # three barriers passed on both ranks
+    assert int(pbs[0].epochs[0]) == 3 and int(pbs[1].epochs[0]) == 3  # three pushes on lane 0
 
 
 def test_missing_peer_is_an_error_not_a_dead_context(two_shards):
