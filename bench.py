@@ -522,10 +522,10 @@ def oracle_parity_c1(ctx, kprime, variant):
     bits_local = w.corpus_bf16.view(torch.int16)
     if ctx.world > 1:
         parts = [torch.empty((shard_rows(n, ctx.world, r), DIM), dtype=torch.int16, device=dev) for r in range(ctx.world)]
-        for r in range(ctx.world):  # broadcast each shard in turn (shards may differ in size)
+        for r in range(ctx.world):  # broadcast each shard in turn (shards may differ in size); NCCL has no int16: send the bytes
             if r == ctx.rank:
                 parts[r].copy_(bits_local)
-            ctx.dist.broadcast(parts[r], src=r)
+            ctx.dist.broadcast(parts[r].view(torch.uint8), src=r)
         bits_all = torch.cat(parts, dim=0)
     else:
         bits_all = bits_local

@@ -64,7 +64,7 @@ TT_STATUS_TU(linear)
 TT_STATUS_TU(attention)
 #undef TT_STATUS_TU
 int launch_attention_varlen(const void* qkv, int64_t n_tokens, int n_heads, const int* cu_seqlens, int n_seq, int max_len,
-                            int max_tiles, float scale, void* out, cudaStream_t st);
+                            int max_tiles, float scale, void* out, int n_sms, cudaStream_t st);
 int launch_cls_head(const void* x, const int* cu_seqlens, int n_seq, int hidden, const float* w1, const float* b1, const float* w2,
                     const float* b2, float* logits, cudaStream_t st);
 int launch_automerge(const int64_t* ids, const float* scores, int n_q, int k, const int32_t* parent_of,
@@ -503,7 +503,13 @@ int tt_attention_varlen_bf16(const void* qkv_bf16, int64_t n_tokens, int n_heads
     TT_CHECK_ARG(max_len >= 1 && max_tiles >= 0 && max_tiles <= 65535 * 32 && n_heads <= 65535, "tt_attention_varlen_bf16: max_len=%d max_tiles=%d", max_len, max_tiles);
     if (n_tokens == 0 || n_seq == 0 || max_tiles == 0) return TT_OK;
     TT_CHECK_ARG(qkv_bf16 && cu_seqlens && out_bf16 && aligned16(qkv_bf16) && aligned16(out_bf16), "tt_attention_varlen_bf16: bad pointer");
-    return launch_attention_varlen(qkv_bf16, n_tokens, n_heads, cu_seqlens, n_seq, max_len, max_tiles, scale, out_bf16, TT_STREAM(stream));
+    const int n_sms = sm_count(current_device());
+    if (n_sms <= 0) {
+        set_error("tt_attention_varlen_bf16: no CUDA device");
+        return TT_ERR_CUDA;
+    }
+    return launch_attention_varlen(qkv_bf16, n_tokens, n_heads, cu_seqlens, n_seq, max_len, max_tiles, scale, out_bf16, n_sms,
+                                   TT_STREAM(stream));
 }
 
 int tt_cls_head_f32(const void* x_bf16, const int32_t* cu_seqlens, int n_seq, int hidden, const float* w1, const float* b1,

@@ -3,21 +3,22 @@
 // SentenceTransformerRerank.postprocess_nodes, wired at /root/reference/src/tensortruth/services/model_manager.py:333-337
 // and run at services/rag_service.py:343-346 on the node list the retriever returned).
 //
-// attn_varlen_kernel: one CTA per (128-row query tile of one packed sequence, head), bidirectional (encoder) attention,
-// head_dim = 64, sequences of up to 512 tokens (XLM-RoBERTa's limit), bf16 in / bf16 out, fp32 accumulation.
+// attn_varlen_kernel: bidirectional (encoder) attention, head_dim = 64, sequences of up to 512 tokens (XLM-RoBERTa's
+// limit), bf16 in / bf16 out, fp32 accumulation.  A work item is (128-row query tile of one packed sequence, head):
 //
-//   S = Q K^T     tcgen05.mma  M = 128 (query rows) x N = 128 (keys of one kv tile) x K = 64, operands K-major SW128
-//                 straight from TMA (the packed [T, 3H] QKV matrix is its own tensor map; a tile is 128 rows x 128 B)
-//   P = exp2((S - m) c)   softmax numerators in registers: thread = query row = TMEM lane, tcgen05.ld of its 128 scores
-//   O += P V      tcgen05.mma  M = 128 x N = 64 (head_dim) x K = 128 (keys): P goes back through shared memory as a
-//                 K-major SW128 A operand (bf16); V is used AS IT LIES in memory -- [keys, 64] rows of 128 B are an
-//                 MN-major B operand (instruction descriptor bit 16), so nothing is transposed
+//   S_j = Q K_j^T   tcgen05.mma  M = 128 (query rows) x N = 128 (keys of kv tile j) x K = 64, operands K-major SW128
+//                   straight from TMA (the packed [T, 3H] QKV matrix is its own tensor map; a tile is 128 rows x 128 B).
+//                   All (at most four) S tiles of the item stay resident in TMEM: 4 x 128 = 512 columns.
+//   P_j = exp2((S_j - m) c)   softmax numerators in registers: thread = query row = TMEM lane; pass A reads the S
+//                   tiles for the row maximum m, pass B reads them again for the numerators with the FINAL maximum --
+//                   so the accumulator O never needs a correction step and nothing is recomputed.
+//   O += P_j V_j    tcgen05.mma  M = 128 x N = 64 (head_dim) x K = 128 (keys): P_j goes back through shared memory as
+//                   a K-major SW128 A operand (bf16, double-buffered); V_j is used AS IT LIES in memory -- [keys, 64]
+//                   rows of 128 B are an MN-major B operand (instruction descriptor bit 16), so nothing is transposed.
+//                   O lives in the TMEM columns of S_0, which pass B has finished with before the first P V is issued.
 //
-// Two passes over the (at most four) kv tiles of the sequence instead of an online softmax: pass A computes the row
-// maxima m (S tiles are recomputed in pass B -- the tensor work is negligible here, the K tiles stay resident in
-// shared memory), pass B the numerators with the FINAL maximum, so the accumulator O in TMEM never needs a
-// correction step.  S tiles are double-buffered in TMEM (pass A / B MMAs run ahead of the softmax warps), P tiles are
-// double-buffered in shared memory (the P V MMA of tile j overlaps the softmax of tile j + 1).
+// Persistent CTAs (one per SM) walk the items; K / V tiles stream through a 7-stage TMA ring and Q through a 2-stage
+// one, so the loads of the next item are in flight while the softmax warps -- the bottleneck -- work on the current one.
 // Six warps: 0-3 softmax / epilogue, 4 TMA producer, 5 TMEM alloc + MMA issue.
 #include "tc_ptx.cuh"
 
@@ -29,21 +30,22 @@ namespace attn {
 using namespace tc;
 
 constexpr int HD = 64;               // head_dim
-constexpr int QT = 128;              // query rows per CTA (MMA M)
+constexpr int QT = 128;              // query rows per item (MMA M)
 constexpr int KT = 128;              // keys per kv tile (MMA N of S, MMA K of P V)
 constexpr int MAX_KV_TILES = 4;      // sequences up to 512 tokens
 constexpr int TILE_BYTES = QT * 128; // a [128 x 64] bf16 tile: 16 KB
 constexpr int P_BYTES = 2 * TILE_BYTES;  // a [128 x 128] bf16 P tile: two 64-column chunks
-constexpr int TMEM_COLS = 512;       // S double buffer at columns 0 / 128, O at 256..319
+constexpr int KV_STAGES = 7;
+constexpr int Q_STAGES = 2;
+constexpr int TMEM_COLS = 512;       // S_j at columns 128 j; O in columns 0..63 (over S_0)
 constexpr int A_THREADS = 192;
+constexpr int MAX_TILES = 1024;      // query tiles per launch (the tile table in shared memory)
 
 struct Params {
     const int* cu_seqlens;  // [n_seq + 1] token offsets of the packed sequences
     int n_seq;
     int n_heads;
     int hidden;             // n_heads * 64
-    int64_t n_tokens;
-    int n_kv_max;           // kv tiles the shared-memory layout was sized for (ceil(max_len / 128))
     float scale_log2e;      // softmax scale * log2(e)
     __nv_bfloat16* out;     // [T, hidden]
 };
@@ -83,34 +85,35 @@ __global__ void __launch_bounds__(A_THREADS, 1)
 attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) {
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-    unsigned char* q_s = smem;
-    unsigned char* k_s = q_s + TILE_BYTES;
-    unsigned char* v_s = k_s + size_t(p.n_kv_max) * TILE_BYTES;
-    unsigned char* p_s = v_s + size_t(p.n_kv_max) * TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * P_BYTES);
-    uint64_t* q_full = bars;                       // 1
-    uint64_t* k_full = bars + 1;                   // MAX_KV_TILES
-    uint64_t* v_full = k_full + MAX_KV_TILES;      // MAX_KV_TILES
-    uint64_t* s_full = v_full + MAX_KV_TILES;      // 2
-    uint64_t* s_empty = s_full + 2;                // 2
-    uint64_t* p_full = s_empty + 2;                // 2
+    unsigned char* q_s = smem;                                   // Q_STAGES x 16 KB
+    unsigned char* kv_s = q_s + Q_STAGES * TILE_BYTES;           // KV_STAGES x 16 KB
+    unsigned char* p_s = kv_s + KV_STAGES * TILE_BYTES;          // 2 x 32 KB
+    int2* tiles = reinterpret_cast<int2*>(p_s + 2 * P_BYTES);    // MAX_TILES x {sequence start, length | tile index << 16}
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + MAX_TILES);
+    uint64_t* kv_full = bars;                      // KV_STAGES
+    uint64_t* kv_empty = kv_full + KV_STAGES;      // KV_STAGES
+    uint64_t* q_full = kv_empty + KV_STAGES;       // Q_STAGES
+    uint64_t* q_empty = q_full + Q_STAGES;         // Q_STAGES
+    uint64_t* s_full = q_empty + Q_STAGES;         // MAX_KV_TILES
+    uint64_t* p_full = s_full + MAX_KV_TILES;      // 2
     uint64_t* p_empty = p_full + 2;                // 2
     uint64_t* o_full = p_empty + 2;                // 1
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(o_full + 1);
-    int* work_s = reinterpret_cast<int*>(tmem_base_s + 1);  // {sequence start, sequence length, first query row of this tile}
+    uint64_t* tmem_free = o_full + 1;              // 1
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_free + 1);
+    int* n_tiles_s = reinterpret_cast<int*>(tmem_base_s + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int head = blockIdx.y;
 
-    // ---- which (sequence, query tile) is this CTA?  warp 0 walks the sequence table 32 entries at a time
+    // ---- the tile table: query tile -> (sequence start, sequence length, tile index within the sequence); warp 0
     if (warp == 0) {
-        int tile = int(blockIdx.x), found = 0, s_beg = 0, s_len = 0, row0 = 0;
-        for (int base = 0; base < p.n_seq && !found; base += 32) {
+        int total = 0;
+        for (int base = 0; base < p.n_seq; base += 32) {
             const int i = base + lane;
             int beg = 0, len = 0;
             if (i < p.n_seq) {
                 beg = __ldg(p.cu_seqlens + i);
                 len = __ldg(p.cu_seqlens + i + 1) - beg;
+                if (len > MAX_KV_TILES * KT) len = 0;  // refused by the host; never reached
             }
             const int nt = (len + QT - 1) / QT;
             int inc = nt;
@@ -119,44 +122,31 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
                 const int o = __shfl_up_sync(0xffffffffu, inc, d);
                 if (lane >= d) inc += o;
             }
-            const int before = inc - nt;
-            const uint32_t hit = __ballot_sync(0xffffffffu, nt > 0 && tile >= before && tile < inc);
-            if (hit) {
-                const int src = __ffs(hit) - 1;
-                s_beg = __shfl_sync(0xffffffffu, beg, src);
-                s_len = __shfl_sync(0xffffffffu, len, src);
-                row0 = (tile - __shfl_sync(0xffffffffu, before, src)) * QT;
-                found = 1;
-            } else {
-                tile -= __shfl_sync(0xffffffffu, inc, 31);
-            }
+            const int first = total + inc - nt;
+            for (int t = 0; t < nt; ++t)
+                if (first + t < MAX_TILES) tiles[first + t] = make_int2(beg, len | (t << 16));
+            total += __shfl_sync(0xffffffffu, inc, 31);
         }
-        if (lane == 0) {
-            work_s[0] = s_beg;
-            work_s[1] = found ? s_len : 0;
-            work_s[2] = row0;
-        }
+        if (lane == 0) *n_tiles_s = min(total, MAX_TILES);
     }
     if (threadIdx.x == 32) {
-        mbar_init(smem_u32(q_full), 1);
-        for (int j = 0; j < MAX_KV_TILES; ++j) {
-            mbar_init(smem_u32(k_full + j), 1);
-            mbar_init(smem_u32(v_full + j), 1);
+        for (int s = 0; s < KV_STAGES; ++s) {
+            mbar_init(smem_u32(kv_full + s), 1);
+            mbar_init(smem_u32(kv_empty + s), 1);
         }
+        for (int s = 0; s < Q_STAGES; ++s) {
+            mbar_init(smem_u32(q_full + s), 1);
+            mbar_init(smem_u32(q_empty + s), 1);
+        }
+        for (int j = 0; j < MAX_KV_TILES; ++j) mbar_init(smem_u32(s_full + j), 1);
         for (int a = 0; a < 2; ++a) {
-            mbar_init(smem_u32(s_full + a), 1);
-            mbar_init(smem_u32(s_empty + a), QT);
             mbar_init(smem_u32(p_full + a), QT);
             mbar_init(smem_u32(p_empty + a), 1);
         }
         mbar_init(smem_u32(o_full), 1);
+        mbar_init(smem_u32(tmem_free), QT);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
-    const int s_beg = work_s[0], s_len = work_s[1], row0 = work_s[2];
-    if (s_len == 0 || s_len > MAX_KV_TILES * KT) return;  // no work for this CTA (uniform: before any TMEM allocation)
-    const int n_kv = (s_len + KT - 1) / KT;
-
     if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
                      "r"(uint32_t(TMEM_COLS))
@@ -167,20 +157,32 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_base_s;
+    const int n_items = *n_tiles_s * p.n_heads;  // item = tile * n_heads + head
 
     if (warp == 4) {
-        // ===================================================== TMA producer: Q, then every K and V tile of the sequence
+        // ===================================================== TMA producer: Q, then the K tiles, then the V tiles of every item
         if (lane == 0) {
-            const int qc = head * HD, kc = p.hidden + head * HD, vc = 2 * p.hidden + head * HD;
-            mbar_expect_tx(smem_u32(q_full), TILE_BYTES);
-            tma_load_2d(smem_u32(q_s), &map_qkv, qc, s_beg + row0, smem_u32(q_full), POLICY_EVICT_FIRST);
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_expect_tx(smem_u32(k_full + j), TILE_BYTES);
-                tma_load_2d(smem_u32(k_s + size_t(j) * TILE_BYTES), &map_qkv, kc, s_beg + j * KT, smem_u32(k_full + j), POLICY_EVICT_LAST);
-            }
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_expect_tx(smem_u32(v_full + j), TILE_BYTES);
-                tma_load_2d(smem_u32(v_s + size_t(j) * TILE_BYTES), &map_qkv, vc, s_beg + j * KT, smem_u32(v_full + j), POLICY_EVICT_LAST);
+            int st = 0;
+            uint32_t ph = 0;
+            int li = 0;  // items this CTA has started
+            for (int it = int(blockIdx.x); it < n_items; it += int(gridDim.x), ++li) {
+                const int2 tl = tiles[it / p.n_heads];
+                const int head = it % p.n_heads;
+                const int s_beg = tl.x, s_len = tl.y & 0xffff, row0 = (tl.y >> 16) * QT;
+                const int n_kv = (s_len + KT - 1) / KT;
+                const int qc = head * HD, kc = p.hidden + head * HD, vc = 2 * p.hidden + head * HD;
+                const int qs = li & 1;
+                mbar_wait(smem_u32(q_empty + qs), (uint32_t(li >> 1) & 1u) ^ 1u);
+                mbar_expect_tx(smem_u32(q_full + qs), TILE_BYTES);
+                tma_load_2d(smem_u32(q_s + size_t(qs) * TILE_BYTES), &map_qkv, qc, s_beg + row0, smem_u32(q_full + qs), POLICY_EVICT_FIRST);
+                for (int j = 0; j < 2 * n_kv; ++j) {  // K_0 .. K_{n-1}, V_0 .. V_{n-1}
+                    const bool is_v = j >= n_kv;
+                    mbar_wait(smem_u32(kv_empty + st), ph ^ 1u);
+                    mbar_expect_tx(smem_u32(kv_full + st), TILE_BYTES);
+                    tma_load_2d(smem_u32(kv_s + size_t(st) * TILE_BYTES), &map_qkv, is_v ? vc : kc, s_beg + (is_v ? j - n_kv : j) * KT,
+                                smem_u32(kv_full + st), POLICY_EVICT_LAST);
+                    if (++st == KV_STAGES) { st = 0; ph ^= 1u; }
+                }
             }
         }
     } else if (warp == 5) {
@@ -188,116 +190,132 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
         if (lane == 0) {
             constexpr uint32_t idesc_s = idesc_bf16(KT, false);
             constexpr uint32_t idesc_o = idesc_bf16(HD, true);
-            const uint32_t q_base = smem_u32(q_s);
-            auto issue_s = [&](int t, int j) {  // S tile number t (over both passes) of kv tile j -> TMEM buffer t & 1
-                const int b = t & 1;
-                mbar_wait(smem_u32(s_empty + b), (uint32_t(t >> 1) & 1u) ^ 1u);
+            int st = 0;
+            uint32_t ph = 0;
+            int li = 0;
+            uint32_t pt = 0;  // P tiles consumed so far (over all items)
+            for (int it = int(blockIdx.x); it < n_items; it += int(gridDim.x), ++li) {
+                const int2 tl = tiles[it / p.n_heads];
+                const int n_kv = ((tl.y & 0xffff) + KT - 1) / KT;
+                const int qs = li & 1;
+                mbar_wait(smem_u32(tmem_free), (uint32_t(li) & 1u) ^ 1u);  // the previous item's O and S tiles have been read
+                mbar_wait(smem_u32(q_full + qs), uint32_t(li >> 1) & 1u);
                 tcgen05_fence_after();
-                const uint32_t k_base = smem_u32(k_s + size_t(j) * TILE_BYTES);
+                const uint32_t q_base = smem_u32(q_s + size_t(qs) * TILE_BYTES);
+                for (int j = 0; j < n_kv; ++j) {
+                    mbar_wait(smem_u32(kv_full + st), ph);
+                    tcgen05_fence_after();
+                    const uint32_t k_base = smem_u32(kv_s + size_t(st) * TILE_BYTES);
 #pragma unroll
-                for (int k = 0; k < HD / 16; ++k)
-                    umma_bf16(tmem_base + uint32_t(b * KT), umma_desc_sw128(q_base + k * 32), umma_desc_sw128(k_base + k * 32), idesc_s,
-                              uint32_t(k != 0));
-                umma_commit(smem_u32(s_full + b));
-            };
-            mbar_wait(smem_u32(q_full), 0);
-            // pass A: row maxima
-            for (int j = 0; j < n_kv; ++j) {
-                mbar_wait(smem_u32(k_full + j), 0);
-                issue_s(j, j);
-            }
-            // pass B: S again (one tile ahead of the softmax), O += P_j V_j
-            issue_s(n_kv, 0);
-            for (int j = 0; j < n_kv; ++j) {
-                if (j + 1 < n_kv) issue_s(n_kv + j + 1, j + 1);
-                const int pb = j & 1;
-                mbar_wait(smem_u32(v_full + j), 0);
-                mbar_wait(smem_u32(p_full + pb), uint32_t(j >> 1) & 1u);
-                tcgen05_fence_after();
-                const uint32_t p_base = smem_u32(p_s + size_t(pb) * P_BYTES);
-                const uint32_t v_base = smem_u32(v_s + size_t(j) * TILE_BYTES);
+                    for (int k = 0; k < HD / 16; ++k)
+                        umma_bf16(tmem_base + uint32_t(j * KT), umma_desc_sw128(q_base + k * 32), umma_desc_sw128(k_base + k * 32), idesc_s,
+                                  uint32_t(k != 0));
+                    umma_commit(smem_u32(kv_empty + st));  // the K tile's ring slot is free once these MMAs retire
+                    umma_commit(smem_u32(s_full + j));
+                    if (++st == KV_STAGES) { st = 0; ph ^= 1u; }
+                }
+                umma_commit(smem_u32(q_empty + qs));       // Q is only read by the S MMAs
+                for (int j = 0; j < n_kv; ++j, ++pt) {
+                    const uint32_t pb = pt & 1u;
+                    mbar_wait(smem_u32(kv_full + st), ph);
+                    mbar_wait(smem_u32(p_full + pb), (pt >> 1) & 1u);
+                    tcgen05_fence_after();
+                    const uint32_t p_base = smem_u32(p_s + size_t(pb) * P_BYTES);
+                    const uint32_t v_base = smem_u32(kv_s + size_t(st) * TILE_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < KT / 16; ++kk)  // 16 keys per instruction: P chunk kk / 4, V rows 16 kk ..
-                    umma_bf16(tmem_base + 2u * KT, umma_desc_sw128(p_base + (kk >> 2) * TILE_BYTES + (kk & 3) * 32),
-                              umma_desc_mn_sw128(v_base + kk * 2048), idesc_o, uint32_t((j | kk) != 0));
-                umma_commit(smem_u32(p_empty + pb));
+                    for (int kk = 0; kk < KT / 16; ++kk)  // 16 keys per instruction: P chunk kk / 4, V rows 16 kk ..
+                        umma_bf16(tmem_base, umma_desc_sw128(p_base + (kk >> 2) * TILE_BYTES + (kk & 3) * 32),
+                                  umma_desc_mn_sw128(v_base + kk * 2048), idesc_o, uint32_t((j | kk) != 0));
+                    umma_commit(smem_u32(kv_empty + st));
+                    umma_commit(smem_u32(p_empty + pb));
+                    if (++st == KV_STAGES) { st = 0; ph ^= 1u; }
+                }
+                umma_commit(smem_u32(o_full));
             }
-            umma_commit(smem_u32(o_full));
         }
         __syncwarp();
     } else {
         // ===================================================== softmax + epilogue: thread = query row = TMEM lane
         const int r = threadIdx.x;  // 0..127
         const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
-        float m = -INFINITY;
-        // ---- pass A
-        for (int j = 0; j < n_kv; ++j) {
-            const int b = j & 1;
-            const int valid = min(KT, s_len - j * KT);
-            mbar_wait(smem_u32(s_full + b), uint32_t(j >> 1) & 1u);
-            tcgen05_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < KT; c += 32) {
-                float v[32];
-                tmem_ld_x32(lane_addr + uint32_t(b * KT + c), v);
-                tmem_ld_wait();
+        uint32_t s_uses[MAX_KV_TILES] = {0u, 0u, 0u, 0u};  // completed phases of every s_full barrier
+        uint32_t pt = 0;
+        int li = 0;
+        for (int it = int(blockIdx.x); it < n_items; it += int(gridDim.x), ++li) {
+            const int2 tl = tiles[it / p.n_heads];
+            const int head = it % p.n_heads;
+            const int s_beg = tl.x, s_len = tl.y & 0xffff, row0 = (tl.y >> 16) * QT;
+            const int n_kv = (s_len + KT - 1) / KT;
+            // ---- pass A: row maximum over every S tile
+            float m = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c + i < valid) m = fmaxf(m, v[i]);
-            }
-            tcgen05_fence_before();
-            mbar_arrive(smem_u32(s_empty + b));
-        }
-        const float mc = m * p.scale_log2e;
-        float l = 0.f;
-        // ---- pass B
-        for (int j = 0; j < n_kv; ++j) {
-            const int t = n_kv + j, b = t & 1, pb = j & 1;
-            const int valid = min(KT, s_len - j * KT);
-            mbar_wait(smem_u32(p_empty + pb), (uint32_t(j >> 1) & 1u) ^ 1u);  // the P V MMA that read this buffer has retired
-            mbar_wait(smem_u32(s_full + b), uint32_t(t >> 1) & 1u);
-            tcgen05_fence_after();
-            unsigned char* prow = p_s + size_t(pb) * P_BYTES + size_t(r) * 128;
+            for (int j = 0; j < MAX_KV_TILES; ++j) {
+                if (j < n_kv) {
+                    const int valid = min(KT, s_len - j * KT);
+                    mbar_wait(smem_u32(s_full + j), s_uses[j] & 1u);
+                    ++s_uses[j];
+                    tcgen05_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < KT; c += 32) {
-                float v[32];
-                tmem_ld_x32(lane_addr + uint32_t(b * KT + c), v);
-                tmem_ld_wait();
-                uint32_t w[16];
+                    for (int c = 0; c < KT; c += 32) {
+                        float v[32];
+                        tmem_ld_x32(lane_addr + uint32_t(j * KT + c), v);
+                        tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float e0 = (c + i < valid) ? exp2f(fmaf(v[i], p.scale_log2e, -mc)) : 0.f;
-                    const float e1 = (c + i + 1 < valid) ? exp2f(fmaf(v[i + 1], p.scale_log2e, -mc)) : 0.f;
-                    l += e0 + e1;
-                    w[i >> 1] = pack_bf16x2(e0, e1);
+                        for (int i = 0; i < 32; ++i)
+                            if (c + i < valid) m = fmaxf(m, v[i]);
+                    }
                 }
-                // 32 keys = four 16-byte units of this row's 128-byte line in chunk c / 64; SW128: unit ^= row % 8
-                unsigned char* chunk = prow + size_t(c >> 6) * TILE_BYTES;
-                const int u0 = (c & 63) >> 3;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
             }
-            tcgen05_fence_before();
-            mbar_arrive(smem_u32(s_empty + b));
-            fence_proxy_async_smem();  // the P tile was written by the generic proxy, the MMA reads it through the async proxy
-            mbar_arrive(smem_u32(p_full + pb));
-        }
-        // ---- epilogue: O / l -> bf16 -> out[row, head * 64 ..]
-        mbar_wait(smem_u32(o_full), 0);
-        tcgen05_fence_after();
-        const float inv_l = 1.f / l;
-        const int qrow = row0 + r;
-        float o[HD];
-        tmem_ld_x32(lane_addr + 2u * KT, o);
-        tmem_ld_x32(lane_addr + 2u * KT + 32u, o + 32);
-        tmem_ld_wait();
-        if (qrow < s_len) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(s_beg) + qrow) * p.hidden + head * HD);
+            const float mc = m * p.scale_log2e;
+            float l = 0.f;
+            // ---- pass B: numerators with the final maximum -> P tiles
+            for (int j = 0; j < n_kv; ++j, ++pt) {
+                const uint32_t pb = pt & 1u;
+                const int valid = min(KT, s_len - j * KT);
+                mbar_wait(smem_u32(p_empty + pb), ((pt >> 1) & 1u) ^ 1u);  // the P V MMA that read this buffer has retired
+                unsigned char* prow = p_s + size_t(pb) * P_BYTES + size_t(r) * 128;
+#pragma unroll 1
+                for (int c = 0; c < KT; c += 32) {
+                    float v[32];
+                    tmem_ld_x32(lane_addr + uint32_t(j * KT + c), v);
+                    tmem_ld_wait();
+                    uint32_t w[16];
 #pragma unroll
-            for (int u = 0; u < HD / 8; ++u)
-                dst[u] = make_uint4(pack_bf16x2(o[8 * u] * inv_l, o[8 * u + 1] * inv_l), pack_bf16x2(o[8 * u + 2] * inv_l, o[8 * u + 3] * inv_l),
-                                    pack_bf16x2(o[8 * u + 4] * inv_l, o[8 * u + 5] * inv_l), pack_bf16x2(o[8 * u + 6] * inv_l, o[8 * u + 7] * inv_l));
+                    for (int i = 0; i < 32; i += 2) {
+                        const float e0 = (c + i < valid) ? exp2f(fmaf(v[i], p.scale_log2e, -mc)) : 0.f;
+                        const float e1 = (c + i + 1 < valid) ? exp2f(fmaf(v[i + 1], p.scale_log2e, -mc)) : 0.f;
+                        l += e0 + e1;
+                        w[i >> 1] = pack_bf16x2(e0, e1);
+                    }
+                    // 32 keys = four 16-byte units of this row's 128-byte line in chunk c / 64; SW128: unit ^= row % 8
+                    unsigned char* chunk = prow + size_t(c >> 6) * TILE_BYTES;
+                    const int u0 = (c & 63) >> 3;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+                }
+                tcgen05_fence_before();     // this thread's reads of S_j (for j = 0: the columns O is about to overwrite) are done
+                fence_proxy_async_smem();   // the P tile was written by the generic proxy, the MMA reads it through the async proxy
+                mbar_arrive(smem_u32(p_full + pb));
+            }
+            // ---- epilogue: O / l -> bf16 -> out[row, head * 64 ..]
+            mbar_wait(smem_u32(o_full), uint32_t(li) & 1u);
+            tcgen05_fence_after();
+            const float inv_l = 1.f / l;
+            const int qrow = row0 + r;
+            float o[HD];
+            tmem_ld_x32(lane_addr, o);
+            tmem_ld_x32(lane_addr + 32u, o + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            mbar_arrive(smem_u32(tmem_free));  // O (and every S tile) of this item is in registers / consumed
+            if (qrow < s_len) {
+                uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(s_beg) + qrow) * p.hidden + head * HD);
+#pragma unroll
+                for (int u = 0; u < HD / 8; ++u)
+                    dst[u] = make_uint4(pack_bf16x2(o[8 * u] * inv_l, o[8 * u + 1] * inv_l), pack_bf16x2(o[8 * u + 2] * inv_l, o[8 * u + 3] * inv_l),
+                                        pack_bf16x2(o[8 * u + 4] * inv_l, o[8 * u + 5] * inv_l), pack_bf16x2(o[8 * u + 6] * inv_l, o[8 * u + 7] * inv_l));
+            }
         }
     }
 
@@ -349,9 +367,13 @@ __global__ void __launch_bounds__(256) cls_head_kernel(const __nv_bfloat16* __re
 }  // namespace attn
 
 int launch_attention_varlen(const void* qkv, int64_t n_tokens, int n_heads, const int* cu_seqlens, int n_seq, int max_len,
-                            int max_tiles, float scale, void* out, cudaStream_t st) {
+                            int max_tiles, float scale, void* out, int n_sms, cudaStream_t st) {
     using namespace attn;
     const int hidden = n_heads * HD;
+    if (max_tiles > MAX_TILES) {
+        set_error("tt_attention_varlen_bf16: %d query tiles in one call (limit %d: split the batch)", max_tiles, MAX_TILES);
+        return TT_ERR_UNSUPPORTED;
+    }
     EncodeTiledFn fn = encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available from this driver");
@@ -374,13 +396,14 @@ int launch_attention_varlen(const void* qkv, int64_t n_tokens, int n_heads, cons
     p.n_seq = n_seq;
     p.n_heads = n_heads;
     p.hidden = hidden;
-    p.n_tokens = n_tokens;
-    p.n_kv_max = (max_len + KT - 1) / KT;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
-    const size_t smem = 1024 + TILE_BYTES + size_t(p.n_kv_max) * 2 * TILE_BYTES + 2 * P_BYTES + 256;
+    const size_t smem = 1024 + size_t(Q_STAGES + KV_STAGES) * TILE_BYTES + 2 * P_BYTES + MAX_TILES * sizeof(int2) + 512;
     TT_CUDA_OK(cudaFuncSetAttribute(attn_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT)));
-    attn_varlen_kernel<<<dim3(max_tiles, n_heads), A_THREADS, smem, st>>>(map, p);
+    int64_t items = int64_t(max_tiles) * n_heads;
+    int grid = int(items < n_sms ? items : n_sms);
+    if (grid < 1) grid = 1;
+    attn_varlen_kernel<<<grid, A_THREADS, smem, st>>>(map, p);
     TT_LAUNCH_OK("attn_varlen_kernel");
     return TT_OK;
 }

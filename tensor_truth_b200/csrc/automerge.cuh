@@ -26,8 +26,9 @@ struct AmArgs {
 struct AmSmem {
     int32_t idA[AM_CAP], idB[AM_CAP];
     double scA[AM_CAP], scB[AM_CAP];
-    int32_t par[AM_CAP];
-    int32_t flag[AM_CAP];
+    int32_t par[AM_CAP];   // parent of B-list entry j (fill-in phase: prev_id of A-list entry j)
+    int32_t cc[AM_CAP];    // child_count of that parent
+    uint8_t flag[AM_CAP];
     int warp_sums[33];
     int bad;
 };
@@ -58,20 +59,29 @@ __device__ __forceinline__ void automerge_block(AmSmem& S, const int64_t* in_ids
     int rounds = 0;
     while (changed && rounds < a.max_rounds) {
         // ================= _fill_in_nodes: A -> B =================
-        int f = 0;
-        int32_t nxt = -1;
-        int32_t my = -1;
+        // Every relation of "my" node is fetched at once (three independent loads: one DRAM latency), its parent's
+        // child count right behind them; the merge phase below then runs entirely out of shared memory.
+        int32_t my = -1, nxt = -1, prv = -1, pr = -1, ccp = 1;
         double ms = 0.0;
         if (t < n) {
             my = S.idA[t];
             ms = S.scA[t];
-            if (t < n - 1) {
-                nxt = a.next_id[my];
-                if (nxt != -1 && nxt == a.prev_id[S.idA[t + 1]]) f = 1;
-            }
+            nxt = a.next_id[my];
+            prv = a.prev_id[my];
+            pr = a.parent_of[my];
+            if (pr >= 0) ccp = a.child_count[pr];
+        }
+        if (t < AM_CAP) S.par[t] = prv;
+        __syncthreads();
+        int f = 0;
+        if (t < n - 1 && nxt != -1 && nxt == S.par[t + 1]) f = 1;
+        int32_t pin = -1, ccin = 1;  // the inserted node's own parent (upstream looks it up like any node's)
+        if (f) {
+            pin = a.parent_of[nxt];
+            if (pin >= 0) ccin = (pin == pr) ? ccp : a.child_count[pin];
         }
         int n_ins;
-        int ex = block_excl_scan(f, S.warp_sums, &n_ins);
+        int ex = block_excl_scan(f, S.warp_sums, &n_ins);  // (its barriers also order the S.par reads above before the writes below)
         const int n2 = n + n_ins;
         if (n2 > AM_CAP) {  // cannot happen while k <= AM_CAP/2 and merges only shrink; guard anyway
             if (t == 0) S.bad = 1;
@@ -81,21 +91,22 @@ __device__ __forceinline__ void automerge_block(AmSmem& S, const int64_t* in_ids
         if (t < n) {
             S.idB[t + ex] = my;
             S.scB[t + ex] = ms;
+            S.par[t + ex] = pr;
+            S.cc[t + ex] = ccp;
+            S.flag[t + ex] = 0;
             if (f) {
                 S.idB[t + ex + 1] = nxt;
                 S.scB[t + ex + 1] = (ms + S.scA[t + 1]) / 2;
+                S.par[t + ex + 1] = pin;
+                S.cc[t + ex + 1] = ccin;
+                S.flag[t + ex + 1] = 0;
             }
         }
         __syncthreads();
 
         // ================= _get_parents_and_merge: B -> A =================
         int32_t p = -1;
-        if (t < n2) p = a.parent_of[S.idB[t]];
-        if (t < AM_CAP) {
-            S.par[t] = p;
-            S.flag[t] = 0;
-        }
-        __syncthreads();
+        if (t < n2) p = S.par[t];
         int first = -1, cnt = 0;
         if (p >= 0) {
             for (int j = 0; j < n2; ++j) {
@@ -112,7 +123,7 @@ __device__ __forceinline__ void automerge_block(AmSmem& S, const int64_t* in_ids
             double sum = 0.0;  // left-to-right float64, like sum() on CPython <= 3.11
             for (int j = t; j < n2; ++j)
                 if (S.par[j] == p) sum = sum + S.scB[j];
-            int cc = a.child_count[p];
+            int cc = S.cc[t];
             if (cc <= 0) cc = 1;
             const double ratio = double(cnt) / double(cc);
             if (ratio > a.ratio_thresh) {
@@ -122,7 +133,7 @@ __device__ __forceinline__ void automerge_block(AmSmem& S, const int64_t* in_ids
             }
         }
         __syncthreads();
-        const int drop = (p >= 0) ? S.flag[first] : 0;
+        const int drop = (p >= 0) ? int(S.flag[first]) : 0;
         const int keep = (t < n2 && !drop) ? 1 : 0;
         int n_keep, n_merge;
         const int exk = block_excl_scan(keep, S.warp_sums, &n_keep);
