@@ -297,6 +297,12 @@ int tt_automerge(const int64_t* ids, const float* scores, int n_q, int k,
  *                             record to the peers (xchg != NULL) or runs stage 3 on it (am != NULL, xchg == NULL).
  *                             ws: tt_rescore_fused_workspace_bytes(n_q, n_cand) bytes, ZEROED ONCE by the caller
  *                             when it allocates them (the tickets; the kernel leaves them zero).
+ *                             cand_approx (stage 1's out_approx) + prefilter_window > 0 (cosine mode, k <= 32,
+ *                             n_cand <= 5120): only candidates whose approximate score is within the window of the
+ *                             k-th best approximate score are re-scored -- exact as long as window >= 2 x the
+ *                             stage-1 error bound the certificate is checked against (a candidate further below
+ *                             cannot reach the exact top-k); one block per query.  A query with more than 1024
+ *                             candidates inside the window comes back unproven (out_margin = -inf).
  *   tt_merge_topk_fused     = tt_merge_topk_pulled + (optionally) the certificate margins every source pushed,
  *                             copied out of the receive region into out_all_margins float [n_lists, n_q], +
  *                             (optionally) stage 3 on the merged list in the same block.  out_scores / out_ids
@@ -323,7 +329,7 @@ int tt_rescore_topk_fused(const void* corpus, int corpus_dtype, int64_t n_rows, 
                           int k, int score_mode,
                           float* out_keys, float* out_scores, int64_t* out_ids, float* out_margin,
                           void* ws, size_t ws_bytes, const tt_exchange_t* xchg, const tt_l2_cert_t* l2_cert,
-                          const tt_automerge_args_t* am, void* stream);
+                          const tt_automerge_args_t* am, const float* cand_approx, float prefilter_window, void* stream);
 int tt_merge_topk_fused(const float* keys, const int64_t* ids, int n_lists, int64_t keys_list_stride,
                         int64_t ids_list_stride, int n_q, int k_in, int k_out, int score_mode,
                         float* out_scores, int64_t* out_ids, const tt_exchange_t* xchg, float* out_all_margins,

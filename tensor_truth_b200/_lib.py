@@ -44,7 +44,8 @@ SIGNATURES = {
     "tt_exchange_push": (_I, [_P, _Z, _P, _P]),
     "tt_peer_barrier": (_I, [_P, _P]),
     "tt_rescore_fused_workspace_bytes": (_Z, [_I, _I]),
-    "tt_rescore_topk_fused": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P, _P, _P, _P]),
+    "tt_rescore_topk_fused": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P, _P, _P, _P,
+                                   C.c_float, _P]),
     "tt_merge_topk_fused": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "tt_merge_topk_pulled": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P, _P]),
     "tt_linear_bf16": (_I, [_P, _L, _I, _P, _I, _P, _P, _I, _P, _P]),

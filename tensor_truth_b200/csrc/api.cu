@@ -50,6 +50,12 @@ int launch_rescore_select(const void* corpus, int dtype, int64_t n_rows, int dim
                           int k, int mode, float* out_keys, float* out_scores, int64_t* out_ids, float* out_margin,
                           uint64_t* packed, unsigned* tickets, const tt_exchange_t* xh, const tt_l2_cert_t* l2,
                           const tt_automerge_args_t* amh, cudaStream_t st);
+int launch_stage2_prefilter(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
+                            const float* q, int n_q, const int64_t* cand_ids, const float* cand_approx, int n_cand, float window,
+                            const float* thresh, int n_thresh, int k, int mode, float* out_keys, float* out_scores,
+                            int64_t* out_ids, float* out_margin, const tt_exchange_t* xh, const tt_automerge_args_t* amh,
+                            cudaStream_t st);
+bool stage2_prefilter_supported(int n_cand, int k, int mode);
 int launch_exchange_push(const void* rec, size_t nbytes, const tt_exchange_t* h, cudaStream_t st);
 int launch_peer_barrier(const tt_exchange_t* h, cudaStream_t st);
 // per-translation-unit status words (tt_common.cuh)
@@ -364,6 +370,11 @@ int tt_rescore_topk_fused(const void* corpus, int corpus_dtype, int64_t n_rows, 
     TT_CHECK_ARG(!(xchg && am), "tt_rescore_topk_fused: a pushed record is merged before stage 3 (tt_merge_topk_fused)");
     if (n_q == 0) return TT_OK;
     TT_CHECK_ARG(q_f32 && (out_ids || xchg) && (n_cand == 0 || cand_ids), "tt_rescore_topk_fused: null pointer");
+    TT_CHECK_ARG(prefilter_window >= 0.f, "tt_rescore_topk_fused: prefilter_window=%f", double(prefilter_window));
+    if (cand_approx && prefilter_window > 0.f && n_cand > 0 && stage2_prefilter_supported(n_cand, k, score_mode))
+        return launch_stage2_prefilter(corpus, corpus_dtype, n_rows, dim, row_stride_elems, id_base, q_f32, n_q, cand_ids,
+                                       cand_approx, n_cand, prefilter_window, cand_thresh, cand_thresh ? n_lists : 0, k,
+                                       score_mode, out_keys, out_scores, out_ids, out_margin, xchg, am, TT_STREAM(stream));
     const size_t need = tt_rescore_fused_workspace_bytes(n_q, n_cand);
     if (ws_bytes < need || !ws) {
         set_error("tt_rescore_topk_fused: workspace %zu < %zu bytes", ws_bytes, need);

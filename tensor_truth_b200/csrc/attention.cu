@@ -19,7 +19,9 @@
 //
 // Persistent CTAs (one per SM) walk the items; K / V tiles stream through a 7-stage TMA ring and Q through a 2-stage
 // one, so the loads of the next item are in flight while the softmax warps -- the bottleneck -- work on the current one.
-// Six warps: 0-3 softmax / epilogue, 4 TMA producer, 5 TMEM alloc + MMA issue.
+// Ten warps: 0-7 softmax / epilogue (warps w and w + 4 share the TMEM lane quarter w % 4 and split every S tile's 128
+// key columns -- and O's 64 -- in halves; row maxima and row sums are combined through shared memory), 8 TMA producer,
+// 9 TMEM alloc + MMA issue.
 #include "tc_ptx.cuh"
 
 namespace tt {
@@ -38,7 +40,8 @@ constexpr int P_BYTES = 2 * TILE_BYTES;  // a [128 x 128] bf16 P tile: two 64-co
 constexpr int KV_STAGES = 7;
 constexpr int Q_STAGES = 2;
 constexpr int TMEM_COLS = 512;       // S_j at columns 128 j; O in columns 0..63 (over S_0)
-constexpr int A_THREADS = 192;
+constexpr int SM_THREADS = 256;      // softmax / epilogue threads: two per query row
+constexpr int A_THREADS = SM_THREADS + 64;
 constexpr int MAX_TILES = 1024;      // query tiles per launch (the tile table in shared memory)
 
 struct Params {
@@ -76,6 +79,12 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int n, bool b_mn_major) {
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -89,7 +98,8 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
     unsigned char* kv_s = q_s + Q_STAGES * TILE_BYTES;           // KV_STAGES x 16 KB
     unsigned char* p_s = kv_s + KV_STAGES * TILE_BYTES;          // 2 x 32 KB
     int2* tiles = reinterpret_cast<int2*>(p_s + 2 * P_BYTES);    // MAX_TILES x {sequence start, length | tile index << 16}
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + MAX_TILES);
+    float* xch = reinterpret_cast<float*>(tiles + MAX_TILES);    // [2][QT] row maxima, then [2][QT] row sums, of the two column halves
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xch + 4 * QT);
     uint64_t* kv_full = bars;                      // KV_STAGES
     uint64_t* kv_empty = kv_full + KV_STAGES;      // KV_STAGES
     uint64_t* q_full = kv_empty + KV_STAGES;       // Q_STAGES
@@ -129,7 +139,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
         }
         if (lane == 0) *n_tiles_s = min(total, MAX_TILES);
     }
-    if (threadIdx.x == 32) {
+    if (threadIdx.x == 64) {
         for (int s = 0; s < KV_STAGES; ++s) {
             mbar_init(smem_u32(kv_full + s), 1);
             mbar_init(smem_u32(kv_empty + s), 1);
@@ -140,14 +150,14 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
         }
         for (int j = 0; j < MAX_KV_TILES; ++j) mbar_init(smem_u32(s_full + j), 1);
         for (int a = 0; a < 2; ++a) {
-            mbar_init(smem_u32(p_full + a), QT);
+            mbar_init(smem_u32(p_full + a), SM_THREADS);
             mbar_init(smem_u32(p_empty + a), 1);
         }
         mbar_init(smem_u32(o_full), 1);
-        mbar_init(smem_u32(tmem_free), QT);
+        mbar_init(smem_u32(tmem_free), SM_THREADS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_s)),
                      "r"(uint32_t(TMEM_COLS))
                      : "memory");
@@ -159,7 +169,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
     const uint32_t tmem_base = *tmem_base_s;
     const int n_items = *n_tiles_s * p.n_heads;  // item = tile * n_heads + head
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ===================================================== TMA producer: Q, then the K tiles, then the V tiles of every item
         if (lane == 0) {
             int st = 0;
@@ -185,7 +195,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ===================================================== MMA issuer (one thread)
         if (lane == 0) {
             constexpr uint32_t idesc_s = idesc_bf16(KT, false);
@@ -235,9 +245,12 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
         }
         __syncwarp();
     } else {
-        // ===================================================== softmax + epilogue: thread = query row = TMEM lane
-        const int r = threadIdx.x;  // 0..127
-        const uint32_t lane_addr = tmem_base + (uint32_t(warp * 32) << 16);
+        // ===================================================== softmax + epilogue: thread = (query row = TMEM lane, column half)
+        const int quarter = warp & 3, half = warp >> 2;
+        const int r = quarter * 32 + lane;  // query row within the tile
+        const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
+        float* mx = xch;            // [2][QT]
+        float* ls = xch + 2 * QT;   // [2][QT]
         uint32_t s_uses[MAX_KV_TILES] = {0u, 0u, 0u, 0u};  // completed phases of every s_full barrier
         uint32_t pt = 0;
         int li = 0;
@@ -246,73 +259,96 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
             const int head = it % p.n_heads;
             const int s_beg = tl.x, s_len = tl.y & 0xffff, row0 = (tl.y >> 16) * QT;
             const int n_kv = (s_len + KT - 1) / KT;
-            // ---- pass A: row maximum over every S tile
-            float m = -INFINITY;
+            // ---- pass A: row maximum over this thread's half of every S tile
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
             for (int j = 0; j < MAX_KV_TILES; ++j) {
                 if (j < n_kv) {
-                    const int valid = min(KT, s_len - j * KT);
+                    const int valid = min(64, max(0, s_len - j * KT - half * 64));  // of this thread's 64 columns
                     mbar_wait(smem_u32(s_full + j), s_uses[j] & 1u);
                     ++s_uses[j];
                     tcgen05_fence_after();
-#pragma unroll 1
-                    for (int c = 0; c < KT; c += 32) {
-                        float v[32];
-                        tmem_ld_x32(lane_addr + uint32_t(j * KT + c), v);
-                        tmem_ld_wait();
+                    float v[64];
+                    tmem_ld_x32(lane_addr + uint32_t(j * KT + half * 64), v);
+                    tmem_ld_x32(lane_addr + uint32_t(j * KT + half * 64 + 32), v + 32);
+                    tmem_ld_wait();
+                    if (valid == 64) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c + i < valid) m = fmaxf(m, v[i]);
+                        for (int i = 0; i < 64; i += 4) {
+                            m0 = fmaxf(m0, v[i]);
+                            m1 = fmaxf(m1, v[i + 1]);
+                            m2 = fmaxf(m2, v[i + 2]);
+                            m3 = fmaxf(m3, v[i + 3]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 64; ++i)
+                            if (i < valid) m0 = fmaxf(m0, v[i]);
                     }
                 }
             }
+            mx[half * QT + r] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            epi_bar_sync<SM_THREADS>();
+            const float m = fmaxf(mx[r], mx[QT + r]);  // finite: column 0 of tile 0 is always a valid key
             const float mc = m * p.scale_log2e;
-            float l = 0.f;
-            // ---- pass B: numerators with the final maximum -> P tiles
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            // ---- pass B: numerators with the final maximum -> this thread's 128-byte line of the P tile (chunk = half)
             for (int j = 0; j < n_kv; ++j, ++pt) {
                 const uint32_t pb = pt & 1u;
-                const int valid = min(KT, s_len - j * KT);
+                const int valid = min(64, max(0, s_len - j * KT - half * 64));
+                float v[64];
+                tmem_ld_x32(lane_addr + uint32_t(j * KT + half * 64), v);
+                tmem_ld_x32(lane_addr + uint32_t(j * KT + half * 64 + 32), v + 32);
                 mbar_wait(smem_u32(p_empty + pb), ((pt >> 1) & 1u) ^ 1u);  // the P V MMA that read this buffer has retired
-                unsigned char* prow = p_s + size_t(pb) * P_BYTES + size_t(r) * 128;
-#pragma unroll 1
-                for (int c = 0; c < KT; c += 32) {
-                    float v[32];
-                    tmem_ld_x32(lane_addr + uint32_t(j * KT + c), v);
-                    tmem_ld_wait();
-                    uint32_t w[16];
+                tmem_ld_wait();
+                uint32_t w[32];
+                if (valid == 64) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const float e0 = (c + i < valid) ? exp2f(fmaf(v[i], p.scale_log2e, -mc)) : 0.f;
-                        const float e1 = (c + i + 1 < valid) ? exp2f(fmaf(v[i + 1], p.scale_log2e, -mc)) : 0.f;
-                        l += e0 + e1;
+                    for (int i = 0; i < 64; i += 4) {
+                        const float e0 = ex2_approx(fmaf(v[i], p.scale_log2e, -mc)), e1 = ex2_approx(fmaf(v[i + 1], p.scale_log2e, -mc));
+                        const float e2 = ex2_approx(fmaf(v[i + 2], p.scale_log2e, -mc)), e3 = ex2_approx(fmaf(v[i + 3], p.scale_log2e, -mc));
+                        l0 += e0;
+                        l1 += e1;
+                        l2 += e2;
+                        l3 += e3;
+                        w[i >> 1] = pack_bf16x2(e0, e1);
+                        w[(i >> 1) + 1] = pack_bf16x2(e2, e3);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 64; i += 2) {
+                        const float e0 = (i < valid) ? ex2_approx(fmaf(v[i], p.scale_log2e, -mc)) : 0.f;
+                        const float e1 = (i + 1 < valid) ? ex2_approx(fmaf(v[i + 1], p.scale_log2e, -mc)) : 0.f;
+                        l0 += e0;
+                        l1 += e1;
                         w[i >> 1] = pack_bf16x2(e0, e1);
                     }
-                    // 32 keys = four 16-byte units of this row's 128-byte line in chunk c / 64; SW128: unit ^= row % 8
-                    unsigned char* chunk = prow + size_t(c >> 6) * TILE_BYTES;
-                    const int u0 = (c & 63) >> 3;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        *reinterpret_cast<uint4*>(chunk + (((u0 + u) ^ (r & 7)) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
                 }
+                // eight 16-byte units of row r's line in chunk `half`; SW128: unit ^= row % 8
+                unsigned char* line = p_s + size_t(pb) * P_BYTES + size_t(half) * TILE_BYTES + size_t(r) * 128;
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    *reinterpret_cast<uint4*>(line + ((u ^ (r & 7)) << 4)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
                 tcgen05_fence_before();     // this thread's reads of S_j (for j = 0: the columns O is about to overwrite) are done
                 fence_proxy_async_smem();   // the P tile was written by the generic proxy, the MMA reads it through the async proxy
                 mbar_arrive(smem_u32(p_full + pb));
             }
-            // ---- epilogue: O / l -> bf16 -> out[row, head * 64 ..]
+            ls[half * QT + r] = (l0 + l1) + (l2 + l3);
+            epi_bar_sync<SM_THREADS>();
+            const float inv_l = 1.f / (ls[r] + ls[QT + r]);
+            // ---- epilogue: this thread's 32 columns of O / l -> bf16 -> out[row, head * 64 + 32 half ..]
             mbar_wait(smem_u32(o_full), uint32_t(li) & 1u);
             tcgen05_fence_after();
-            const float inv_l = 1.f / l;
             const int qrow = row0 + r;
-            float o[HD];
-            tmem_ld_x32(lane_addr, o);
-            tmem_ld_x32(lane_addr + 32u, o + 32);
+            float o[32];
+            tmem_ld_x32(lane_addr + uint32_t(half * 32), o);
             tmem_ld_wait();
             tcgen05_fence_before();
             mbar_arrive(smem_u32(tmem_free));  // O (and every S tile) of this item is in registers / consumed
             if (qrow < s_len) {
-                uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(s_beg) + qrow) * p.hidden + head * HD);
+                uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t(s_beg) + qrow) * p.hidden + head * HD + half * 32);
 #pragma unroll
-                for (int u = 0; u < HD / 8; ++u)
+                for (int u = 0; u < 4; ++u)
                     dst[u] = make_uint4(pack_bf16x2(o[8 * u] * inv_l, o[8 * u + 1] * inv_l), pack_bf16x2(o[8 * u + 2] * inv_l, o[8 * u + 3] * inv_l),
                                         pack_bf16x2(o[8 * u + 4] * inv_l, o[8 * u + 5] * inv_l), pack_bf16x2(o[8 * u + 6] * inv_l, o[8 * u + 7] * inv_l));
             }
@@ -321,7 +357,7 @@ attn_varlen_kernel(const __grid_constant__ CUtensorMap map_qkv, const Params p) 
 
     tcgen05_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tcgen05_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(uint32_t(TMEM_COLS)) : "memory");
     }
@@ -398,7 +434,7 @@ int launch_attention_varlen(const void* qkv, int64_t n_tokens, int n_heads, cons
     p.hidden = hidden;
     p.scale_log2e = scale * 1.4426950408889634f;
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
-    const size_t smem = 1024 + size_t(Q_STAGES + KV_STAGES) * TILE_BYTES + 2 * P_BYTES + MAX_TILES * sizeof(int2) + 512;
+    const size_t smem = 1024 + size_t(Q_STAGES + KV_STAGES) * TILE_BYTES + 2 * P_BYTES + MAX_TILES * sizeof(int2) + 4 * QT * sizeof(float) + 512;
     TT_CUDA_OK(cudaFuncSetAttribute(attn_varlen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_LIMIT)));
     int64_t items = int64_t(max_tiles) * n_heads;
     int grid = int(items < n_sms ? items : n_sms);

@@ -288,7 +288,8 @@ __device__ __forceinline__ void sel_emit(const SelArgs& a, const XNow& now, int 
 
 // certificate margin of query b (all THREADS threads call; `kth` = k-th selected entry, valid in thread 0)
 template <int THREADS>
-__device__ __forceinline__ void sel_margin(const SelArgs& a, const XNow& now, int b, uint64_t kth, float* red, double* red64) {
+__device__ __forceinline__ void sel_margin(const SelArgs& a, const XNow& now, int b, uint64_t kth, float* red, double* red64,
+                                           bool force_fail = false) {
     if (!a.out_margin) return;
     const int t = threadIdx.x;
     float m = -INFINITY;
@@ -309,6 +310,7 @@ __device__ __forceinline__ void sel_margin(const SelArgs& a, const XNow& now, in
         else if (a.mode == TT_SCORE_COSINE) margin = entry_key(kth) - m;
         else if (l2c) margin = entry_key(kth) - l2_upper_bound(m + a.cert.eps, qq, a.cert.nlo, a.cert.nhi);  // > 0 proves it
         else margin = -INFINITY;                          // cosine-ordered shortlist, no norm bounds given
+        if (force_fail) margin = -INFINITY;               // the selection itself was cut short: never certify it
         a.out_margin[b] = margin;
         if (a.x.push_world) xchg_store_margin(a.x, now, b, margin);
     }
@@ -539,6 +541,114 @@ __global__ void __launch_bounds__(SMALL ? FUSED_SMALL_THREADS : SEL_THREADS) res
     else select_body(a, b, reinterpret_cast<uint64_t*>(smem_raw), gridDim.y);
 }
 
+// ------------------------------------------------------------------ stage 2 with a pre-filter: ONE block per query
+// The shortlist holds thousands of candidates (148 lists x K'), the answer k of them.  With |approx - exact| <= eps --
+// the very bound the certificate rests on -- a candidate whose approximate score lies more than 2 eps below the k-th
+// best approximate score a_k cannot reach the exact top-k (its exact score is < a_k - eps <= the k-th exact score).
+// So: find a_k (k rounds of a block-wide maximum over register-resident 32-bit keys; ties fall together, which only
+// lowers the bound), keep the candidates with approx >= a_k - window, re-score only THOSE in fp64 (a few dozen rows
+// instead of 4736: one warp each), sort them, emit.  One block, no second wave, no cross-block hand-over -- the
+// latency chain of a batch-1 query shrinks by about ten microseconds and stage 2's HBM traffic by two orders of
+// magnitude.  More than S2_CAP survivors (a dense neighbourhood under a wide hi-only window, or near-duplicates) is
+// reported as an unproven query (margin = -inf): the caller's repair ladder re-runs it.
+constexpr int S2_THREADS = 512;
+constexpr int S2_EPT = 10;    // candidates per thread: 5120 per query
+constexpr int S2_CAP = 1024;  // survivors per query
+
+struct S2Src {
+    const void* corpus;
+    int64_t n_rows;
+    int dim;
+    int64_t stride, id_base;
+    const float* q;            // [n_q, dim]
+    const int64_t* cand_ids;   // [n_q, n_cand]
+    const float* cand_approx;  // [n_q, n_cand]
+    float window;              // 2 eps
+};
+
+union S2Smem {
+    AmSmem am;
+    struct {
+        uint64_t ex[S2_CAP];
+        uint32_t rows[S2_CAP];
+    } s;
+};
+
+template <typename CT>
+__global__ void __launch_bounds__(S2_THREADS) stage2_prefilter_kernel(const S2Src r, const SelArgs a) {
+    __shared__ S2Smem sm;
+    __shared__ uint32_t part[2][S2_THREADS / 32];
+    __shared__ float red[32];
+    __shared__ double red64[32];
+    __shared__ int sh_n;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int n_cand = a.n_in, k = a.k;
+    const XNow now = xchg_now(a.x, a.x.push_world > 0);
+    const int64_t* ids = r.cand_ids + size_t(b) * n_cand;
+    const float* apx = r.cand_approx + size_t(b) * n_cand;
+    if (t == 0) sh_n = 0;
+
+    // ---- 1. order-preserving 32-bit images of the approximate scores, register-resident (0 = no candidate)
+    uint32_t ok[S2_EPT], wk[S2_EPT];
+#pragma unroll
+    for (int i = 0; i < S2_EPT; ++i) {
+        const int j = t + i * S2_THREADS;
+        uint32_t v = 0u;
+        if (j < n_cand && __ldcg(ids + j) >= 0) v = okey_of(__ldcg(apx + j));
+        ok[i] = wk[i] = v;
+    }
+    // ---- 2. the k-th largest distinct key: a lower bound on the k-th best approximate score
+    uint32_t kth = 0u;
+    int found = 0;
+    for (int rd = 0; rd < k; ++rd) {
+        uint32_t m = wk[0];
+#pragma unroll
+        for (int i = 1; i < S2_EPT; ++i) m = max(m, wk[i]);
+        m = __reduce_max_sync(0xffffffffu, m);
+        if (lane == 0) part[rd & 1][warp] = m;
+        __syncthreads();
+        const uint32_t w = __reduce_max_sync(0xffffffffu, lane < S2_THREADS / 32 ? part[rd & 1][lane] : 0u);
+        if (w == 0u) break;  // fewer than k distinct scores: everything survives (uniform: every thread sees the same w)
+        kth = w;
+        ++found;
+#pragma unroll
+        for (int i = 0; i < S2_EPT; ++i)
+            if (wk[i] == w) wk[i] = 0u;
+    }
+    const float cut = (found == k) ? key_of_okey(kth) - r.window : -INFINITY;
+    __syncthreads();
+    // ---- 3. survivors
+#pragma unroll
+    for (int i = 0; i < S2_EPT; ++i) {
+        if (ok[i] != 0u && key_of_okey(ok[i]) >= cut) {
+            const int slot = atomicAdd(&sh_n, 1);
+            if (slot < S2_CAP) sm.s.rows[slot] = uint32_t(__ldcg(ids + t + i * S2_THREADS) - r.id_base);
+        }
+    }
+    __syncthreads();
+    const bool overflow = sh_n > S2_CAP;
+    const int n_s = min(sh_n, S2_CAP);
+    // ---- 4. exact fp64 re-score of the survivors, one warp each
+    const float* qb = r.q + size_t(b) * r.dim;
+    for (int i = warp; i < n_s; i += S2_THREADS / 32) {
+        const uint64_t e = rescore_one<CT>(reinterpret_cast<const CT*>(r.corpus), r.n_rows, r.dim, r.stride, r.id_base, qb,
+                                           r.id_base + int64_t(sm.s.rows[i]), a.mode, lane);
+        if (lane == 0) sm.s.ex[i] = e;
+    }
+    int lim = 32;
+    while (lim < n_s) lim <<= 1;
+    __syncthreads();
+    for (int i = n_s + t; i < lim; i += S2_THREADS) sm.s.ex[i] = 0ull;
+    __syncthreads();
+    block_bitonic_sort_desc(sm.s.ex, lim);
+    // ---- 5. emit (+ push to the peers / + auto-merge)
+    for (int i = t; i < k; i += S2_THREADS) sel_emit(a, now, b, i, i < n_s ? sm.s.ex[i] : 0ull);
+    const uint64_t kth_exact = (k - 1 < n_s) ? sm.s.ex[k - 1] : 0ull;
+    sel_margin<S2_THREADS>(a, now, b, kth_exact, red, red64, overflow);
+    if (a.x.push_world) xchg_publish(a.x, now, gridDim.x);
+    sel_automerge(a, b, sm.am);  // (starts with a barrier: the survivors' storage is dead by then)
+}
+
 // ------------------------------------------------------------------ exchange without compute
 // one block per peer copies the finished local record to it, then the flags are raised (used when the record was
 // repaired on the host side of the certificate check)
@@ -753,6 +863,45 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
 }
 
 // re-score + select (+ push / + auto-merge) in one launch; ws = [packed n_q*n_cand u64 | tickets n_q u32]
+int launch_stage2_prefilter(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
+                            const float* q, int n_q, const int64_t* cand_ids, const float* cand_approx, int n_cand, float window,
+                            const float* thresh, int n_thresh, int k, int mode, float* out_keys, float* out_scores,
+                            int64_t* out_ids, float* out_margin, const tt_exchange_t* xh, const tt_automerge_args_t* amh,
+                            cudaStream_t st) {
+    SelArgs a;
+    memset(&a, 0, sizeof(a));
+    {
+        int rc = fill_xchg(&a.x, xh, xh != nullptr, false);
+        if (rc) return rc;
+    }
+    fill_am(&a.am, amh);
+    if (a.am.out_len) {
+        TT_CHECK_ARG(out_ids && out_scores && a.am.out_ids && a.am.out_scores && a.am.max_out >= 1 && a.am.max_rounds >= 1,
+                     "fused auto-merge: null output or max_out / max_rounds < 1");
+        TT_CHECK_ARG(a.am.n_nodes == 0 || (a.am.parent_of && a.am.child_count && a.am.prev_id && a.am.next_id),
+                     "fused auto-merge: null tree array");
+    }
+    a.n_in = n_cand;
+    a.n_q = n_q;
+    a.k = k;
+    a.mode = mode;
+    a.thresh = thresh;
+    a.n_thresh = n_thresh;
+    a.out_keys = out_keys;
+    a.out_scores = out_scores;
+    a.out_ids = out_ids;
+    a.out_margin = out_margin;
+    S2Src r{corpus, n_rows, dim, stride, id_base, q, cand_ids, cand_approx, window};
+    if (dtype == TT_DTYPE_BF16) stage2_prefilter_kernel<__nv_bfloat16><<<n_q, S2_THREADS, 0, st>>>(r, a);
+    else stage2_prefilter_kernel<float><<<n_q, S2_THREADS, 0, st>>>(r, a);
+    TT_LAUNCH_OK("stage2_prefilter_kernel");
+    return TT_OK;
+}
+
+bool stage2_prefilter_supported(int n_cand, int k, int mode) {
+    return mode == TT_SCORE_COSINE && k <= SMALL_K && n_cand <= S2_THREADS * S2_EPT;
+}
+
 int launch_rescore_select(const void* corpus, int dtype, int64_t n_rows, int dim, int64_t stride, int64_t id_base,
                           const float* q, int n_q, const int64_t* cand_ids, int n_cand, const float* thresh, int n_thresh,
                           int k, int mode, float* out_keys, float* out_scores, int64_t* out_ids, float* out_margin,

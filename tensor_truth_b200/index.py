@@ -277,18 +277,21 @@ class DeviceIndex:
                                   self.n_nodes, float(ratio_thresh), int(max_rounds), ptr(out.ids), ptr(out.scores),
                                   ptr(out.lens), int(out.ids.shape[1]))
 
-    def _stage2(self, q, b, w, n_cand, n_lists, k, xchg=None, cert=None, am=None):
-        """Exact re-score of the shortlist + top-k selection in ONE launch (``tt_rescore_topk_fused``): the block that
-        finishes a query's re-scoring last selects, then pushes the record to the peer ranks (``xchg``) or runs the
-        auto-merge on it (``am``)."""
+    def _stage2(self, q, b, w, n_cand, n_lists, k, xchg=None, cert=None, am=None, eps=0.0):
+        """Exact re-score of the shortlist + top-k selection in ONE launch (``tt_rescore_topk_fused``), which then pushes
+        the record to the peer ranks (``xchg``) or runs the auto-merge on it (``am``).  In cosine mode only the
+        candidates within ``2 eps`` of the k-th best approximate score are re-scored (``eps``: the stage-1 error bound
+        the certificate is checked against) -- a candidate further below cannot reach the exact top-k."""
         src = self.master if self.master is not None else self.corpus
+        window = 2.0 * float(eps) if (cert is None and not os.environ.get("TT_NO_PREFILTER")) else 0.0
         check(self.lib.tt_rescore_topk_fused(ptr(src), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
                                              self.n_rows, self.dim, self._row_stride(src), self.id_base, ptr(q), b,
                                              ptr(w["cand_ids"]), n_cand, ptr(w["cand_thresh"]), n_lists, k, self.score_mode,
                                              ptr(w["keys"]), ptr(w["scores"]), ptr(w["ids"]), ptr(w["margin"]),
                                              ptr(w["ws"]), w["ws"].numel(), C.byref(xchg) if xchg is not None else None,
                                              C.byref(cert) if cert is not None else None,
-                                             C.byref(am) if am is not None else None, self._stream()))
+                                             C.byref(am) if am is not None else None, ptr(w["cand_approx"]), window,
+                                             self._stream()))
 
     def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None, hi_only: Optional[bool] = None,
                xchg=None, am=None) -> SearchResult:
@@ -346,7 +349,7 @@ class DeviceIndex:
             if self.scan_events is not None:
                 e1.record()
                 self.scan_events.append((e0, e1))
-            self._stage2(q, b, w, n_cand, n_lists, k, xchg, cert, am)
+            self._stage2(q, b, w, n_cand, n_lists, k, xchg, cert, am, eps)
         # cosine: proven iff margin > eps;  L2: the bound already contains eps, proven iff margin > 0
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if l2 else eps, bool(hi_only))
 

@@ -98,7 +98,7 @@ class SegmentedIndex(DeviceIndex):
                                                 self.id_base, self._seg_end, self.n_seg, ptr(w["cand_ids"]),
                                                 ptr(w["cand_approx"]), ptr(w["cand_thresh"]), ptr(w["scan_ws"]),
                                                 w["scan_ws"].numel(), st))
-            self._stage2(q_rep, vb, w, n_cand, self.n_lists, k, None, cert, am)
+            self._stage2(q_rep, vb, w, n_cand, self.n_lists, k, None, cert, am, self.eps)
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if cert is not None else self.eps, False)
 
     def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool) -> None:
