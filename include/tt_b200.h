@@ -151,10 +151,14 @@ int tt_scan_topk_bf16_segmented(const void* corpus_bf16, int64_t n_rows, int dim
  * epilogue filters with.  The score matrix never reaches HBM.
  * kprime in {128, 256, 512}; dim % 64 == 0; ws: tt_scan_gemm_workspace_bytes(n_q, kprime) bytes
  * (no initialisation needed; 16 * kprime * 8 B per query).
+ * q_lo_bf16 != NULL (n_q <= 32): the hi+lo pass -- every query occupies two of the 64 MMA columns (hi half, lo half), the
+ * epilogue adds the two accumulators, a(r) carries 16 mantissa bits of the query like tt_scan_topk_bf16 with q_lo: the
+ * tight certificate bound at the bytes-in-flight of the streaming pipeline (batches of 17-32 queries).
  */
 size_t tt_scan_gemm_workspace_bytes(int n_q, int kprime);
 int tt_scan_gemm_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
-                           const float* inv_norm, const void* q_hi_bf16, int n_q, int kprime, int64_t id_base,
+                           const float* inv_norm, const void* q_hi_bf16, const void* q_lo_bf16 /* nullable */, int n_q,
+                           int kprime, int64_t id_base,
                            int64_t* out_ids, float* out_approx, float* out_thresh,
                            void* ws, size_t ws_bytes, void* stream);
 

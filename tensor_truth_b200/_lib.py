@@ -34,7 +34,7 @@ SIGNATURES = {
     "tt_scan_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "tt_scan_topk_bf16_segmented": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _P, _I, _P, _P, _P, _P, _Z, _P]),
     "tt_scan_gemm_workspace_bytes": (_Z, [_I, _I]),
-    "tt_scan_gemm_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _I, _I, _L, _P, _P, _P, _P, _Z, _P]),
+    "tt_scan_gemm_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _P, _P, _P, _P, _Z, _P]),
     "tt_rescore_workspace_bytes": (_Z, [_I, _I]),
     "tt_rescore_topk": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "tt_scan_exact_workspace_bytes": (_Z, [_I, _I, _I]),
@@ -118,6 +118,7 @@ def lib():
 # ---- device-side status (include/tt_b200.h, "Device-side status"): one pinned, device-mapped word per GPU that the
 # kernels OR a TT_STATUS_* code into when a bounded wait runs out; polled after every host synchronisation.
 _status_words: dict = {}
+_status_np: dict = {}
 
 
 def status_word(device_index: int):
@@ -133,6 +134,7 @@ def status_word(device_index: int):
                 ms = int(os.environ.get("TT_WAIT_TIMEOUT_MS", "0"))
                 with torch.cuda.device(device_index):
                     check(lib().tt_status_configure(w.data_ptr(), ms))
+                _status_np[device_index] = w.numpy()  # polled after every host synchronisation: a plain memory read
                 _status_words[device_index] = w
     return w
 
@@ -149,12 +151,13 @@ def set_wait_timeout_ms(device_index: int, ms: int) -> None:
 def check_status(device_index: int) -> None:
     """Raise ``TTError(ERR_TIMEOUT)`` if a kernel on this GPU gave up a wait since the last check (call after the
     stream has been synchronised).  Clears the condition: the caller decides whether the index is still usable."""
-    w = _status_words.get(device_index)
-    if w is None or int(w[0]) == 0:
+    wn = _status_np.get(device_index)
+    if wn is None or wn[0] == 0:
         return
     import torch
 
-    code = int(w[0]) & 0xFFFFFFFF
+    w = _status_words[device_index]
+    code = int(wn[0]) & 0xFFFFFFFF
     w.zero_()
     with torch.cuda.device(device_index):
         out = C.c_uint32(0)

@@ -29,8 +29,8 @@ int scan_tc2_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride,
 size_t scan_gemm_workspace_bytes(int n_q, int kprime);
 bool scan_gemm_supported(int dim, int kprime, int n_lists);
 int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
-                     int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx, float* out_thresh,
-                     void* ws, int n_sms, cudaStream_t st);
+                     const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
+                     float* out_thresh, void* ws, int n_sms, cudaStream_t st);
 int launch_linear(const void* x, int64_t n_rows, int k_in, const void* w, int n_out, const float* bias, const void* residual,
                   int activation, void* y, int n_sms, cudaStream_t st);
 int launch_layernorm(const void* x, int64_t n_rows, int dim, const float* gamma, const float* beta, float eps, void* y,
@@ -259,9 +259,11 @@ size_t tt_scan_gemm_workspace_bytes(int n_q, int kprime) {
 }
 
 int tt_scan_gemm_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,
-                           const float* inv_norm, const void* q_hi_bf16, int n_q, int kprime, int64_t id_base,
-                           int64_t* out_ids, float* out_approx, float* out_thresh, void* ws, size_t ws_bytes,
+                           const float* inv_norm, const void* q_hi_bf16, const void* q_lo_bf16, int n_q, int kprime,
+                           int64_t id_base, int64_t* out_ids, float* out_approx, float* out_thresh, void* ws, size_t ws_bytes,
                            void* stream) {
+    TT_CHECK_ARG(!q_lo_bf16 || (n_q <= 32 && (reinterpret_cast<uintptr_t>(q_lo_bf16) & 15) == 0),
+                 "tt_scan_gemm_topk_bf16: the hi+lo pass takes at most 32 queries (n_q=%d), 16-byte aligned", n_q);
     TT_CHECK_ARG(n_rows >= 0 && n_q >= 0, "tt_scan_gemm_topk_bf16: n_rows=%lld n_q=%d", (long long)n_rows, n_q);
     TT_CHECK_ARG(dim > 0 && dim % 64 == 0, "tt_scan_gemm_topk_bf16: dim=%d must be a positive multiple of 64", dim);
     TT_CHECK_ARG(row_stride_elems >= dim && row_stride_elems % 8 == 0, "tt_scan_gemm_topk_bf16: row stride %lld",
@@ -289,8 +291,8 @@ int tt_scan_gemm_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int
         set_error("tt_scan_gemm_topk_bf16: workspace %zu < %zu bytes", ws_bytes, need);
         return TT_ERR_WORKSPACE;
     }
-    return scan_gemm_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, n_q, kprime, id_base, out_ids,
-                            out_approx, out_thresh, ws, n_sms, TT_STREAM(stream));
+    return scan_gemm_approx(corpus_bf16, n_rows, dim, row_stride_elems, inv_norm, q_hi_bf16, q_lo_bf16, n_q, kprime, id_base,
+                            out_ids, out_approx, out_thresh, ws, n_sms, TT_STREAM(stream));
 }
 
 size_t tt_rescore_workspace_bytes(int n_q, int n_cand) {
@@ -356,7 +358,8 @@ int tt_rescore_topk_fused(const void* corpus, int corpus_dtype, int64_t n_rows, 
                           int64_t id_base, const float* q_f32, int n_q, const int64_t* cand_ids, int n_cand,
                           const float* cand_thresh, int n_lists, int k, int score_mode, float* out_keys, float* out_scores,
                           int64_t* out_ids, float* out_margin, void* ws, size_t ws_bytes, const tt_exchange_t* xchg,
-                          const tt_l2_cert_t* l2_cert, const tt_automerge_args_t* am, void* stream) {
+                          const tt_l2_cert_t* l2_cert, const tt_automerge_args_t* am, const float* cand_approx,
+                          float prefilter_window, void* stream) {
     TT_CHECK_ARG(!l2_cert || (l2_cert->row_norm_min >= 0.f && l2_cert->row_norm_max >= l2_cert->row_norm_min &&
                               l2_cert->eps >= 0.f),
                  "tt_rescore_topk_fused: bad L2 certificate bounds");

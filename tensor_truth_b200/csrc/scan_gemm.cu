@@ -90,9 +90,15 @@ static __device__ __noinline__ void flush_staged(const uint4* stg, int n, unsign
 //   [ barriers: full[stages] (CTA 0), empty[stages], tmem_full[2], tmem_empty[2] (CTA 0) ][ tmem base ]
 // Ten warps: 0-7 epilogue (warps w and w+4 share the TMEM lane quarter w%4 and split the 256 query columns in
 // halves), 8 TMA producer, 9 TMEM alloc + MMA issue (leader CTA).
-template <int NQB, int CH>
+// HILO (NQB = 64 only): up to 32 queries, each as TWO MMA columns -- column j is the bf16 hi half of query j, column
+// 32 + j its lo half (CTA 0 of the pair stages the hi rows, CTA 1 the lo rows: map_q / map_q2) -- and the epilogue
+// adds the two accumulators before it filters.  16 mantissa bits of the query reach the tensor cores, so the tight
+// certificate bound of the hi+lo scan holds, at the bytes-in-flight of the streaming GEMM pipeline.
+template <int NQB, int CH, bool HILO>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS3, 1)
-scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_q, const Params p) {
+scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_q,
+                 const __grid_constant__ CUtensorMap map_q2, const Params p) {
+    static_assert(!HILO || NQB == 64, "the hi+lo variant is the 64-column pass");
     constexpr int NH = NQB / 2;                     // query rows (B operand) held by each CTA of the pair
     constexpr int STAGE_A = CH * CHUNK_BYTES;       // 128 corpus rows x CH 64-column chunks (256 B contiguous per row at CH = 2)
     constexpr int STAGE_B = CH * NH * 128;          // NH query rows x CH chunks
@@ -149,7 +155,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
                 const int qb = int(w % p.n_qb);
                 const int super = int((uint64_t(p.i0 + int(w / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
                 const int row0 = super * 256 + int(rank) * TILE_ROWS;
-                const int qrow0 = qb * NQB + int(rank) * NH;
+                const int qrow0 = HILO ? 0 : qb * NQB + int(rank) * NH;  // HILO: one block of <= 32 queries, hi rows / lo rows
                 for (int c = 0; c < p.n_chunks; c += CH) {
                     mbar_wait(smem_u32(empty_bar + stage), phase ^ 1u);
                     const uint32_t fb = mapa(smem_u32(full_bar + stage), 0);
@@ -157,7 +163,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
                     else mbar_arrive_cluster(fb);
                     const uint32_t dst = smem_u32(ring + size_t(stage) * STAGE_BYTES);
                     tma_load_3d_pair(dst, &map_c, 0, row0, c, fb, POLICY_EVICT_NORMAL);  // re-read from L2 by every query block
-                    tma_load_3d_pair(dst + STAGE_A, &map_q, 0, qrow0, c, fb, POLICY_EVICT_LAST);
+                    tma_load_3d_pair(dst + STAGE_A, (HILO && rank == 1) ? &map_q2 : &map_q, 0, qrow0, c, fb, POLICY_EVICT_LAST);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -232,13 +238,27 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
 
             mbar_wait(smem_u32(tmem_full + a), uint32_t(it >> 1) & 1u);
             tcgen05_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(a * NQB + half * (NQB / 2));
-            const uint32_t th_addr = smem_u32(th + half * (NQB / 2));
+            // HILO: this warp's 16 queries are columns [16 half, 16 half + 16) (hi) and the same + 32 (lo)
+            const int col0 = HILO ? half * 16 : half * (NQB / 2);
+            const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(a * NQB + col0);
+            const uint32_t th_addr = smem_u32(th + col0);
 #pragma unroll 1
-            for (int c32 = 0; c32 < NQB / 2; c32 += 32) {
+            for (int c32 = 0; c32 < (HILO ? 32 : NQB / 2); c32 += 32) {
                 float v[32];
-                tmem_ld_x32(taddr + c32, v);
-                tmem_ld_wait();
+                if (HILO) {
+                    float lo[16];
+                    tmem_ld_x16(taddr, v);
+                    tmem_ld_x16(taddr + 32, lo);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        v[i] += lo[i];
+                        v[16 + i] = -INFINITY;  // columns this warp does not own: never pass (their thresholds are some other query's)
+                    }
+                } else {
+                    tmem_ld_x32(taddr + c32, v);
+                    tmem_ld_wait();
+                }
                 // fast filter: does any of the 32 columns beat its threshold?  fma(v, inv, -tau) > 0 is implied by
                 // the exact test (v * inv rounded) > tau used below, so nothing is missed.
                 float m = -INFINITY;
@@ -264,7 +284,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
                     }
                     if (!row_ok) hm = 0u;
                     uint32_t any = __reduce_or_sync(0xffffffffu, hm);
-                    const int q0 = qb * NQB + half * (NQB / 2) + c32;
+                    const int q0 = qb * NQB + col0 + c32;
                     while (any) {
                         const int j = __ffs(any) - 1;
                         any &= any - 1u;
@@ -439,10 +459,10 @@ bool scan_gemm_supported(int dim, int kprime, int n_lists) {
 
 namespace tc3 {
 
-template <int NQB, int CH>
+template <int NQB, int CH, bool HILO = false>
 static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
                       int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx, float* out_thresh,
-                      void* ws, int n_sms, cudaStream_t st) {
+                      void* ws, int n_sms, cudaStream_t st, const void* q_lo = nullptr) {
     constexpr int NH = NQB / 2;
     constexpr int STAGE_BYTES = CH * (CHUNK_BYTES + NH * 128);
     const int n_qb = (n_q + NQB - 1) / NQB;
@@ -478,14 +498,16 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
     p.cnt = cnt;
     p.cap = cap;
 
-    CUtensorMap map_c, map_q;
+    CUtensorMap map_c, map_q, map_q2;
     if (n_rows > 0) {
         int rc = tc::make_map(&map_c, corpus, n_rows, dim, stride, tc::TILE_ROWS, CH);
         if (rc) return rc;
         rc = tc::make_map(&map_q, q_hi, n_q, dim, dim, NH, CH);
         if (rc) return rc;
+        rc = tc::make_map(&map_q2, HILO ? q_lo : q_hi, n_q, dim, dim, NH, CH);
+        if (rc) return rc;
     }
-    auto kern = scan_gemm_kernel<NQB, CH>;
+    auto kern = scan_gemm_kernel<NQB, CH, HILO>;
     TT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
     TT_CUDA_OK(cudaFuncSetAttribute(gemm_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (cap + kprime) * 8));
 
@@ -509,7 +531,7 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
         if (upto >= p.n_super || p.n_super - upto < next / 2) upto = p.n_super;  // fold a short tail into this phase
         p.i0 = seen;
         p.i1 = upto;
-        kern<<<grid, THREADS3, smem, st>>>(map_c, map_q, p);
+        kern<<<grid, THREADS3, smem, st>>>(map_c, map_q, map_q2, p);
         TT_LAUNCH_OK("scan_gemm_kernel");
         done = upto == p.n_super;
         gemm_cut_kernel<<<n_q, CUT_THREADS, (cap + kprime) * 8, st>>>(buf, cnt, tau, ovf, cap, kprime, done ? 1 : 0, id_base,
@@ -524,8 +546,15 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
 }  // namespace tc3
 
 int scan_gemm_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm, const void* q_hi,
-                     int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx, float* out_thresh,
-                     void* ws, int n_sms, cudaStream_t st) {
+                     const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids, float* out_approx,
+                     float* out_thresh, void* ws, int n_sms, cudaStream_t st) {
+    if (q_lo) {  // hi+lo: <= 32 queries as 64 MMA columns, two 64-column chunks per ring stage when dim allows
+        if (dim % 128 == 0)
+            return tc3::run_phases<64, 2, true>(corpus, n_rows, dim, stride, inv_norm, q_hi, n_q, kprime, id_base, out_ids, out_approx,
+                                                out_thresh, ws, n_sms, st, q_lo);
+        return tc3::run_phases<64, 1, true>(corpus, n_rows, dim, stride, inv_norm, q_hi, n_q, kprime, id_base, out_ids, out_approx,
+                                            out_thresh, ws, n_sms, st, q_lo);
+    }
     int width = n_q <= 64 ? 64 : n_q <= 128 ? 128 : 256;  // one narrower query block when the batch fits it
     if (const char* e = getenv("TT_GEMM_WIDTH")) {         // tuning knob
         const int w = atoi(e);

@@ -36,6 +36,7 @@ EPS_HI_ONLY = 3.95e-3      # added when the query travels as bf16 hi only (|q - 
 HI_ONLY_ABOVE = 32         # batches larger than this scan hi-only first.  (17-32 queries hi-only through the GEMM-shaped scan were
                            # measured at 3.4 ms against 3.56 ms hi+lo: not worth giving up the tight certificate bound by default)
 MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist workspace: 148 * K' * 12 B per query)
+HILO_GEMM_FROM = 17        # hi+lo batches of 17-32 queries take the 64-column GEMM-shaped pass with (hi, lo) column pairs
 GEMM_ABOVE = 33            # hi-only batches at least this large take the GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass
                            # per 4096 queries, one list per query (64 queries: 3.04 ms at 10M rows vs 3.35 ms for the pair kernel)
 GRAPH_AFTER = 3            # retrieve_host: eager calls of a (batch, k) shape before its pipeline is captured in a CUDA graph
@@ -199,12 +200,21 @@ class DeviceIndex:
         return (hi_only and b >= int(os.environ.get("TT_GEMM_ABOVE", GEMM_ABOVE)) and self.variant in (SCAN_AUTO, _lib.SCAN_TCGEN05) and self.dim % 64 == 0
                 and self.n_rows > 0 and not os.environ.get("TT_NO_GEMM"))
 
+    def _use_gemm_hilo(self, b: int) -> bool:
+        """17-32 hi+lo queries: the 64-column pass of the GEMM-shaped scan with every query on two MMA columns (hi, lo).
+        The resident-query kernel needs 128 KB of shared memory for such a block and starves its TMA ring (3.56 ms per
+        pass at 10M rows); the streaming pipeline keeps its bytes in flight."""
+        return (HILO_GEMM_FROM <= b <= 32 and self.variant in (SCAN_AUTO, _lib.SCAN_TCGEN05) and self.dim % 64 == 0
+                and self.n_rows > 0 and not os.environ.get("TT_NO_GEMM") and not os.environ.get("TT_NO_GEMM_HILO"))
+
     def _buffers(self, b: int, k: int, slot: int = 0, hi_only: Optional[bool] = None, kprime: Optional[int] = None):
         """Workspace set for a (batch, k) shape; ``slot`` separates sets used concurrently on different streams;
         ``kprime`` overrides the per-CTA shortlist length (the repair ladder's deeper re-scan)."""
-        gemm = self._use_gemm(b, b > HI_ONLY_ABOVE if hi_only is None else hi_only) and kprime is None
+        hi = b > HI_ONLY_ABOVE if hi_only is None else hi_only
+        hilo = (not hi) and kprime is None and self._use_gemm_hilo(b)
+        gemm = (self._use_gemm(b, hi) and kprime is None) or hilo
         kprime = int(kprime or self.kprime)
-        key = (b, k, slot, gemm, kprime)
+        key = (b, k, slot, gemm, kprime, hilo)
         w = self._ws.get(key)
         if w is None and gemm:
             dev, kp = self.device, gemm_kprime(k)
@@ -212,7 +222,7 @@ class DeviceIndex:
             w = {
                 "gemm": True, "kprime": kp, "slice": sl,
                 "q_hi": torch.empty((b, self.dim), dtype=torch.bfloat16, device=dev),
-                "q_lo": None,
+                "q_lo": torch.empty((b, self.dim), dtype=torch.bfloat16, device=dev) if hilo else None,
                 "cand_ids": torch.empty((b, kp), dtype=torch.int64, device=dev),
                 "cand_approx": torch.empty((b, kp), dtype=torch.float32, device=dev),
                 "cand_thresh": torch.empty((b, 1), dtype=torch.float32, device=dev),
@@ -325,7 +335,7 @@ class DeviceIndex:
         if l2:  # (near-)unit-norm rows: the cosine bound of a dropped row bounds its L2 key (tt_l2_cert_t)
             cert = _lib.L2Cert(self.norm_lo, self.norm_hi, eps)
         L, st = self.lib, self._stream()
-        gemm = bool(w.get("gemm")) and hi_only
+        gemm = bool(w.get("gemm")) and (hi_only or w.get("q_lo") is not None)
         kprime = w.get("kprime", self.kprime)
         n_cand, n_lists = (kprime, 1) if gemm else (self.n_lists * kprime, self.n_lists)
         with self._on_device():
@@ -337,7 +347,8 @@ class DeviceIndex:
                 for a in range(0, b, w["slice"]):
                     n = min(w["slice"], b - a)
                     check(L.tt_scan_gemm_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus),
-                                                   ptr(self.inv_norm), ptr(w["q_hi"][a:]), n, n_cand, self.id_base,
+                                                   ptr(self.inv_norm), ptr(w["q_hi"][a:]), None if hi_only else ptr(w["q_lo"][a:]), n,
+                                                   n_cand, self.id_base,
                                                    ptr(w["cand_ids"][a:]), ptr(w["cand_approx"][a:]), ptr(w["cand_thresh"][a:]),
                                                    ptr(w["gemm_ws"]), w["gemm_ws"].numel(), st))
             else:
@@ -485,7 +496,9 @@ class DeviceIndex:
 
             dev = torch.zeros(total, dtype=torch.uint8, device=self.device)
             host = torch.zeros(total, dtype=torch.uint8).pin_memory()
-            r = self._ws[key] = {"dev": dev, "host": host, "d": views(dev), "h": views(host), "bytes": total,
+            hv = views(host)
+            r = self._ws[key] = {"dev": dev, "host": host, "d": views(dev), "h": hv, "bytes": total,
+                                 "hn": {name: t.numpy() for name, t in hv.items()},  # numpy views of the pinned record
                                  "event": torch.cuda.Event()}
         return r
 
@@ -525,7 +538,7 @@ class DeviceIndex:
                 r = self.search(q_dev, k, out=w, am=am)  # prepare -> scan -> re-score + select + auto-merge: 3 kernels
                 rec["host"].copy_(rec["dev"], non_blocking=True)
             torch.cuda.current_stream(self.device).wait_stream(side)
-            g.update(graph=graph, q_pin=q_pin, q_dev=q_dev, result=r, rec=rec)
+            g.update(graph=graph, q_pin=q_pin, q_pin_np=q_pin.numpy(), q_dev=q_dev, result=r, rec=rec)
             return g
         except Exception as exc:  # capture refused (driver, another thread capturing, ...): keep the eager path
             import warnings
@@ -555,9 +568,12 @@ class DeviceIndex:
             b = int(q_host.shape[0])
             g = self._pipeline_graph(b, k, ratio_thresh, merged) if (q_host.dim() == 2 and q_host.shape[1] == self.dim) else None
             if g is not None:
-                g["q_pin"].copy_(q_host)
+                if q_host.dtype == torch.float32 and q_host.device.type == "cpu":
+                    g["q_pin_np"][...] = q_host.numpy()  # the common case: a plain memory copy into the pinned staging buffer
+                else:
+                    g["q_pin"].copy_(q_host)
                 q, r, rec = g["q_dev"], g["result"], g["rec"]
-                d, h = rec["d"], rec["h"]
+                d, h = rec["d"], rec["hn"]
                 with self._on_device():
                     g["graph"].replay()
             else:
@@ -565,7 +581,7 @@ class DeviceIndex:
                 q = self._check_queries(q)
                 vb = self._result_rows(b)
                 rec = self._record(vb, k, merged)
-                d, h = rec["d"], rec["h"]
+                d, h = rec["d"], rec["hn"]
                 w = dict(self._buffers(vb, k))
                 w["margin"] = d["margin"]
                 if not merged:
@@ -576,7 +592,7 @@ class DeviceIndex:
             rec["event"].record()
             rec["event"].synchronize()
             _lib.check_status(self._dev_index)
-            bad = np.nonzero(~(h["margin"].numpy() > r.eps))[0]
+            bad = np.nonzero(~(h["margin"] > r.eps))[0]
             if bad.size:  # not proven exact: re-run those queries (tighter scan, then the exact fp64 scan)
                 self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only)
                 if merged:
@@ -585,8 +601,8 @@ class DeviceIndex:
                 rec["event"].record()
                 rec["event"].synchronize()
                 _lib.check_status(self._dev_index)
-            ids, scores = h["ids"].numpy().copy(), h["scores"].numpy().astype(np.float64)
-            lens = h["lens"].numpy().copy() if merged else (ids >= 0).sum(axis=1).astype(np.int32)
+            ids, scores = h["ids"].copy(), h["scores"].astype(np.float64)
+            lens = h["lens"].copy() if merged else (ids >= 0).sum(axis=1).astype(np.int32)
             return ids, scores, lens
 
     def close(self) -> None:

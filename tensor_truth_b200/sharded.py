@@ -361,9 +361,9 @@ class ShardedIndex:
 
     @staticmethod
     def _unpack_host(rec, merged):
-        h = rec["h"]
-        ids_h, scores_h = h["ids"].numpy().copy(), h["scores"].numpy().astype("float64")
-        lens = h["lens"].numpy().copy() if merged else (ids_h >= 0).sum(axis=1).astype("int32")
+        h = rec["hn"]
+        ids_h, scores_h = h["ids"].copy(), h["scores"].astype("float64")
+        lens = h["lens"].copy() if merged else (ids_h >= 0).sum(axis=1).astype("int32")
         return ids_h, scores_h, lens
 
     # ------------------------------------------------------------------ host in / host out, peer transport
@@ -423,7 +423,7 @@ class ShardedIndex:
         # every rank makes it, so the lane's epochs stay in lockstep
         with local._on_device():
             graph, _ = capture_on_side_stream(self.device, fn)
-        g.update(graph=graph, q_pin=q_pin, q_dev=q_dev, result=out["r"], rec=rec)
+        g.update(graph=graph, q_pin=q_pin, q_pin_np=q_pin.numpy(), q_dev=q_dev, result=out["r"], rec=rec)
         return g
 
     def _retrieve_host_peer(self, pb, q_host, b, k, ratio_thresh, merged):
@@ -436,7 +436,10 @@ class ShardedIndex:
         local = self.local
         g = self._host_graph(pb, b, k, ratio_thresh, merged)
         if g is not None:
-            g["q_pin"].copy_(q_host)
+            if q_host.dtype == torch.float32 and q_host.device.type == "cpu":
+                g["q_pin_np"][...] = q_host.numpy()  # the common case: a plain memory copy into the pinned staging buffer
+            else:
+                g["q_pin"].copy_(q_host)
             q, r, rec = g["q_dev"], g["result"], g["rec"]
             with local._on_device():
                 g["graph"].replay()
@@ -449,7 +452,7 @@ class ShardedIndex:
         rec["event"].record()
         rec["event"].synchronize()
         self._lib.check_status(local._dev_index)
-        all_h = rec["h"]["extra"].numpy().reshape(pb.world, b)
+        all_h = rec["hn"]["extra"].reshape(pb.world, b)
         proven = all_h > r.eps                    # [world, B], the same on every rank
         if not proven.all():
             mine = (~proven[pb.rank]).nonzero()[0]

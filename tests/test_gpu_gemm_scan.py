@@ -42,7 +42,7 @@ def _gemm_scan(idx, q, kp):
     ws = torch.empty(int(L.tt_scan_gemm_workspace_bytes(b, kp)), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(L.tt_prepare_queries(ptr(q), b, idx.dim, ptr(q_hi), None, st))
-    _lib.check(L.tt_scan_gemm_topk_bf16(ptr(idx.corpus), idx.n_rows, idx.dim, idx.dim, ptr(idx.inv_norm), ptr(q_hi), b, kp,
+    _lib.check(L.tt_scan_gemm_topk_bf16(ptr(idx.corpus), idx.n_rows, idx.dim, idx.dim, ptr(idx.inv_norm), ptr(q_hi), None, b, kp,
                                         idx.id_base, ptr(ids), ptr(approx), ptr(thresh), ptr(ws), ws.numel(), st))
     torch.cuda.synchronize()
     return _np(ids), _np(approx), _np(thresh)
@@ -218,3 +218,44 @@ def test_massive_ties_resolve_by_smaller_id(b):
     assert (np.diff(_np(r.ids), axis=1) > 0).all()  # ten copies of the best vector, ids ascending
     if b > 32:  # one shortlist of 128 per query cannot hold ~750 tied rows: the certificate must have refused
         assert idx.retries + idx.fallbacks > 0
+
+
+@pytest.mark.parametrize("b", [17, 24, 32])
+def test_hilo_pass_17_to_32_queries(mid, b):
+    """Batches of 17-32 hi+lo queries take the 64-column GEMM-shaped pass with (hi, lo) column pairs: the approximate
+    scores carry 16 mantissa bits of the query (error far below the hi+lo certificate bound), the shortlist contract
+    holds, and the certified result equals the oracle's bit for bit with no repair."""
+    tree, bits, inv, q = mid
+    idx = _index(bits, tree)
+    assert idx._use_gemm_hilo(b)
+    qd = torch.from_numpy(q[:b]).cuda()
+    # the C-ABI entry point directly
+    L, ptr = idx.lib, _lib.ptr
+    kp = 128
+    q_hi = torch.empty((b, idx.dim), dtype=torch.bfloat16, device=idx.device)
+    q_lo = torch.empty_like(q_hi)
+    ids = torch.empty((b, kp), dtype=torch.int64, device=idx.device)
+    approx = torch.empty((b, kp), dtype=torch.float32, device=idx.device)
+    thresh = torch.empty((b,), dtype=torch.float32, device=idx.device)
+    ws = torch.empty(int(L.tt_scan_gemm_workspace_bytes(b, kp)), dtype=torch.uint8, device=idx.device)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.tt_prepare_queries(ptr(qd), b, idx.dim, ptr(q_hi), ptr(q_lo), st))
+    _lib.check(L.tt_scan_gemm_topk_bf16(ptr(idx.corpus), idx.n_rows, idx.dim, idx.dim, ptr(idx.inv_norm), ptr(q_hi), ptr(q_lo), b, kp,
+                                        idx.id_base, ptr(ids), ptr(approx), ptr(thresh), ptr(ws), ws.numel(), st))
+    torch.cuda.synchronize()
+    cos = _exact_cosines(bits, q[:b])
+    ids_h, approx_h, thresh_h = _np(ids), _np(approx), _np(thresh)
+    for i in range(b):
+        assert (ids_h[i] >= 0).all() and len(set(ids_h[i].tolist())) == kp
+        err = np.abs(approx_h[i] - cos[i, ids_h[i]]).max()
+        assert err < 2.5e-4 / 4, err                         # hi+lo precision, not hi-only (which is ~1e-3)
+        left_out = np.ones(bits.shape[0], bool)
+        left_out[ids_h[i]] = False
+        assert cos[i, left_out].max() <= thresh_h[i] + 2.5e-4  # the out_thresh contract
+    # through the index: certified, no retries
+    idx.retries = idx.deep_rescans = idx.fallbacks = 0
+    r = idx.search_certified(qd, 10)
+    torch.cuda.synchronize()
+    ids_o, sc_o, _ = cport.scan_topk(bits, q[:b], 10)
+    assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
+    assert r.eps < 1e-3 and not r.hi_only and idx.retries == idx.deep_rescans == idx.fallbacks == 0
