@@ -43,6 +43,8 @@ struct Params {
     int n_qb;             // NQB-query blocks
     int i0, i1;           // this phase: permuted super-tile indices [i0, i1)
     uint32_t perm_mul;    // super = (i * perm_mul) % n_super, gcd(perm_mul, n_super) == 1
+    int* sched;           // {next work item} counter, zero at launch: work items are claimed dynamically (clusters run at
+                          // different speeds -- HBM channels, L2 slices -- and a static interleave leaves the fast ones idle)
     const float* tau;     // [>= n_qb * NQB] running thresholds (+inf in the padding columns)
     unsigned long long* buf;  // [n_q, cap] packed (approx key, local row) entries
     int* cnt;             // [>= n_qb * NQB] entries appended so far (may exceed cap: overflow)
@@ -50,6 +52,7 @@ struct Params {
 };
 
 constexpr int STG_CAP = 64;  // staged survivors per epilogue warp (16 B each)
+constexpr int SCHED_SLOTS = 4;  // work-item ring between CTA 0's producer and every other role of the pair
 
 // v[j] for a warp-uniform j: a select tree instead of dynamic register indexing
 __device__ __forceinline__ float pick32(const float (&v)[32], int j) {
@@ -116,12 +119,28 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
     uint64_t* empty_bar = bars + p.stages;
     uint64_t* tmem_full = bars + 2 * p.stages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* sched_full = tmem_empty + 2;               // SCHED_SLOTS: a work item id has been published in this CTA's ring
+    uint64_t* sched_empty = sched_full + SCHED_SLOTS;    // SCHED_SLOTS (used in CTA 0): every consumer of both CTAs has read it
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(sched_empty + SCHED_SLOTS);
+    volatile int* work_ring = reinterpret_cast<volatile int*>(tmem_base_s + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = int(blockIdx.x) >> 1, n_clusters = int(gridDim.x) >> 1;
-    const int64_t n_work = int64_t(p.i1 - p.i0) * p.n_qb;  // (super-tile, query block) pairs, query block fastest
+    const int n_work = int(min(int64_t(p.i1 - p.i0) * p.n_qb, int64_t(0x7fffffff)));  // (super-tile, query block) pairs, query block fastest
+    // Work items travel from CTA 0's producer (the only thread that claims them) to every other role of both CTAs
+    // through a SCHED_SLOTS-deep ring: id written into both CTAs' rings, sched_full raised in both, sched_empty (CTA 0)
+    // collects one arrival per consumer.  -1 ends the stream.
+    auto sched_take = [&](int it) -> int {  // consumers: the it-th work item (blocking)
+        const int slot = it & (SCHED_SLOTS - 1);
+        const uint32_t par = uint32_t(it / SCHED_SLOTS) & 1u;
+        if (rank == 0) mbar_wait(smem_u32(sched_full + slot), par);
+        else mbar_wait_cluster(smem_u32(sched_full + slot), par);
+        return work_ring[slot];
+    };
+    auto sched_release = [&](int it) {      // one thread per consumer, after its last read of the ring slot
+        mbar_arrive_cluster(mapa(smem_u32(sched_empty + (it & (SCHED_SLOTS - 1))), 0));
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -131,6 +150,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
         for (int a = 0; a < 2; ++a) {
             mbar_init(smem_u32(tmem_full + a), 1);
             mbar_init(smem_u32(tmem_empty + a), 2 * (EPI3 / 32));  // one lane per epilogue warp of both CTAs
+        }
+        for (int r = 0; r < SCHED_SLOTS; ++r) {
+            mbar_init(smem_u32(sched_full + r), 1);
+            mbar_init(smem_u32(sched_empty + r), 2 * (EPI3 / 32) + 2);  // epilogue warps of both CTAs + MMA thread + CTA 1's producer
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -151,9 +174,9 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int64_t w = cluster_id; w < n_work; w += n_clusters) {
-                const int qb = int(w % p.n_qb);
-                const int super = int((uint64_t(p.i0 + int(w / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
+            auto load_item = [&](int w) {
+                const int qb = w % p.n_qb;
+                const int super = int((uint64_t(p.i0 + w / p.n_qb) * p.perm_mul) % uint32_t(p.n_super));
                 const int row0 = super * 256 + int(rank) * TILE_ROWS;
                 const int qrow0 = HILO ? 0 : qb * NQB + int(rank) * NH;  // HILO: one block of <= 32 queries, hi rows / lo rows
                 for (int c = 0; c < p.n_chunks; c += CH) {
@@ -166,6 +189,34 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
                     tma_load_3d_pair(dst + STAGE_A, (HILO && rank == 1) ? &map_q2 : &map_q, 0, qrow0, c, fb, POLICY_EVICT_LAST);
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
+            };
+            if (rank == 0) {
+                // the publisher: item `it + 1` is claimed and published BEFORE the loads of item `it` are issued, so every
+                // consumer (the epilogue prefetches one item ahead) finds its next id waiting
+                auto publish = [&](int it, int w) {
+                    const int slot = it & (SCHED_SLOTS - 1);
+                    mbar_wait(smem_u32(sched_empty + slot), (uint32_t(it / SCHED_SLOTS) & 1u) ^ 1u);
+                    work_ring[slot] = w;
+                    st_shared_cluster_u32(mapa(smem_u32(const_cast<int*>(work_ring) + slot), 1), uint32_t(w));
+                    mbar_arrive(smem_u32(sched_full + slot));
+                    mbar_arrive_cluster_release(mapa(smem_u32(sched_full + slot), 1));
+                };
+                int w = cluster_id < n_work ? cluster_id : -1;
+                publish(0, w);
+                for (int it = 0; w >= 0; ++it) {
+                    int nx = p.sched ? n_clusters + atomicAdd(p.sched, 1) : w + n_clusters;
+                    if (nx >= n_work) nx = -1;
+                    publish(it + 1, nx);
+                    load_item(w);
+                    w = nx;
+                }
+            } else {
+                for (int it = 0;; ++it) {
+                    const int w = sched_take(it);
+                    sched_release(it);
+                    if (w < 0) break;
+                    load_item(w);
+                }
             }
         }
     } else if (warp == 9) {
@@ -174,8 +225,10 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
             constexpr uint32_t idesc = umma_idesc_bf16_m256(NQB);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int64_t w = cluster_id; w < n_work; w += n_clusters, ++it) {
+            for (int it = 0;; ++it) {
+                const int w = sched_take(it);
+                sched_release(it);
+                if (w < 0) break;
                 const int a = it & 1;
                 mbar_wait(smem_u32(tmem_empty + a), (uint32_t(it >> 1) & 1u) ^ 1u);
                 tcgen05_fence_after();
@@ -208,18 +261,17 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
         const int64_t row_in_super = int64_t(rank) * TILE_ROWS + quarter * 32 + lane;
         // thresholds and inv_norm of a tile are fetched one tile ahead (their latency hides behind the current tile)
         float tau_n = INFINITY, inv_n = 1.f;
-        if (cluster_id < n_work) {
-            const int64_t w = cluster_id;
-            const int super = int((uint64_t(p.i0 + int(w / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
+        int w = sched_take(0);
+        if (w >= 0) {
+            const int super = int((uint64_t(p.i0 + w / p.n_qb) * p.perm_mul) % uint32_t(p.n_super));
             const int64_t row = int64_t(super) * 256 + row_in_super;
             if (int(threadIdx.x) < NQB) tau_n = __ldcg(p.tau + size_t(w % p.n_qb) * NQB + threadIdx.x);
             if (p.inv_norm && row < p.n_rows) inv_n = __ldg(p.inv_norm + row);
         }
-        int it = 0;
-        for (int64_t w = cluster_id; w < n_work; w += n_clusters, ++it) {
+        for (int it = 0; w >= 0; ++it) {
             const int a = it & 1;
-            const int qb = int(w % p.n_qb);
-            const int super = int((uint64_t(p.i0 + int(w / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
+            const int qb = w % p.n_qb;
+            const int super = int((uint64_t(p.i0 + w / p.n_qb) * p.perm_mul) % uint32_t(p.n_super));
             const int64_t row = int64_t(super) * 256 + row_in_super;
             const bool row_ok = row < p.n_rows;
             const float inv = inv_n;
@@ -228,9 +280,9 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
             float* th = tau_s + a * NQB;
             if (int(threadIdx.x) < NQB) th[threadIdx.x] = tau_n;
             epi_bar_sync<EPI3>();
-            if (w + n_clusters < n_work) {
-                const int64_t w2 = w + n_clusters;
-                const int super2 = int((uint64_t(p.i0 + int(w2 / p.n_qb)) * p.perm_mul) % uint32_t(p.n_super));
+            const int w2 = sched_take(it + 1);  // published one item ahead of the loads: normally waiting already
+            if (w2 >= 0) {
+                const int super2 = int((uint64_t(p.i0 + w2 / p.n_qb) * p.perm_mul) % uint32_t(p.n_super));
                 const int64_t row2 = int64_t(super2) * 256 + row_in_super;
                 if (int(threadIdx.x) < NQB) tau_n = __ldcg(p.tau + size_t(w2 % p.n_qb) * NQB + threadIdx.x);
                 inv_n = (p.inv_norm && row2 < p.n_rows) ? __ldg(p.inv_norm + row2) : 1.f;
@@ -305,7 +357,12 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(a ? te1 : te0);  // this warp is done with the accumulator (leader's barrier)
+            if (lane == 0) {
+                mbar_arrive_cluster(a ? te1 : te0);  // this warp is done with the accumulator (leader's barrier)
+                sched_release(it);                   // ... and with ring slot `it` (slot it + 1 stays held until the next round)
+            }
+            w = w2;
+            if (w < 0 && lane == 0) sched_release(it + 1);  // the terminator's slot
         }
         if (n_stg > 0) flush_staged(stg, n_stg, p.buf, p.cnt, p.cap);
     }
@@ -450,7 +507,7 @@ static uint32_t pick_perm_mul(uint32_t n) {
 
 size_t scan_gemm_workspace_bytes(int n_q, int kprime) {
     const size_t n_pad = size_t((n_q + tc3::NQB_MAX - 1) / tc3::NQB_MAX) * tc3::NQB_MAX;
-    return 3 * n_pad * 4 + size_t(n_q) * size_t(16 * kprime) * 8;
+    return 3 * n_pad * 4 + 16 /* work-item counter */ + size_t(n_q) * size_t(16 * kprime) * 8;
 }
 
 bool scan_gemm_supported(int dim, int kprime, int n_lists) {
@@ -471,19 +528,20 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
     int* cnt = reinterpret_cast<int*>(ws);
     float* tau = reinterpret_cast<float*>(cnt + n_pad);
     int* ovf = reinterpret_cast<int*>(tau + n_pad);
-    unsigned long long* buf = reinterpret_cast<unsigned long long*>(ovf + n_pad);
+    int* sched = ovf + n_pad;  // 16 bytes: the work-item counter of the dynamic scheduler (zeroed before every phase)
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(sched + 4);
 
     gemm_init_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(cnt, tau, ovf, n_q, n_pad);
     TT_LAUNCH_OK("gemm_init_kernel");
 
-    int stages = (tc::SMEM_LIMIT - 1024 - 2 * NQB * 4 - (EPI3 / 32) * STG_CAP * 16 - 256) / (STAGE_BYTES + 16);
+    int stages = (tc::SMEM_LIMIT - 1024 - 2 * NQB * 4 - (EPI3 / 32) * STG_CAP * 16 - 384) / (STAGE_BYTES + 16);
     if (stages > 12) stages = 12;
     if (const char* e = getenv("TT_GEMM_STAGES")) {
         const int want = atoi(e);
         if (want >= 2 && want < stages) stages = want;
     }
     const size_t smem = 1024 + size_t(stages) * STAGE_BYTES + 2 * NQB * 4 + (EPI3 / 32) * STG_CAP * 16 +
-                        (2 * size_t(stages) + 4) * 8 + 16;
+                        (2 * size_t(stages) + 4 + 2 * SCHED_SLOTS) * 8 + 16 + SCHED_SLOTS * 4;
 
     Params p;
     p.inv_norm = inv_norm;
@@ -493,6 +551,11 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
     p.stages = stages;
     p.n_qb = n_qb;
     p.perm_mul = pick_perm_mul(uint32_t(p.n_super));
+    // Static interleave by default.  Measured at 10M rows (profiles/r02_gemm_sweep_*.log): claiming items dynamically
+    // moves 64 queries from 2.97 to 2.95 ms and 4096 x top-100 from 63.4 to 63.1 ms (noise) but costs 128 queries 5 %
+    // (3.22 -> 3.40 ms: the publisher's cluster-scope release sits on the TMA issue path once per item) -- the
+    // clusters of this kernel do not drift apart the way the single-CTA scan's did.  TT_GEMM_DYNAMIC=1 turns it on.
+    p.sched = getenv("TT_GEMM_DYNAMIC") ? sched : nullptr;
     p.tau = tau;
     p.buf = buf;
     p.cnt = cnt;
@@ -531,6 +594,7 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
         if (upto >= p.n_super || p.n_super - upto < next / 2) upto = p.n_super;  // fold a short tail into this phase
         p.i0 = seen;
         p.i1 = upto;
+        if (p.sched) TT_CUDA_OK(cudaMemsetAsync(p.sched, 0, 16, st));
         kern<<<grid, THREADS3, smem, st>>>(map_c, map_q, map_q2, p);
         TT_LAUNCH_OK("scan_gemm_kernel");
         done = upto == p.n_super;

@@ -264,6 +264,38 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Publishing DATA to the peer CTA through a barrier (the dynamic tile scheduler of the cluster kernels: one tile id per
+// work item, microseconds apart -- here the cluster-scope release / acquire pair is affordable and required).
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t cluster_addr, uint32_t v) {
+    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
+}
+// mbar_wait with acquire at cluster scope (pairs with mbar_arrive_cluster_release)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if ((spins & 0xfffu) == 0xfffu) {
+            if (status_raised()) return;
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > status_timeout_cycles()) {
+                status_report(TT_STATUS_RING_TIMEOUT);
+                return;
+            }
+        }
+    }
+}
 // TMA load whose completion is signalled on a barrier that may live in the peer CTA (cta_group::2)
 __device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
                                                  uint32_t bar_cluster_addr, uint64_t policy) {

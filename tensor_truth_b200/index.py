@@ -228,6 +228,10 @@ class DeviceIndex:
                 "cand_thresh": torch.empty((b, 1), dtype=torch.float32, device=dev),
                 "ws": torch.zeros(max(8, int(self.lib.tt_rescore_fused_workspace_bytes(b, kp))), dtype=torch.uint8, device=dev),
                 "gemm_ws": torch.empty(int(self.lib.tt_scan_gemm_workspace_bytes(sl, kp)), dtype=torch.uint8, device=dev),
+                # more than one slice: odd slices run on a side stream with their own candidate buffers, so that one slice's
+                # phase boundaries (drain, per-query cut, launch) are filled by the other slice's GEMM phases
+                "gemm_ws2": (torch.empty(int(self.lib.tt_scan_gemm_workspace_bytes(sl, kp)), dtype=torch.uint8, device=dev)
+                             if b > sl and not os.environ.get("TT_GEMM_ONE_STREAM") else None),
                 "keys": torch.empty((b, k), dtype=torch.float32, device=dev),
                 "scores": torch.empty((b, k), dtype=torch.float32, device=dev),
                 "ids": torch.empty((b, k), dtype=torch.int64, device=dev),
@@ -344,13 +348,29 @@ class DeviceIndex:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             if gemm:  # the tensor-bound regime: GEMM-shaped scan, one shortlist per query, GEMM_SLICE queries per corpus pass
-                for a in range(0, b, w["slice"]):
+                ws2 = w.get("gemm_ws2")
+                side = None
+                if ws2 is not None:  # fork: odd slices go to a side stream (joined below)
+                    side = self._ws.get("side_stream")
+                    if side is None:
+                        side = self._ws["side_stream"] = torch.cuda.Stream(self.device)
+                    cur = torch.cuda.current_stream(self.device)
+                    fork = torch.cuda.Event()
+                    fork.record(cur)
+                    side.wait_event(fork)
+                for i, a in enumerate(range(0, b, w["slice"])):
                     n = min(w["slice"], b - a)
+                    odd = side is not None and (i & 1)
+                    gws = ws2 if odd else w["gemm_ws"]
                     check(L.tt_scan_gemm_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus),
                                                    ptr(self.inv_norm), ptr(w["q_hi"][a:]), None if hi_only else ptr(w["q_lo"][a:]), n,
                                                    n_cand, self.id_base,
                                                    ptr(w["cand_ids"][a:]), ptr(w["cand_approx"][a:]), ptr(w["cand_thresh"][a:]),
-                                                   ptr(w["gemm_ws"]), w["gemm_ws"].numel(), st))
+                                                   ptr(gws), gws.numel(), side.cuda_stream if odd else st))
+                if side is not None:  # join
+                    join = torch.cuda.Event()
+                    join.record(side)
+                    cur.wait_event(join)
             else:
                 check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus), ptr(self.inv_norm),
                                           ptr(w["q_hi"]), None if hi_only else ptr(w["q_lo"]), b, kprime, self.id_base,

@@ -70,7 +70,8 @@ def test_push_merge_automerge_matches_oracle(two_shards, b, k):
         torch.cuda.synchronize()
         for r in (1, 0):  # rank 1 first: rank 0's merge must really wait for a flag raised by another stream
             with torch.cuda.stream(streams[r]):
-                w = dict(shards[r]._buffers(b, k, slot=("t", lane)))
+                # top-100 needs deeper per-CTA lists than the index default of 32 to be certifiable (the bench does the same)
+                w = dict(shards[r]._buffers(b, k, slot=("t", lane), hi_only=False, kprime=128 if k > 32 else None))
                 w["margin"] = margins[r]
                 shards[r].search(qd, k, out=w, xchg=pbs[r].desc(lane))
         for r in (0, 1):
