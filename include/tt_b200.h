@@ -55,6 +55,9 @@ extern "C" {
  */
 #define TT_STATUS_RING_TIMEOUT 1u
 #define TT_STATUS_EXCHANGE_TIMEOUT 2u /* bits 8..15: the source rank that was waited for */
+/* cudaStreamSynchronize(stream) for hosts that hold nothing but the raw handle (the Python binding: one foreign call
+ * that releases the interpreter lock, instead of an event record + an event wait through PyTorch). */
+int tt_stream_synchronize(void* stream);
 int tt_status_configure(uint32_t* mapped_word_host, int timeout_ms);
 int tt_status_read(uint32_t* out_host, int clear);
 
@@ -193,11 +196,24 @@ int tt_rescore_topk(const void* corpus, int corpus_dtype, int64_t n_rows, int di
  * Same outputs as tt_rescore_topk (no margin: the result is exact by construction).
  * ws >= tt_scan_exact_workspace_bytes(device, n_q, k).
  */
+/*
+ * ROW GATE (metadata filters; reference: _build_metadata_filters, rag_engine.py:301-365 -> the
+ * `filters=` of index.as_retriever): a search restricted to a subset of the rows passes an inv_norm array in which the
+ * excluded rows hold NaN.  Every stage-1 variant then never shortlists them (a NaN score passes no comparison; the
+ * certificate's thresholds bound the dropped ELIGIBLE rows only), and tt_scan_exact_f64_gated -- the exact scan computes
+ * its own norms -- reads the same array as `row_gate` just for that test.  NULL = every row is eligible.
+ */
 size_t tt_scan_exact_workspace_bytes(int device, int n_q, int k);
 int tt_scan_exact_f64(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
                       int64_t id_base, const float* q_f32, int n_q, int k, int score_mode,
                       float* out_keys, float* out_scores, int64_t* out_ids,
                       void* ws, size_t ws_bytes, void* stream);
+
+int tt_scan_exact_f64_gated(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                            int64_t id_base, const float* q_f32, int n_q, int k, int score_mode,
+                            const float* row_gate /* [n_rows], NaN = excluded; nullable */,
+                            float* out_keys, float* out_scores, int64_t* out_ids,
+                            void* ws, size_t ws_bytes, void* stream);
 
 /*
  * k-way merge of per-shard top-k lists after the all-gather (row-sharded corpus).

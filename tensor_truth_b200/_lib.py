@@ -25,6 +25,7 @@ _P, _I, _L, _Z, _D = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
 SIGNATURES = {
     "tt_version": (_I, []),
     "tt_last_error": (C.c_char_p, []),
+    "tt_stream_synchronize": (_I, [_P]),
     "tt_status_configure": (_I, [_P, _I]),
     "tt_status_read": (_I, [_P, _I]),
     "tt_scan_num_lists": (_I, [_I]),
@@ -39,6 +40,7 @@ SIGNATURES = {
     "tt_rescore_topk": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "tt_scan_exact_workspace_bytes": (_Z, [_I, _I, _I]),
     "tt_scan_exact_f64": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _I, _I, _P, _P, _P, _P, _Z, _P]),
+    "tt_scan_exact_f64_gated": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P]),
     "tt_merge_topk": (_I, [_P, _P, _I, _L, _L, _I, _I, _I, _I, _P, _P, _P]),
     "tt_rescore_topk_push": (_I, [_P, _I, _L, _I, _L, _L, _P, _I, _P, _I, _P, _I, _I, _I, _P, _P, _P, _P, _P, _Z, _P, _P, _P]),
     "tt_exchange_push": (_I, [_P, _Z, _P, _P]),

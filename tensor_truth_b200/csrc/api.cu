@@ -14,7 +14,8 @@ int scan_simt_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride
                      const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
                      float* out_approx, float* out_thresh, int n_lists, cudaStream_t st);
 int scan_simt_exact(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t stride, const float* q_f32,
-                    int n_q, int kprime, int64_t id_base, int mode, uint64_t* out_packed, int n_lists, cudaStream_t st);
+                    int n_q, int kprime, int64_t id_base, int mode, uint64_t* out_packed, int n_lists, cudaStream_t st,
+                    const float* row_gate);
 bool scan_tc_supported(int64_t n_rows, int dim, int64_t stride, int kprime, const void* corpus);
 int scan_tc_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
                    const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
@@ -88,6 +89,12 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) on = getenv("TT_PDL") ? 1 : 0;  // opt-in until measured
+    return on == 1;
 }
 
 int current_device() {
@@ -167,6 +174,11 @@ int tt_status_read(uint32_t* out_host, int clear) {
         return TT_ERR_CUDA;
     }
     *out_host = v;
+    return TT_OK;
+}
+
+int tt_stream_synchronize(void* stream) {
+    TT_CUDA_OK(cudaStreamSynchronize(TT_STREAM(stream)));
     return TT_OK;
 }
 
@@ -400,6 +412,13 @@ size_t tt_scan_exact_workspace_bytes(int device, int n_q, int k) {
 int tt_scan_exact_f64(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
                       int64_t id_base, const float* q_f32, int n_q, int k, int score_mode, float* out_keys,
                       float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes, void* stream) {
+    return tt_scan_exact_f64_gated(corpus, corpus_dtype, n_rows, dim, row_stride_elems, id_base, q_f32, n_q, k, score_mode,
+                                   nullptr, out_keys, out_scores, out_ids, ws, ws_bytes, stream);
+}
+
+int tt_scan_exact_f64_gated(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t row_stride_elems,
+                            int64_t id_base, const float* q_f32, int n_q, int k, int score_mode, const float* row_gate,
+                            float* out_keys, float* out_scores, int64_t* out_ids, void* ws, size_t ws_bytes, void* stream) {
     TT_CHECK_ARG(corpus_dtype == TT_DTYPE_BF16 || corpus_dtype == TT_DTYPE_F32, "tt_scan_exact_f64: dtype %d", corpus_dtype);
     TT_CHECK_ARG(score_mode == TT_SCORE_COSINE || score_mode == TT_SCORE_CHROMA_L2_EXP, "tt_scan_exact_f64: score_mode %d",
                  score_mode);
@@ -425,7 +444,7 @@ int tt_scan_exact_f64(const void* corpus, int corpus_dtype, int64_t n_rows, int 
     }
     uint64_t* packed = reinterpret_cast<uint64_t*>(ws);
     int rc = scan_simt_exact(corpus, corpus_dtype, n_rows, dim, row_stride_elems, q_f32, n_q, kp, id_base, score_mode,
-                             packed, n_lists, TT_STREAM(stream));
+                             packed, n_lists, TT_STREAM(stream), row_gate);
     if (rc) return rc;
     return launch_select(packed, n_lists * kp, nullptr, nullptr, 0, 0, 0, n_q, 0, k, score_mode, nullptr, 0, out_keys,
                          out_scores, out_ids, nullptr, TT_STREAM(stream));

@@ -17,6 +17,7 @@ __global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __res
                                                               __nv_bfloat16* __restrict__ q_hi,
                                                               __nv_bfloat16* __restrict__ q_lo) {
     __shared__ double red[8];
+    pdl_launch_dependents();  // the scan may become resident now: all it needs from this kernel it waits for (pdl_wait)
     const float* qb = q + size_t(blockIdx.x) * dim;
     double a = 0.0;
     for (int d = threadIdx.x; d < dim; d += blockDim.x) { double v = qb[d]; a += v * v; }
@@ -495,6 +496,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const SelArgs a) {
 
 template <int THREADS, int EPT>
 __global__ void __launch_bounds__(THREADS) select_small_kernel(const SelArgs a) {
+    pdl_wait();  // (a merge launched as a programmatic dependent of the pushing kernel: its local outputs are read below)
     select_small_body<THREADS, EPT>(a, blockIdx.x, gridDim.x);
 }
 // the 1024 x 8 shape: 40 registers is what lets a block become resident next to a scan CTA (40 K + 24 K of 64 K)
@@ -520,6 +522,8 @@ __global__ void __launch_bounds__(SMALL ? FUSED_SMALL_THREADS : SEL_THREADS) res
     __shared__ unsigned sh_last;
     const int b = blockIdx.y, lane = threadIdx.x & 31;
     const int n_cand = a.n_in;
+    pdl_launch_dependents();
+    pdl_wait();
     const float* qb = q + size_t(b) * dim;
     constexpr int WARPS = (SMALL ? FUSED_SMALL_THREADS : SEL_THREADS) / 32;
     for (int c = int(blockIdx.x) * WARPS + int(threadIdx.x >> 5); c < n_cand; c += int(gridDim.x) * WARPS) {
@@ -583,6 +587,8 @@ __global__ void __launch_bounds__(S2_THREADS) stage2_prefilter_kernel(const S2Sr
     __shared__ int sh_n;
     const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n_cand = a.n_in, k = a.k;
+    pdl_launch_dependents();  // (row-sharded: the merging kernel may become resident)
+    pdl_wait();               // everything below reads what the scan wrote
     const XNow now = xchg_now(a.x, a.x.push_world > 0);
     const int64_t* ids = r.cand_ids + size_t(b) * n_cand;
     const float* apx = r.cand_approx + size_t(b) * n_cand;
@@ -837,8 +843,8 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
     do {                                                                                                                     \
         auto kern = rescore_select_kernel<CT, SM>;                                                                           \
         if (!(SM)) TT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_CHUNK * int(sizeof(uint64_t)))); \
-        kern<<<grid, threads, smem, st>>>(reinterpret_cast<const CT*>(rs->corpus), rs->n_rows, rs->dim, rs->stride,          \
-                                              rs->id_base, rs->q, rs->cand_ids, rs->packed, rs->tickets, a);                 \
+        TT_CUDA_OK(launch_kernel(kern, grid, dim3(threads), smem, st, true, reinterpret_cast<const CT*>(rs->corpus), rs->n_rows, \
+                                 rs->dim, rs->stride, rs->id_base, rs->q, rs->cand_ids, rs->packed, rs->tickets, a));         \
     } while (0)
         if (bf16 && small) TT_RS(__nv_bfloat16, true);
         else if (bf16) TT_RS(__nv_bfloat16, false);
@@ -849,8 +855,9 @@ int launch_select(const uint64_t* packed, int n_in, const float* in_keys, const 
         return TT_OK;
     }
     if (small) {
-        if (!packed && total <= 512) select_small_kernel<512, 1><<<n_q, 512, 0, st>>>(a);
-        else if (!packed && total <= 1024) select_small_kernel<512, 2><<<n_q, 512, 0, st>>>(a);
+        const bool dep = a.x.wait_world > 0;  // the shard merge follows the pushing kernel in its stream
+        if (!packed && total <= 512) TT_CUDA_OK(launch_kernel(select_small_kernel<512, 1>, dim3(n_q), dim3(512), 0, st, dep, a));
+        else if (!packed && total <= 1024) TT_CUDA_OK(launch_kernel(select_small_kernel<512, 2>, dim3(n_q), dim3(512), 0, st, dep, a));
         else select_small_kernel_1024<<<n_q, SEL_THREADS, 0, st>>>(a);
         TT_LAUNCH_OK("select_small_kernel");
         return TT_OK;
@@ -892,8 +899,8 @@ int launch_stage2_prefilter(const void* corpus, int dtype, int64_t n_rows, int d
     a.out_ids = out_ids;
     a.out_margin = out_margin;
     S2Src r{corpus, n_rows, dim, stride, id_base, q, cand_ids, cand_approx, window};
-    if (dtype == TT_DTYPE_BF16) stage2_prefilter_kernel<__nv_bfloat16><<<n_q, S2_THREADS, 0, st>>>(r, a);
-    else stage2_prefilter_kernel<float><<<n_q, S2_THREADS, 0, st>>>(r, a);
+    if (dtype == TT_DTYPE_BF16) TT_CUDA_OK(launch_kernel(stage2_prefilter_kernel<__nv_bfloat16>, dim3(n_q), dim3(S2_THREADS), 0, st, true, r, a));
+    else TT_CUDA_OK(launch_kernel(stage2_prefilter_kernel<float>, dim3(n_q), dim3(S2_THREADS), 0, st, true, r, a));
     TT_LAUNCH_OK("stage2_prefilter_kernel");
     return TT_OK;
 }

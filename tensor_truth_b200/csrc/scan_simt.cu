@@ -141,8 +141,12 @@ scan_simt_kernel(const CT* __restrict__ corpus, int64_t n_rows, int dim, int64_t
                 }
             }
         }
+        // inv_norm doubles as the ROW GATE: a row whose entry is NaN does not exist for this search (metadata filters).
+        // The approximate scan inherits that from the arithmetic (NaN scores are never inserted); the exact scan, which
+        // computes its own norms, reads the array only for the gate.
         float in0 = 1.f, in1 = 1.f;
-        if (!EXACT && inv_norm) { in0 = inv_norm[r0]; in1 = inv_norm[has1 ? r1 : r0]; }
+        if (inv_norm) { in0 = inv_norm[r0]; in1 = inv_norm[has1 ? r1 : r0]; }
+        const bool ok0 = in0 == in0, ok1 = has1 && in1 == in1;
         if (EXACT) { nn0 = Acc(warp_sum_f64(double(nn0))); nn1 = Acc(warp_sum_f64(double(nn1))); }
 #pragma unroll
         for (int qi = 0; qi < QT; ++qi) {
@@ -156,8 +160,8 @@ scan_simt_kernel(const CT* __restrict__ corpus, int64_t n_rows, int dim, int64_t
                 k1 = warp_sum_f32(float(dot1[qi])) * in1;
             }
             if (qi < nq_here) {
-                lists[qi].insert(pack_entry(k0, uint32_t(r0)));
-                if (has1) lists[qi].insert(pack_entry(k1, uint32_t(r1)));
+                if (ok0) lists[qi].insert(pack_entry(k0, uint32_t(r0)));
+                if (ok1) lists[qi].insert(pack_entry(k1, uint32_t(r1)));
             }
         }
     }
@@ -245,10 +249,10 @@ int scan_simt_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride
 
 int scan_simt_exact(const void* corpus, int corpus_dtype, int64_t n_rows, int dim, int64_t stride,
                     const float* q_f32, int n_q, int kprime, int64_t id_base, int mode,
-                    uint64_t* out_packed, int n_lists, cudaStream_t st) {
+                    uint64_t* out_packed, int n_lists, cudaStream_t st, const float* row_gate) {
     const int E = kprime_to_E(kprime);
 #define TT_SIMT_X(EE, CT)                                                                                       \
-    return launch_simt<EE, 1, CT, double, true>(corpus, n_rows, dim, stride, nullptr, nullptr, nullptr, q_f32, n_q, \
+    return launch_simt<EE, 1, CT, double, true>(corpus, n_rows, dim, stride, row_gate, nullptr, nullptr, q_f32, n_q, \
                                                 id_base, mode, nullptr, nullptr, nullptr, out_packed, n_lists, st)
     if (corpus_dtype == TT_DTYPE_BF16) {
         if (E == 1) TT_SIMT_X(1, __nv_bfloat16);

@@ -87,6 +87,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int steps_per_tile = p.n_chunks / CH;
     constexpr int TMEM_COLS = (2 * N < 32) ? 32 : 2 * N;  // power of two for N in {16, 32, 64}
+    pdl_launch_dependents();  // stage 2 may become resident next to this CTA (tt_common.cuh, PDL); it waits for this grid to end
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -122,6 +123,7 @@ scan_tc_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constant_
     if (warp == 4) {
         // ===================================================== TMA producer
         if (lane == 0) {
+            pdl_wait();  // launched as a programmatic dependent of prepare_queries: q_hi / q_lo are complete from here on
             mbar_expect_tx(smem_u32(q_full), uint32_t(p.n_chunks * N * 128));
             for (int c = 0; c < p.n_chunks; ++c) {
                 tma_load_3d(smem_u32(q_s + size_t(c) * N * 128), &map_qhi, 0, p.q0, c, smem_u32(q_full), POLICY_EVICT_LAST);
@@ -369,7 +371,8 @@ static int launch(const void* corpus, int64_t n_rows, int dim, int64_t stride, c
     for (int q0 = 0; q0 < n_q; q0 += NQ) {
         p.q0 = q0;
         p.nq_here = (n_q - q0 < NQ) ? n_q - q0 : NQ;
-        kern<<<n_lists, THREADS, smem, st>>>(map_c, map_qhi, map_qlo, p);
+        // only the first pass may overlap its predecessor (prepare_queries): later passes share the scheduler counters
+        TT_CUDA_OK(launch_kernel(kern, dim3(n_lists), dim3(THREADS), smem, st, q0 == 0, map_c, map_qhi, map_qlo, p));
         TT_LAUNCH_OK("scan_tc_kernel");
     }
     return TT_OK;

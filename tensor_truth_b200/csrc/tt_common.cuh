@@ -32,6 +32,26 @@ int current_device();
         }                                                                                      \
     } while (0)
 
+#ifdef __CUDACC__
+// kernel<<<grid, block, smem, st>>>(args...) with the PDL attribute when `dependent` (and not switched off: TT_NO_PDL)
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool dependent,
+                                 Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (dependent && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #define TT_LAUNCH_OK(what)                                                                     \
     do {                                                                                       \
         cudaError_t _e = cudaGetLastError();                                                   \
@@ -108,6 +128,16 @@ static inline int status_read_tu(unsigned* out, bool clear) {
     *out |= v;
     return 0;
 }
+
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// The three / four kernels of a query form a strict chain (prepare -> scan -> stage 2 [-> merge]).  Launched with the
+// programmatic-stream-serialization attribute, a kernel may become resident while its predecessor still runs; it then
+// blocks in pdl_wait() -- which returns once the predecessor grid has completed and its writes are visible -- right
+// before it first touches the predecessor's output.  What that buys: the dependent's launch latency, and for the scan
+// everything that does not need the prepared queries (barrier init, TMEM allocation), disappear from the latency chain.
+// Both instructions are no-ops in a kernel that was launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // every translation unit whose kernels can wait defines its pair of hooks with this (api.cu calls them all)
 #define TT_DEFINE_STATUS_HOOKS(tu)                                                                        \

@@ -307,25 +307,41 @@ class DeviceIndex:
                                              C.byref(am) if am is not None else None, ptr(w["cand_approx"]), window,
                                              self._stream()))
 
+    def row_filter(self, eligible, key=None):
+        """A ``filters.RowFilter`` for this index (bool ``[n_rows]`` eligibility -> gated ``inv_norm`` in HBM), cached by
+        ``key`` when one is given (e.g. a canonical form of the filter)."""
+        from .filters import RowFilter
+
+        if key is not None:
+            hit = self._ws.get(("row_filter", key))
+            if hit is not None:
+                return hit
+        rf = RowFilter(self, eligible, key)
+        if key is not None:
+            self._ws[("row_filter", key)] = rf
+        return rf
+
     def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None, hi_only: Optional[bool] = None,
-               xchg=None, am=None) -> SearchResult:
+               xchg=None, am=None, row_filter=None) -> SearchResult:
         """Shortlist scan + exact re-score.  Asynchronous on the current stream; ``margin[b] > result.eps``
         certifies that query b's top-k is the exact one (``search_certified`` acts on it).
         ``hi_only``: send the queries through the tensor cores as bf16 hi halves only (twice the queries per
         corpus pass, wider certificate); default: batches above ``HI_ONLY_ABOVE``.
         ``xchg`` (``_lib.Exchange``): row-sharded corpus -- the selecting kernel also pushes this shard's top-k
         record to every peer rank (sharded.py).
-        ``am`` (``_am_args``): single shard -- the selecting kernel also auto-merges the list it selected."""
+        ``am`` (``_am_args``): single shard -- the selecting kernel also auto-merges the list it selected.
+        ``row_filter`` (``filters.RowFilter``): only the rows it admits exist for this search (metadata filters)."""
         q = self._check_queries(q)
         b = int(q.shape[0])
         if hi_only is None:
             hi_only = b > HI_ONLY_ABOVE
         w = out if out is not None else self._buffers(b, k, hi_only=hi_only)
+        inv_norm = row_filter.inv_norm if row_filter is not None else self.inv_norm
         l2 = self.score_mode != SCORE_COSINE
         if l2 and not (self.norm_lo > 0.0 and self.norm_hi <= 1.05 * self.norm_lo):
             # chroma_l2_exp on rows of clearly unequal norm: cosine order says little about squared-L2 order, the
             # certificate below would refuse every query -- let the exact fp64 scan answer directly.
-            ex = self.search_exact(q, k, out=w)
+            ex = self.search_exact(q, k, out=w, row_filter=row_filter)
             w["margin"].fill_(float("inf"))
             if xchg is not None:
                 raise ValueError("chroma_l2_exp over a row-sharded corpus needs (near-)equal row norms")
@@ -363,7 +379,7 @@ class DeviceIndex:
                     odd = side is not None and (i & 1)
                     gws = ws2 if odd else w["gemm_ws"]
                     check(L.tt_scan_gemm_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus),
-                                                   ptr(self.inv_norm), ptr(w["q_hi"][a:]), None if hi_only else ptr(w["q_lo"][a:]), n,
+                                                   ptr(inv_norm), ptr(w["q_hi"][a:]), None if hi_only else ptr(w["q_lo"][a:]), n,
                                                    n_cand, self.id_base,
                                                    ptr(w["cand_ids"][a:]), ptr(w["cand_approx"][a:]), ptr(w["cand_thresh"][a:]),
                                                    ptr(gws), gws.numel(), side.cuda_stream if odd else st))
@@ -372,7 +388,7 @@ class DeviceIndex:
                     join.record(side)
                     cur.wait_event(join)
             else:
-                check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus), ptr(self.inv_norm),
+                check(L.tt_scan_topk_bf16(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus), ptr(inv_norm),
                                           ptr(w["q_hi"]), None if hi_only else ptr(w["q_lo"]), b, kprime, self.id_base,
                                           self.variant,
                                           ptr(w["cand_ids"]), ptr(w["cand_approx"]), ptr(w["cand_thresh"]),
@@ -384,7 +400,8 @@ class DeviceIndex:
         # cosine: proven iff margin > eps;  L2: the bound already contains eps, proven iff margin > 0
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if l2 else eps, bool(hi_only))
 
-    def search_exact(self, q: torch.Tensor, k: int, out: Optional[dict] = None, rows: Optional[tuple] = None) -> SearchResult:
+    def search_exact(self, q: torch.Tensor, k: int, out: Optional[dict] = None, rows: Optional[tuple] = None,
+                     row_filter=None) -> SearchResult:
         """fp64 scoring of every row (CUDA cores): certificate-failure fallback, the chroma_l2_exp path and the
         on-GPU secondary oracle.  ``rows = (lo, hi)`` restricts the scan to that local row range (one segment)."""
         q = self._check_queries(q)
@@ -401,23 +418,24 @@ class DeviceIndex:
         with torch.cuda.device(dev):
             nbytes = int(self.lib.tt_scan_exact_workspace_bytes(dev.index or 0, b, k))
             ws = torch.empty(max(1, nbytes), dtype=torch.uint8, device=dev)
-            check(self.lib.tt_scan_exact_f64(ptr(src[lo:hi]), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
-                                             hi - lo, self.dim, self._row_stride(src), self.id_base + lo, ptr(q), b, k,
-                                             self.score_mode, ptr(keys), ptr(scores), ptr(ids), ptr(ws), ws.numel(),
-                                             self._stream()))
+            gate = ptr(row_filter.inv_norm[lo:hi]) if row_filter is not None else None
+            check(self.lib.tt_scan_exact_f64_gated(ptr(src[lo:hi]), _lib.DTYPE_F32 if self.master is not None else _lib.DTYPE_BF16,
+                                                   hi - lo, self.dim, self._row_stride(src), self.id_base + lo, ptr(q), b, k,
+                                                   self.score_mode, gate, ptr(keys), ptr(scores), ptr(ids), ptr(ws), ws.numel(),
+                                                   self._stream()))
         return SearchResult(keys, scores, ids, None)
 
-    def search_certified(self, q: torch.Tensor, k: int) -> SearchResult:
+    def search_certified(self, q: torch.Tensor, k: int, row_filter=None) -> SearchResult:
         """``search`` + certificate check (one device->host read of the margins); queries that are not
-        proven exact are re-run through ``search_exact``.  Synchronises the current stream."""
+        proven exact climb the repair ladder.  Synchronises the current stream."""
         q = self._check_queries(q)
-        r = self.search(q, k)
+        r = self.search(q, k, row_filter=row_filter)
         bad = torch.nonzero(~(r.margin > r.eps)).flatten()  # NaN-safe
         if bad.numel():
-            self._repair(q, k, r, bad, hi_lo_first=r.hi_only)
+            self._repair(q, k, r, bad, hi_lo_first=r.hi_only, row_filter=row_filter)
         return r
 
-    def _rescan(self, q, k, r: SearchResult, bad: torch.Tensor, kprime: Optional[int]) -> torch.Tensor:
+    def _rescan(self, q, k, r: SearchResult, bad: torch.Tensor, kprime: Optional[int], row_filter=None) -> torch.Tensor:
         """Re-run the queries ``bad`` hi+lo (optionally with deeper per-CTA shortlists), copy the ones that are now proven
         into ``r`` and return the indices still unproven.  The sub-batch is padded to a power of two (repeating its
         last query) so that a long-lived service keeps a handful of repair workspaces, not one per failure count."""
@@ -425,7 +443,8 @@ class DeviceIndex:
         n_pad = 1 << max(0, n_bad - 1).bit_length()
         sel = bad if n_pad == n_bad else torch.cat([bad, bad[-1:].expand(n_pad - n_bad)])
         sub = q.index_select(0, sel)
-        r2 = self.search(sub, k, out=dict(self._buffers(n_pad, k, slot=-1, hi_only=False, kprime=kprime)), hi_only=False)
+        r2 = self.search(sub, k, out=dict(self._buffers(n_pad, k, slot=-1, hi_only=False, kprime=kprime)), hi_only=False,
+                         row_filter=row_filter)
         ok = (r2.margin > r2.eps)[:n_bad]
         good = bad[ok]
         if good.numel():
@@ -434,20 +453,20 @@ class DeviceIndex:
             r.ids.index_copy_(0, good, r2.ids[:n_bad][ok])
         return bad[~ok]
 
-    def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool) -> None:
+    def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool, row_filter=None) -> None:
         """Queries whose certificate failed climb a ladder: (a hi-only batch first gets the tighter hi+lo scan,) then a
         hi+lo re-scan with the deepest per-CTA shortlists the kernel has (K' = 128: many near-ties of the k-th score
         inside one CTA's share of the corpus are what defeats a short list), then the exact fp64 scan."""
         if hi_lo_first and bad.numel():
             self.retries += int(bad.numel())
-            bad = self._rescan(q, k, r, bad, None)
+            bad = self._rescan(q, k, r, bad, None, row_filter)
         deep = int(self.lib.tt_scan_max_kprime())
         if bad.numel() and self.kprime < deep and not os.environ.get("TT_NO_DEEP_RUNG"):
             self.deep_rescans += int(bad.numel())
-            bad = self._rescan(q, k, r, bad, deep)
+            bad = self._rescan(q, k, r, bad, deep, row_filter)
         if bad.numel():
             self.fallbacks += int(bad.numel())
-            ex = self.search_exact(q.index_select(0, bad), k)
+            ex = self.search_exact(q.index_select(0, bad), k, row_filter=row_filter)
             r.keys.index_copy_(0, bad, ex.keys)
             r.scores.index_copy_(0, bad, ex.scores)
             r.ids.index_copy_(0, bad, ex.ids)
@@ -575,18 +594,20 @@ class DeviceIndex:
         finally:
             _CAPTURE_LOCK.release()
 
-    def retrieve_host(self, q_host: torch.Tensor, k: int, ratio_thresh: float = 0.5, merge: bool = True):
+    def retrieve_host(self, q_host: torch.Tensor, k: int, ratio_thresh: float = 0.5, merge: bool = True, row_filter=None):
         """Query embeddings in host memory -> merged ``(ids, scores, lens)`` in host memory (numpy).
         The H2D copy of the queries and the single D2H read of the result record are part of the call;
-        the certificate is checked on the host from the margins in that record."""
+        the certificate is checked on the host from the margins in that record.  ``row_filter``: a metadata filter
+        resolved by ``row_filter()`` (such calls take the eager pipeline: the captured graph reads the ungated norms)."""
         merged = bool(merge and self.tree is not None)
         if int(q_host.shape[0]) > MAX_HOST_BATCH:  # bound the workspaces: large batches go through in slices
-            parts = [self.retrieve_host(q_host[i:i + MAX_HOST_BATCH], k, ratio_thresh, merge)
+            parts = [self.retrieve_host(q_host[i:i + MAX_HOST_BATCH], k, ratio_thresh, merge, row_filter)
                      for i in range(0, int(q_host.shape[0]), MAX_HOST_BATCH)]
             return tuple(np.concatenate([p[j] for p in parts], axis=0) for j in range(3))
         with self._lock:
             b = int(q_host.shape[0])
-            g = self._pipeline_graph(b, k, ratio_thresh, merged) if (q_host.dim() == 2 and q_host.shape[1] == self.dim) else None
+            g = (self._pipeline_graph(b, k, ratio_thresh, merged)
+                 if (row_filter is None and q_host.dim() == 2 and q_host.shape[1] == self.dim) else None)
             if g is not None:
                 if q_host.dtype == torch.float32 and q_host.device.type == "cpu":
                     g["q_pin_np"][...] = q_host.numpy()  # the common case: a plain memory copy into the pinned staging buffer
@@ -607,19 +628,17 @@ class DeviceIndex:
                 if not merged:
                     w["ids"], w["scores"] = d["ids"], d["scores"]
                 am = self._am_args(ratio_thresh, MergeResult(d["ids"], d["scores"], d["lens"])) if merged else None
-                r = self.search(q, k, out=w, am=am)
+                r = self.search(q, k, out=w, am=am, row_filter=row_filter)
                 rec["host"].copy_(rec["dev"], non_blocking=True)
-            rec["event"].record()
-            rec["event"].synchronize()
-            _lib.check_status(self._dev_index)
+            check(self.lib.tt_stream_synchronize(self._stream()))  # one GIL-releasing call (an event record + wait through
+            _lib.check_status(self._dev_index)                     # PyTorch costs ~15 us of Python per query)
             bad = np.nonzero(~(h["margin"] > r.eps))[0]
             if bad.size:  # not proven exact: re-run those queries (tighter scan, then the exact fp64 scan)
-                self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only)
+                self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only, row_filter=row_filter)
                 if merged:
                     self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
                 rec["host"].copy_(rec["dev"], non_blocking=True)
-                rec["event"].record()
-                rec["event"].synchronize()
+                check(self.lib.tt_stream_synchronize(self._stream()))
                 _lib.check_status(self._dev_index)
             ids, scores = h["ids"].copy(), h["scores"].astype(np.float64)
             lens = h["lens"].copy() if merged else (ids >= 0).sum(axis=1).astype(np.int32)

@@ -93,12 +93,28 @@ class B200VectorIndexRetriever(_RetrieverBase):
     """``index.as_retriever(similarity_top_k=k)``: exact top-k leaves of the index for the query."""
 
     def __init__(self, index, similarity_top_k: int = 10, embed_model: Any = None,
-                 node_table: Optional[NodeTable] = None):
-        """``index``: a ``DeviceIndex``, or a ``ShardedIndex`` (row-sharded over GPUs; every rank then makes the same calls)."""
+                 node_table: Optional[NodeTable] = None, filters: Any = None,
+                 leaf_metadata: Optional[Sequence[Optional[dict]]] = None):
+        """``index``: a ``DeviceIndex``, or a ``ShardedIndex`` (row-sharded over GPUs; every rank then makes the same calls).
+        ``filters``: what ``index.as_retriever(..., filters=...)`` takes upstream -- a LlamaIndex ``MetadataFilters`` or the
+        reference's filter-spec dict (``_build_metadata_filters``, rag_engine.py:301-365); evaluated once, here, over
+        ``leaf_metadata`` (one dict per corpus row; default: the ``.metadata`` of the node table's leaves) and applied
+        to every search as a row gate (filters.py).  Single-GPU indexes only."""
         self.index = index
         self.similarity_top_k = int(similarity_top_k)
         self.embed_model = embed_model
         self.node_table = node_table or NodeTable(node_ids=getattr(index.tree, "node_ids", None) if index.tree else None)
+        self.row_filter = None
+        if filters is not None:
+            from .filters import clauses_from_filters, eligible_rows
+
+            clauses = clauses_from_filters(filters)
+            if clauses:
+                if not hasattr(index, "row_filter"):
+                    raise ValueError("metadata filters need a single-GPU DeviceIndex")
+                if leaf_metadata is None:
+                    leaf_metadata = [getattr(self.node_table(o), "metadata", None) for o in range(index.n_rows)]
+                self.row_filter = index.row_filter(eligible_rows(filters, leaf_metadata), key=repr(sorted(map(repr, clauses))))
 
     def _query_tensor(self, query_bundle: QueryBundle) -> torch.Tensor:
         emb = query_bundle.embedding
@@ -123,7 +139,8 @@ class B200VectorIndexRetriever(_RetrieverBase):
         return torch.as_tensor(np.asarray(emb, dtype=np.float32)).reshape(1, -1)
 
     def _retrieve(self, query_bundle: QueryBundle) -> List[NodeWithScore]:
-        ids, scores, lens = self.index.retrieve_host(self._query_tensor(query_bundle), self.similarity_top_k, merge=False)
+        kw = {"row_filter": self.row_filter} if self.row_filter is not None else {}
+        ids, scores, lens = self.index.retrieve_host(self._query_tensor(query_bundle), self.similarity_top_k, merge=False, **kw)
         return [NodeWithScore(node=self.node_table(int(o)), score=float(s))
                 for o, s in zip(ids[0, :lens[0]], scores[0, :lens[0]])]
 
@@ -150,8 +167,10 @@ class B200AutoMergingRetriever(_RetrieverBase):
 
     def _retrieve(self, query_bundle: QueryBundle) -> List[NodeWithScore]:
         q = self._vector_retriever._query_tensor(query_bundle)
+        rf = self._vector_retriever.row_filter
+        kw = {"row_filter": rf} if rf is not None else {}
         ids, scores, lens = self.index.retrieve_host(q, self._vector_retriever.similarity_top_k,
-                                                     self._simple_ratio_thresh, merge=True)
+                                                     self._simple_ratio_thresh, merge=True, **kw)
         if lens[0] < 0:
             raise RuntimeError("auto-merge output overflow")
         return self._wrap(ids[0], scores[0], int(lens[0]))
@@ -159,8 +178,10 @@ class B200AutoMergingRetriever(_RetrieverBase):
     # ---- batch extension (not in the reference; what the bench drives)
     def retrieve_batch(self, embeddings) -> List[List[NodeWithScore]]:
         q = torch.as_tensor(np.asarray(embeddings, dtype=np.float32)) if not torch.is_tensor(embeddings) else embeddings
+        rf = self._vector_retriever.row_filter
+        kw = {"row_filter": rf} if rf is not None else {}
         ids, scores, lens = self.index.retrieve_host(q, self._vector_retriever.similarity_top_k,
-                                                     self._simple_ratio_thresh, merge=True)
+                                                     self._simple_ratio_thresh, merge=True, **kw)
         if (lens < 0).any():
             raise RuntimeError("auto-merge output overflow")
         return [self._wrap(ids[b], scores[b], int(lens[b])) for b in range(ids.shape[0])]

@@ -72,11 +72,12 @@ class SegmentedIndex(DeviceIndex):
 
     # ------------------------------------------------------------------ stage 1 + 2 over virtual queries
     def search(self, q: torch.Tensor, k: int, out: Optional[dict] = None, hi_only: Optional[bool] = None,
-               xchg=None, am=None) -> SearchResult:
+               xchg=None, am=None, row_filter=None) -> SearchResult:
         """Exact top-k of every segment for every query: rows v = s * B + b of the result belong to (segment s,
         query b); ids are rows of the concatenated corpus.  Asynchronous on the current stream."""
         if xchg is not None or hi_only:
             raise ValueError("SegmentedIndex.search: hi+lo queries on one GPU only")
+        inv_norm = row_filter.inv_norm if row_filter is not None else self.inv_norm  # a gate over the concatenated rows
         q = self._check_queries(q)
         b = int(q.shape[0])
         vb = self.n_seg * b
@@ -94,20 +95,20 @@ class SegmentedIndex(DeviceIndex):
             check(L.tt_prepare_queries(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), st))
             # one call; the library runs ceil(B / 8) passes, each writing its query columns of every segment
             check(L.tt_scan_topk_bf16_segmented(ptr(self.corpus), self.n_rows, self.dim, self._row_stride(self.corpus),
-                                                ptr(self.inv_norm), ptr(w["q_hi"]), ptr(w["q_lo"]), b, self.kprime,
+                                                ptr(inv_norm), ptr(w["q_hi"]), ptr(w["q_lo"]), b, self.kprime,
                                                 self.id_base, self._seg_end, self.n_seg, ptr(w["cand_ids"]),
                                                 ptr(w["cand_approx"]), ptr(w["cand_thresh"]), ptr(w["scan_ws"]),
                                                 w["scan_ws"].numel(), st))
             self._stage2(q_rep, vb, w, n_cand, self.n_lists, k, None, cert, am, self.eps)
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if cert is not None else self.eps, False)
 
-    def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool) -> None:
+    def _repair(self, q, k, r: SearchResult, bad: torch.Tensor, hi_lo_first: bool, row_filter=None) -> None:
         """A (segment, query) pair whose certificate failed: the exact fp64 scan of that segment's rows."""
         b = int(q.shape[0])
         for v in bad.tolist():
             s, bq = divmod(int(v), b)
             lo = self.leaf_off[s]
-            ex = self.search_exact(q[bq:bq + 1], k, rows=(lo, lo + self.seg_rows[s]))
+            ex = self.search_exact(q[bq:bq + 1], k, rows=(lo, lo + self.seg_rows[s]), row_filter=row_filter)
             r.keys[v].copy_(ex.keys[0])
             r.scores[v].copy_(ex.scores[0])
             r.ids[v].copy_(ex.ids[0])

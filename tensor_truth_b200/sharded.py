@@ -449,8 +449,7 @@ class ShardedIndex:
             r = self._host_round(pb, q, rec, b, k, ratio_thresh, merged)
             rec["host"].copy_(rec["dev"], non_blocking=True)
         self.last = r
-        rec["event"].record()
-        rec["event"].synchronize()
+        self._lib.check(self._lib.lib().tt_stream_synchronize(local._stream()))
         self._lib.check_status(local._dev_index)
         all_h = rec["hn"]["extra"].reshape(pb.world, b)
         proven = all_h > r.eps                    # [world, B], the same on every rank

@@ -4,6 +4,8 @@ tests/unit/test_rag_engine.py:17-245), the docstore -> flat-array importer core,
 from types import SimpleNamespace
 from unittest.mock import MagicMock
 
+import os
+
 import numpy as np
 import pytest
 
@@ -337,3 +339,76 @@ def test_rerank_postprocessor_semantics_with_a_stand_in_encoder():
     with pytest.raises(ValueError, match="Missing query bundle"):
         rr.postprocess_nodes(list(nodes))
     assert len(rr.postprocess_nodes(list(nodes), query_str="as a plain string")) == 2
+
+
+# --------------------------------------------------------------------------- metadata filters (the filter tail)
+_FILTER_SPECS = [
+    {"doc_type": "library"},
+    {"version": {"$gte": "2.0"}},
+    {"doc_type": ["library", "book"]},
+    {"doc_type": "paper", "year": {"$lt": 2020}, "lang": ["en", "de"]},
+    {"x": {"$bogus": 1}},                      # unknown operator: the clause is dropped
+    {"x": {"$ne": 3, "$gt": 1}},               # only the first key of an operator dict counts
+    {"tags": {"$nin": ["draft"]}},
+    {},
+]
+
+
+def test_filter_clauses_and_row_eligibility():
+    from tensor_truth_b200.filters import clauses_from_spec, eligible_rows
+
+    assert clauses_from_spec(_FILTER_SPECS[3]) == [("doc_type", "$eq", "paper"), ("year", "$lt", 2020), ("lang", "$in", ["en", "de"])]
+    assert clauses_from_spec(_FILTER_SPECS[4]) == [] and clauses_from_spec(_FILTER_SPECS[5]) == [("x", "$ne", 3)]
+    meta = [{"doc_type": "paper", "year": 2019, "lang": "en"}, {"doc_type": "paper", "year": 2021, "lang": "en"},
+            {"doc_type": "book", "year": 2000, "lang": "de"}, {"doc_type": "paper", "lang": "de"}, None,
+            {"doc_type": "paper", "year": "2019", "lang": "en"}]
+    assert eligible_rows(_FILTER_SPECS[3], meta).tolist() == [True, False, False, False, False, False]  # missing key / wrong type: no match
+    assert eligible_rows({"year": {"$ne": 2019}}, meta).tolist() == [False, True, True, True, True, True]  # $ne matches a missing key
+    assert eligible_rows({"lang": {"$nin": ["en"]}}, meta).tolist() == [False, False, True, True, True, False]
+    assert eligible_rows(None, meta).all() and eligible_rows({}, meta).all()
+    with pytest.raises(ValueError):
+        eligible_rows({"t": {"$text_match": "x"}}, meta)
+
+
+def test_filter_spec_parser_equals_the_references_builder():
+    """``clauses_from_spec`` against the reference's own ``_build_metadata_filters`` (rag_engine.py:301-365), executed as
+    it lies under stand-ins for the LlamaIndex filter types (this container only)."""
+    import importlib.util
+    from dataclasses import dataclass, field
+    from enum import Enum
+    from typing import Any, List
+
+    from tensor_truth_b200.filters import clauses_from_filters, clauses_from_spec
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_multi_index_golden", os.path.join(here, "golden", "make_multi_index_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    if not gen.reference_available():
+        pytest.skip("/root/reference is not on this machine")
+
+    class FilterOperator(str, Enum):
+        EQ, NE, GT, GTE, LT, LTE, IN, NIN, CONTAINS, TEXT_MATCH = "==", "!=", ">", ">=", "<", "<=", "in", "nin", "contains", "text_match"
+
+    class FilterCondition(str, Enum):
+        AND, OR = "and", "or"
+
+    @dataclass
+    class MetadataFilter:
+        key: str
+        value: Any
+        operator: FilterOperator = FilterOperator.EQ
+
+    @dataclass
+    class MetadataFilters:
+        filters: List[Any] = field(default_factory=list)
+        condition: FilterCondition = FilterCondition.AND
+
+    ref = gen.load_reference_rag_engine(dict(FilterOperator=FilterOperator, FilterCondition=FilterCondition,
+                                             MetadataFilter=MetadataFilter, MetadataFilters=MetadataFilters))
+    for fs in _FILTER_SPECS:
+        built = ref._build_metadata_filters(fs)
+        mine = clauses_from_spec(fs)
+        assert (built is None) == (mine == []), fs
+        if built is not None:
+            assert clauses_from_filters(built) == mine, fs
