@@ -53,6 +53,36 @@ def _worker(rank, world, port, transport, out_dir):
         scores, ids = sh.search(qd, 10)
         torch.cuda.synchronize()
         assert (ids.cpu().numpy() == ids_o).all() and (scores.cpu().numpy() == sc_o).all(), rep
+    if transport == "peer":
+        # the whole sharded step as ONE CUDA graph per lane (device-resident exchange epochs): two lanes on two streams,
+        # replayed alternately like the bench's throughput loop, every replay checked against the oracle
+        lanes = [sh.step_graph(1, 10, 0.5, lane) for lane in range(2)]
+        streams = [torch.cuda.Stream(dev) for _ in range(2)]
+        torch.cuda.synchronize()
+        kept = []
+        for step in range(10):
+            lane = step % 2
+            g = lanes[lane]
+            with torch.cuda.stream(streams[lane]):
+                g.q.copy_(qd[step:step + 1], non_blocking=True)
+                g.replay()
+                kept.append((step, g.result.ids.clone(), g.result.scores.clone(), g.merged.ids.clone(), g.merged.scores.clone(),
+                             g.merged.lens.clone(), g.result.margin.clone()))
+        torch.cuda.synchronize()
+        from tensor_truth_b200 import _lib as _l
+
+        _l.check_status(rank)
+        for step, ids, scores, mids, msc, mlens, margin in kept:
+            assert (ids.cpu().numpy() == ids_o[step:step + 1]).all() and (scores.cpu().numpy() == sc_o[step:step + 1]).all(), step
+            assert float(margin[0]) > lanes[0].eps
+            exp = oracle.retrieve(bits, q[step], 10, tree)
+            n = int(mlens[0])
+            assert [(int(o), float(s)) for o, s in zip(mids[0, :n].tolist(), msc[0, :n].tolist())] == exp, step
+        # the host path switches to its graph after GRAPH_AFTER eager calls: results must not change across the switch
+        for rep in range(6):
+            ids_h, sc_h, lens = sh.retrieve_host(torch.from_numpy(q[rep:rep + 1]), 10)
+            exp = oracle.retrieve(bits, q[rep], 10, tree)
+            assert [(int(o), float(s)) for o, s in zip(ids_h[0, :lens[0]], sc_h[0, :lens[0]])] == exp, rep
     ids_h, sc_h, lens = sh.retrieve_host(torch.from_numpy(q[:3]), 10)
     for b in range(3):
         exp = oracle.retrieve(bits, q[b], 10, tree)
