@@ -64,7 +64,7 @@ def measured_tensor_peak():
 class ClockSampler:
     """Samples SM clocks and throttle reasons of one GPU with NVML while the timed region runs."""
 
-    def __init__(self, index: int, period_s: float = 0.02):
+    def __init__(self, index: int, period_s: float = 0.001):
         self.index, self.period = index, period_s
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
