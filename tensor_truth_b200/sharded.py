@@ -186,14 +186,19 @@ class ShardedIndex:
 
     LANES = 2
 
-    def __init__(self, local_index, group=None):
+    def __init__(self, local_index, group=None, _local=None):
+        """``_local = (world, rank, registry)``: one of several simulated ranks inside ONE process on ONE device
+        (``LocalShardGroup``): the exchange buffers come from ``PeerBuffers.local_group`` instead of symmetric memory."""
         from . import _lib
 
         self._lib = _lib
         self.local = local_index
         self.device = local_index.device
         self._margins = None
+        self._local = _local
         self.plumbing = ShardedSearch(self._local_search, self._merge, self.device, group)
+        if _local is not None:
+            self.plumbing.world, self.plumbing.rank = _local[0], _local[1]
         self._out: dict = {}
         self.group = group
         self._peers: dict = {}
@@ -207,6 +212,12 @@ class ShardedIndex:
         if self.transport != "peer":
             return None
         pb = self._peers.get((b, k))
+        if pb is None and self._local is not None:
+            world, rank, registry = self._local
+            group = registry.get((b, k))
+            if group is None:
+                group = registry[(b, k)] = PeerBuffers.local_group(world, b, k, self.device, lanes=self.LANES)
+            pb = self._peers[(b, k)] = group[rank]
         if pb is None:
             try:
                 pb = self._peers[(b, k)] = PeerBuffers(b, k, self.device, self.group, lanes=self.LANES)
@@ -260,11 +271,16 @@ class ShardedIndex:
                                   self.local.score_mode, ptr(o[0]), ptr(o[1]), self.local._stream()))
         return o
 
-    def search(self, q, k, margins: Optional[torch.Tensor] = None, slot: int = 0, merged_out=None, ratio_thresh: float = 0.5):
-        """Merged exact top-k, identical on every rank: ``(scores [B,k], ids [B,k])``.  ``margins`` (float32 [B])
-        receives this rank's certificate margins (compare with ``self.last.eps``).  ``slot``: the lane (stream) of a
-        pipelined caller, < ``LANES``.  ``merged_out`` (``MergeResult``): also auto-merge the merged list into it -- on
-        the peer transport inside the merging kernel."""
+    @staticmethod
+    def _run(gen):
+        """Run a phased procedure (a generator that yields wherever a wait for the peers follows a push) to its end."""
+        try:
+            while True:
+                next(gen)
+        except StopIteration as stop:
+            return stop.value
+
+    def _search_phases(self, q, k, margins, slot, merged_out, ratio_thresh):
         self._margins = margins
         q = self.local._check_queries(q)
         b = int(q.shape[0])
@@ -279,8 +295,16 @@ class ShardedIndex:
         if margins is not None:
             w["margin"] = margins
         self.last = self.local.search(q, k, out=w, xchg=pb.desc(slot))
+        yield  # every rank's push is enqueued before anybody enqueues a wait (matters to LocalShardGroup only)
         am = self.local._am_args(ratio_thresh, merged_out) if merged_out is not None else None
         return self._merge_pulled(pb, slot, b, k, k, slot, am=am)
+
+    def search(self, q, k, margins: Optional[torch.Tensor] = None, slot: int = 0, merged_out=None, ratio_thresh: float = 0.5):
+        """Merged exact top-k, identical on every rank: ``(scores [B,k], ids [B,k])``.  ``margins`` (float32 [B])
+        receives this rank's certificate margins (compare with ``self.last.eps``).  ``slot``: the lane (stream) of a
+        pipelined caller, < ``LANES``.  ``merged_out`` (``MergeResult``): also auto-merge the merged list into it -- on
+        the peer transport inside the merging kernel."""
+        return self._run(self._search_phases(q, k, margins, slot, merged_out, ratio_thresh))
 
     def step_graph(self, b: int, k: int, ratio_thresh: float = 0.5, lane: int = 0, merged: bool = True):
         """The sharded step over device-resident buffers as ONE CUDA graph: prepare -> scan -> re-score + select + push
@@ -292,8 +316,8 @@ class ShardedIndex:
         g = self._graphs.get(key)
         if g is None:
             pb = self.peers(b, k)
-            if pb is None:
-                raise RuntimeError("ShardedIndex.step_graph needs the peer transport (symmetric memory)")
+            if pb is None or self._local is not None:
+                raise RuntimeError("ShardedIndex.step_graph needs the peer transport (symmetric memory) and one process per rank")
             dev = self.device
             q = torch.zeros((b, self.local.dim), dtype=torch.float32, device=dev)
             margins = torch.empty((b,), dtype=torch.float32, device=dev)
@@ -320,6 +344,8 @@ class ShardedIndex:
 
     def barrier(self, b: int = 1, k: int = 10) -> None:
         """Device-side rendezvous of all ranks on the current stream (peer transport); a host barrier otherwise."""
+        if self._local is not None:
+            return  # simulated ranks share one process and one device: nothing to rendezvous
         pb = self.peers(b, k)
         if pb is None:
             if self.plumbing.world > 1:
@@ -367,20 +393,23 @@ class ShardedIndex:
         return ids_h, scores_h, lens
 
     # ------------------------------------------------------------------ host in / host out, peer transport
-    def _host_round(self, pb, q, rec, b, k, ratio_thresh, merged):
-        """First round of a host query batch on lane 0, enqueued on the current stream: local scan + re-score + select
-        + push, then flag-wait + merge (+ auto-merge), everything landing in the result record ``rec`` -- merged lists,
-        this rank's margins and the margins EVERY rank pushed (``extra``: [world, B])."""
+    def _host_push(self, pb, q, rec, b, k):
+        """First half of a host round on lane 0: local scan + stage 2, which pushes this rank's record (and margins) to
+        every peer; this rank's margins land in the result record."""
+        w = dict(self.local._buffers(b, k, slot=("host", 0)))
+        w["margin"] = rec["d"]["margin"]
+        return self.local.search(q, k, out=w, xchg=pb.desc(0))
+
+    def _host_merge(self, pb, rec, b, k, ratio_thresh, merged):
+        """Second half: flag-wait + merge (+ auto-merge), everything landing in the result record ``rec`` -- merged lists
+        and the margins EVERY rank pushed (``extra``: [world, B])."""
+        import ctypes as C
+
         from .index import MergeResult
 
         local = self.local
         d = rec["d"]
-        w = dict(local._buffers(b, k, slot=("host", 0)))
-        w["margin"] = d["margin"]
-        r = local.search(q, k, out=w, xchg=pb.desc(0))
         L, ptr, check = self._lib.lib(), self._lib.ptr, self._lib.check
-        import ctypes as C
-
         region = pb.region_ptr(0)
         if merged:
             o = self._outputs(b, k, ("host", 0))
@@ -391,6 +420,11 @@ class ShardedIndex:
             check(L.tt_merge_topk_fused(region, region + pb.ids_off, pb.world, pb.rec_stride // 4, pb.rec_stride // 8, b, k,
                                         k, local.score_mode, ptr(o[0]), ptr(o[1]), C.byref(pb.desc(0)), ptr(d["extra"]),
                                         C.byref(am) if am is not None else None, local._stream()))
+
+    def _host_round(self, pb, q, rec, b, k, ratio_thresh, merged):
+        """Both halves back to back (what the captured graph of the host path holds)."""
+        r = self._host_push(pb, q, rec, b, k)
+        self._host_merge(pb, rec, b, k, ratio_thresh, merged)
         return r
 
     def _host_graph(self, pb, b, k, ratio_thresh, merged):
@@ -426,15 +460,17 @@ class ShardedIndex:
         g.update(graph=graph, q_pin=q_pin, q_pin_np=q_pin.numpy(), q_dev=q_dev, result=out["r"], rec=rec)
         return g
 
-    def _retrieve_host_peer(self, pb, q_host, b, k, ratio_thresh, merged):
+    def _host_phases(self, pb, q_host, b, k, ratio_thresh, merged):
         """Peer transport, ONE host synchronisation per query batch: the selecting kernel pushes this rank's record AND
         its certificate margins to every peer, the merging kernel copies all ranks' margins into the result record, so
         they come back with the answer.  Only if some rank's top-k was not proven (every rank sees that, from identical
-        data) do all ranks take a second round: local repair, plain push, merge again."""
+        data) do all ranks take a second round: local repair, plain push, merge again.
+        A generator: it yields wherever a wait for the peers follows a push, so that ``LocalShardGroup`` can step several
+        simulated ranks in lockstep; a real rank just runs it through (``_run``)."""
         import ctypes as C
 
         local = self.local
-        g = self._host_graph(pb, b, k, ratio_thresh, merged)
+        g = self._host_graph(pb, b, k, ratio_thresh, merged) if self._local is None else None
         if g is not None:
             if q_host.dtype == torch.float32 and q_host.device.type == "cpu":
                 g["q_pin_np"][...] = q_host.numpy()  # the common case: a plain memory copy into the pinned staging buffer
@@ -446,7 +482,9 @@ class ShardedIndex:
         else:
             q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
             rec = local._record(b, k, merged, extra_f32=pb.world * b)
-            r = self._host_round(pb, q, rec, b, k, ratio_thresh, merged)
+            r = self._host_push(pb, q, rec, b, k)
+            yield
+            self._host_merge(pb, rec, b, k, ratio_thresh, merged)
             rec["host"].copy_(rec["dev"], non_blocking=True)
         self.last = r
         self._lib.check(self._lib.lib().tt_stream_synchronize(local._stream()))
@@ -464,6 +502,7 @@ class ShardedIndex:
             with local._on_device():
                 self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), pb.rec_bytes // 4 * 4, C.byref(pb.desc(0)),
                                                                  local._stream()))
+            yield
             scores, mids = self._merge_pulled(pb, 0, b, k, k, ("host", 1))
             rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged)
             rec["event"].synchronize()
@@ -471,9 +510,8 @@ class ShardedIndex:
             self.second_rounds += 1
         return self._unpack_host(rec, merged)
 
-    def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True):
-        """Host queries in, merged (+ auto-merged) lists out (numpy), with the certificate enforced per rank.
-        Same contract as ``DeviceIndex.retrieve_host``, so the retriever classes take either; every rank must call it."""
+    def _retrieve_host_phases(self, q_host, k, ratio_thresh, merge):
+        """``retrieve_host`` as a phased procedure (peer transport), or None when this index exchanges through NCCL."""
         merged = bool(merge and self.local.tree is not None)
         if q_host.dim() != 2 or q_host.shape[1] != self.local.dim:
             raise ValueError(f"queries must be [B, {self.local.dim}], got {tuple(q_host.shape)}")
@@ -481,7 +519,17 @@ class ShardedIndex:
         if self.transport == "peer":
             pb0 = self.peers(b, k)
             if pb0 is not None:
-                return self._retrieve_host_peer(pb0, q_host, b, k, ratio_thresh, merged)
+                return self._host_phases(pb0, q_host, b, k, ratio_thresh, merged)
+        return None
+
+    def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True):
+        """Host queries in, merged (+ auto-merged) lists out (numpy), with the certificate enforced per rank.
+        Same contract as ``DeviceIndex.retrieve_host``, so the retriever classes take either; every rank must call it."""
+        phases = self._retrieve_host_phases(q_host, k, ratio_thresh, merge)
+        if phases is not None:
+            return self._run(phases)
+        merged = bool(merge and self.local.tree is not None)
+        b = int(q_host.shape[0])
         local = self.local
         q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
         hb = self._host_bufs.get(b)
@@ -505,3 +553,49 @@ class ShardedIndex:
         rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged)
         rec["event"].synchronize()
         return self._unpack_host(rec, merged)
+
+
+class LocalShardGroup:
+    """Several row shards of one corpus on ONE GPU in ONE process, each behind its own ``ShardedIndex`` and its own
+    stream -- the multi-GPU protocol (push into every rank's receive ring, flags, merge, margins of every rank, second
+    round after a repair) with plain device buffers standing in for the peer mappings.  What it is for: exercising
+    ``ShardedIndex`` itself on a single-GPU box (tests/test_gpu_exchange_one_device.py); the kernels and descriptors
+    are exactly those of the real thing.
+
+    One thread drives all ranks, so the phased procedures of the ranks are stepped in LOCKSTEP: every rank enqueues
+    its push before any rank enqueues the wait that follows -- a kernel never waits for one enqueued after it (two
+    streams of one process may share a hardware queue)."""
+
+    def __init__(self, shards):
+        registry: dict = {}
+        world = len(shards)
+        self.ranks = [ShardedIndex(s, _local=(world, r, registry)) for r, s in enumerate(shards)]
+        self.streams = [torch.cuda.Stream(s.device) for s in shards]
+
+    def _lockstep(self, gens):
+        out = [None] * len(gens)
+        live = list(range(len(gens)))
+        while live:
+            for r in list(live):
+                with torch.cuda.stream(self.streams[r]):
+                    try:
+                        next(gens[r])
+                    except StopIteration as stop:
+                        out[r] = stop.value
+                        live.remove(r)
+        return out
+
+    def search(self, q, k, merged_out=None, ratio_thresh: float = 0.5):
+        """Every rank's ``ShardedIndex.search``; returns the per-rank ``(scores, ids)`` (all equal)."""
+        cur = torch.cuda.current_stream(self.ranks[0].device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        outs = merged_out if merged_out is not None else [None] * len(self.ranks)
+        res = self._lockstep([rk._search_phases(q, k, None, 0, outs[r], ratio_thresh) for r, rk in enumerate(self.ranks)])
+        for st in self.streams:
+            cur.wait_stream(st)
+        return res
+
+    def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True):
+        """Every rank's ``ShardedIndex.retrieve_host``; returns the per-rank ``(ids, scores, lens)`` (all equal)."""
+        return self._lockstep([rk._retrieve_host_phases(q_host, k, ratio_thresh, merge) for rk in self.ranks])

@@ -2,7 +2,8 @@
 streams, plain device buffers standing in for the NVLink peer mappings -- ``PeerBuffers.local_group``), driven through
 the C ABI the multi-GPU path uses -- ``tt_rescore_topk_fused`` (push) -> ``tt_merge_topk_fused`` (flag wait, merge,
 margins, auto-merge) -> ``tt_exchange_push`` (second round) -> ``tt_peer_barrier`` -- and compared with the CPU oracle
-on the whole corpus.  What a 1-GPU box cannot show is only the NVLink transport itself (tests/test_gpu_sharded.py)."""
+on the whole corpus; then ``ShardedIndex`` itself (``search``, ``retrieve_host``, the second round after a repair) through
+``LocalShardGroup``.  What a 1-GPU box cannot show is only the NVLink transport itself (tests/test_gpu_sharded.py)."""
 
 import ctypes as C
 
@@ -243,3 +244,87 @@ def test_step_graph_replays_match_eager(two_shards):
         exp = oracle.auto_merge([(int(o), float(s)) for o, s in zip(leaf[0][0], leaf[1][0]) if o >= 0], tree.parent_of,
                                 tree.child_count, tree.prev_id, tree.next_id)
         assert got == exp, i
+
+
+# ---- ShardedIndex itself (not just the ABI calls under it) on one GPU: LocalShardGroup steps two simulated ranks in lockstep
+
+
+def test_sharded_index_search_on_one_gpu(two_shards):
+    import oracle
+    from oracle import cport
+    from tensor_truth_b200 import _lib
+    from tensor_truth_b200.index import MergeResult
+    from tensor_truth_b200.sharded import LocalShardGroup
+
+    tree, bits, q, shards = two_shards
+    dev = shards[0].device
+    grp = LocalShardGroup(shards)
+    assert all(rk.transport == "peer" and rk.peers(1, 10) is not None for rk in grp.ranks)  # no NCCL fallback underneath
+    ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
+    qd = torch.from_numpy(q).to(dev)
+    for rep in range(5):  # both slots of the lane's ring several times over, two batch shapes (two PeerBuffers groups)
+        for b in (1, 12):
+            mos = [MergeResult(torch.empty((b, 20), dtype=torch.int64, device=dev), torch.empty((b, 20), dtype=torch.float64, device=dev),
+                               torch.empty((b,), dtype=torch.int32, device=dev)) for _ in range(2)]
+            res = grp.search(qd[rep:rep + b], 10, merged_out=mos)
+            torch.cuda.synchronize()
+            _lib.check_status(0)
+            for r, (scores, ids) in enumerate(res):
+                assert (ids.cpu().numpy() == ids_o[rep:rep + b]).all() and (scores.cpu().numpy() == sc_o[rep:rep + b]).all(), (rep, b, r)
+                for i in range(b):
+                    n = int(mos[r].lens[i])
+                    got = [(int(o), float(s)) for o, s in zip(mos[r].ids[i, :n].tolist(), mos[r].scores[i, :n].tolist())]
+                    assert got == oracle.retrieve(bits, q[rep + i], 10, tree), (rep, b, r, i)
+
+
+def test_sharded_index_retrieve_host_on_one_gpu(two_shards):
+    import oracle
+    from tensor_truth_b200.sharded import LocalShardGroup
+
+    tree, bits, q, shards = two_shards
+    grp = LocalShardGroup(shards)
+    for rep in range(4):
+        for b in (1, 3):
+            res = grp.retrieve_host(torch.from_numpy(q[rep:rep + b]), 10)
+            for r, (ids_h, sc_h, lens) in enumerate(res):
+                for i in range(b):
+                    got = [(int(o), float(s)) for o, s in zip(ids_h[i, :lens[i]], sc_h[i, :lens[i]])]
+                    assert got == oracle.retrieve(bits, q[rep + i], 10, tree), (rep, b, r, i)
+    assert all(rk.second_rounds == 0 for rk in grp.ranks)
+    with pytest.raises(RuntimeError):
+        grp.ranks[0].step_graph(1, 10)  # graphs of the sharded step need one process per rank
+
+
+def test_sharded_index_second_round_on_one_gpu():
+    """One shard whose top-k cannot be proven (near-duplicate rows), one that can: EVERY rank must see it (the margins
+    travel with the records), the rank concerned repairs, and all ranks exchange a second time."""
+    import oracle
+    from oracle import cport
+    from tensor_truth_b200 import _lib
+    from tensor_truth_b200.index import DeviceIndex
+    from tensor_truth_b200.sharded import LocalShardGroup, shard_bounds
+    from tensor_truth_b200.synth import make_small
+
+    dev = torch.device("cuda:0")
+    _lib.set_wait_timeout_ms(0, 1500)
+    try:
+        tree, bits, inv, q = make_small(20_000, 4, dim=1024, levels=3, seed=78)
+        rng = np.random.default_rng(3)
+        base = rng.standard_normal(1024).astype(np.float32)
+        dup = oracle.f32_to_bf16_bits(base[None, :] * (1.0 + 2e-3 * rng.standard_normal((20_000, 1024)).astype(np.float32)))
+        mixed = np.concatenate([bits[:20_000], dup])
+        shards = []
+        for r in range(2):
+            lo, hi = shard_bounds(mixed.shape[0], 2, r)
+            shards.append(DeviceIndex(mixed[lo:hi], None, id_base=lo, device=dev))
+        grp = LocalShardGroup(shards)
+        q2 = np.stack([q[0], (base * (1.0 + 1e-3 * rng.standard_normal(1024))).astype(np.float32), q[1]])
+        ids_m, sc_m, _ = cport.scan_topk(mixed, q2, 10)
+        for rep in range(3):
+            res = grp.retrieve_host(torch.from_numpy(q2), 10, merge=False)
+            for r, (ids_h, sc_h, lens) in enumerate(res):
+                assert (ids_h == ids_m).all() and (sc_h == sc_m.astype(np.float64)).all(), (rep, r)
+        assert [rk.second_rounds for rk in grp.ranks] == [3, 3]
+        assert [rk.local.fallbacks > 0 for rk in grp.ranks] == [False, True]
+    finally:
+        _lib.set_wait_timeout_ms(0, 0)
