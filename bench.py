@@ -435,6 +435,7 @@ class Bench:
             out = call(warm + i)
         ctx.barrier()
         e2e_s = ctx.max_over_ranks(time.perf_counter() - t0)
+        two = guarded("e2e_two_callers", lambda: self.e2e_two_callers(am, q_lists, steps, warm), sys.stderr)
         idx = self.idx
         d2h = idx._record(1, self.k, True, extra_f32=ctx.world if (self.sharded is not None and self.sharded.transport == "peer") else 0)["bytes"]
         return {"value": steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": DIM * 4, "d2h_bytes_per_step": d2h,
@@ -442,7 +443,57 @@ class Bench:
                 "api": "B200AutoMergingRetriever.retrieve(QueryBundle)" + ("" if self.sharded is None else " over ShardedIndex, every rank"),
                 "retries": idx.retries, "deep_rescans": idx.deep_rescans, "fallbacks": idx.fallbacks,
                 "second_rounds": getattr(self.sharded, "second_rounds", 0) if self.sharded is not None else 0,
-                "nodes_returned_last": len(out)}
+                "nodes_returned_last": len(out), "callers": 1, "two_callers": two}
+
+    def e2e_two_callers(self, am, q_lists, steps, warm):
+        """The same ``retrieve()`` calls from TWO host threads (what a serving process with concurrent requests does, and
+        what ``value``'s two device lanes correspond to): the index pipelines them over its host lanes, so one caller's
+        exchange + D2H + Python work overlaps the other's corpus scan.  ``steps`` calls in total, wall clock, max over ranks.
+        On a sharded index thread t of every rank serves lane t (``retriever.for_lane(t)``)."""
+        import threading
+
+        from tensor_truth_b200.schema import QueryBundle
+
+        ctx, n, callers = self.ctx, len(q_lists), 2
+        rets = [am.for_lane(t) if self.sharded is not None else am for t in range(callers)]
+        gate = threading.Barrier(callers + 1)
+        errors, last = [], [None] * callers
+
+        def worker(t):
+            try:
+                torch.cuda.set_device(ctx.device)
+                call = lambda i: rets[t].retrieve(QueryBundle(query_str=f"q{i}", embedding=q_lists[i % n]))  # noqa: E731
+                for i in range(warm):
+                    call(i)
+                gate.wait()   # warm-up done (graphs of both lanes captured)
+                gate.wait()   # clock started
+                for i in range(t, steps, callers):
+                    last[t] = call(warm + i)
+            except Exception as exc:  # noqa: BLE001
+                errors.append(exc)
+                gate.abort()
+
+        threads = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(callers)]
+        for th in threads:
+            th.start()
+        try:
+            gate.wait()
+            ctx.barrier()
+            t0 = time.perf_counter()
+            gate.wait()
+        except threading.BrokenBarrierError:
+            pass
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        ctx.barrier()
+        sec = ctx.max_over_ranks(time.perf_counter() - t0)
+        ref = am.retrieve(QueryBundle(query_str="check", embedding=q_lists[(warm + steps - 1) % n]))
+        same = [(x.node.node_id, x.score) for x in last[(steps - 1) % callers]] == [(x.node.node_id, x.score) for x in ref]
+        return {"value": steps / sec, "unit": UNIT, "callers": callers, "steps": steps,
+                "equals_single_caller_answer": bool(same),
+                "note": "two host threads, each a synchronous retrieve(); pipelined over the index's host lanes"}
 
 
 class Ctx:

@@ -18,6 +18,7 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import os
+import queue
 import threading
 from dataclasses import dataclass
 from typing import Optional
@@ -39,6 +40,7 @@ MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist work
 HILO_GEMM_FROM = 17        # hi+lo batches of 17-32 queries take the 64-column GEMM-shaped pass with (hi, lo) column pairs
 GEMM_ABOVE = 33            # hi-only batches at least this large take the GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass
                            # per 4096 queries, one list per query (64 queries: 3.04 ms at 10M rows vs 3.35 ms for the pair kernel)
+HOST_LANES = 2             # concurrent retrieve_host callers in flight per index (own stream, buffers, record and graph each)
 GRAPH_AFTER = 3            # retrieve_host: eager calls of a (batch, k) shape before its pipeline is captured in a CUDA graph
 GEMM_SLICE = 4096          # queries per GEMM-shaped corpus pass (candidate buffers: 16 K' * 8 B per query)
 
@@ -49,8 +51,22 @@ def gemm_kprime(k: int) -> int:
 
 
 _NULL_CTX = contextlib.nullcontext()
-_CAPTURE_LOCK = threading.Lock()  # one CUDA-graph capture at a time per process: torch.cuda.graph() synchronises the device on
-                                  # entry, which is an error while another thread's stream is capturing
+_CAPTURE_LOCK = threading.Lock()  # one CUDA-graph capture at a time per process
+
+
+@contextlib.contextmanager
+def capturing(graph, stream):
+    """``torch.cuda.graph(graph, stream=stream)`` without its device-wide synchronisation on entry: whoever holds
+    ``_CAPTURE_LOCK`` must never wait for the device.  With several host lanes in flight a device-wide wait includes
+    another lane's merge kernel, which waits for a PEER's push, which that peer's thread may be unable to issue because it
+    waits for the peer's own capture lock -- a lock-order cycle across ranks.  Nothing here needs the synchronisation: the
+    shapes captured were run eagerly first, so the capture allocates nothing."""
+    with torch.cuda.stream(stream):
+        graph.capture_begin(capture_error_mode="thread_local")
+        try:
+            yield
+        finally:
+            graph.capture_end()
 
 
 @dataclass
@@ -92,7 +108,7 @@ def capture_on_side_stream(device, fn):
         side = torch.cuda.Stream(device)
         side.wait_stream(cur)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+        with capturing(graph, side):
             out = fn()
         cur.wait_stream(side)
     return graph, out
@@ -162,7 +178,14 @@ class DeviceIndex:
                 lo_v, hi_v = float(nrm.min()), float(nrm.max())
             self.norm_lo, self.norm_hi = max(0.0, lo_v * (1 - 1e-5)), hi_v * (1 + 1e-5)
         self._ws: dict = {}
-        self._lock = threading.Lock()  # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420)
+        # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420) and the web app serves requests
+        # concurrently: ``retrieve_host`` callers are pipelined over HOST_LANES lanes (own stream, buffers, result record
+        # and captured graph each), so one caller's tail + host work overlaps the next caller's corpus scan
+        self._lanes: "queue.LifoQueue[int]" = queue.LifoQueue()
+        for lane in reversed(range(HOST_LANES)):
+            self._lanes.put(lane)
+        self._lane_streams: dict = {}
+        self._repair_lock = threading.Lock()  # the repair ladder's workspaces are shared; repairs are rare
         self.set_tree(tree)
         _lib.status_word(self._dev_index)  # device-side timeouts surface as TTError after the next host synchronisation
         self.fallbacks = 0             # queries whose certificate failed and were re-run through the exact scan
@@ -174,13 +197,34 @@ class DeviceIndex:
     def set_tree(self, tree: Optional[NodeTree]) -> None:
         """Install (or drop) the node tree.  Captured pipelines bake the old tree arrays' addresses in, so every cached
         graph / step graph is dropped with them."""
-        lock = getattr(self, "_lock", None) or contextlib.nullcontext()
-        with lock:
+        held = [self._lanes.get() for _ in range(HOST_LANES)]  # no retrieve_host call in flight while the tree changes
+        try:
             ws = getattr(self, "_ws", None)
             if ws:
                 for key in [key for key in ws if isinstance(key, tuple) and key and key[0] in ("graph", "step")]:
                     del ws[key]
             self._set_tree_locked(tree)
+        finally:
+            for lane in reversed(held):
+                self._lanes.put(lane)
+
+    @contextlib.contextmanager
+    def _host_lane(self):
+        """Take a free host lane (blocks while all are busy).  Lane 0 runs on the caller's current stream, the others on
+        a stream of their own, which is current inside the context."""
+        lane = self._lanes.get()
+        try:
+            if lane == 0:
+                yield 0
+            else:
+                st = self._lane_streams.get(lane)
+                if st is None:
+                    st = self._lane_streams[lane] = torch.cuda.Stream(self.device)
+                    st.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(st):
+                    yield lane
+        finally:
+            self._lanes.put(lane)
 
     def _set_tree_locked(self, tree: Optional[NodeTree]) -> None:
         self.tree = tree
@@ -512,12 +556,12 @@ class DeviceIndex:
         return g
 
     # ------------------------------------------------------------------ whole path, host in / host out
-    def _record(self, b: int, k: int, merged: bool, extra_f32: int = 0):
+    def _record(self, b: int, k: int, merged: bool, extra_f32: int = 0, lane: int = 0):
         """One contiguous result record per query batch, so the whole answer (and the certificate margins)
         comes back in ONE device->host copy into pinned memory:
         ``[ lens i32 B | margin f32 B | ids i64 B*w | scores (f64 merged / f32 leaves) B*w | extra f32 ]``
         (``extra``: the row-sharded path's margins of every rank, [world, B])."""
-        key = ("rec", b, k, merged, extra_f32)
+        key = ("rec", b, k, merged, extra_f32, lane)
         r = self._ws.get(key)
         if r is None:
             w = max(2 * k, 1) if merged else k
@@ -541,13 +585,13 @@ class DeviceIndex:
                                  "event": torch.cuda.Event()}
         return r
 
-    def _pipeline_graph(self, b: int, k: int, ratio_thresh: float, merged: bool):
+    def _pipeline_graph(self, b: int, k: int, ratio_thresh: float, merged: bool, lane: int = 0):
         """The whole device pipeline of one ``retrieve_host`` shape as ONE CUDA graph: H2D of the queries from a pinned
         staging buffer -> prepare -> stage 1 -> re-score/select -> auto-merge -> D2H of the result record.  Captured
         after ``GRAPH_AFTER`` eager calls of the shape; a replay costs one launch instead of ~10 (the kernels, their
         arguments and the buffers are the same ones the eager path uses).  Returns None while the shape is still
         warming up, or for good if capture is not possible (the eager path then keeps serving)."""
-        key = ("graph", b, k, float(ratio_thresh), merged)
+        key = ("graph", b, k, float(ratio_thresh), merged, lane)
         g = self._ws.get(key)
         if g is None:
             g = self._ws[key] = {"calls": 0, "graph": None, "dead": bool(os.environ.get("TT_NO_GRAPH"))}
@@ -560,9 +604,9 @@ class DeviceIndex:
             return None
         try:
             vb = self._result_rows(b)
-            rec = self._record(vb, k, merged)
+            rec = self._record(vb, k, merged, lane=lane)
             d = rec["d"]
-            w = dict(self._buffers(vb, k))
+            w = dict(self._buffers(vb, k, slot=self._host_slot(lane)))
             w["margin"] = d["margin"]
             if not merged:
                 w["ids"], w["scores"] = d["ids"], d["scores"]
@@ -571,7 +615,7 @@ class DeviceIndex:
             side = torch.cuda.Stream(self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+            with capturing(graph, side):
                 q_dev.copy_(q_pin, non_blocking=True)
                 am = self._am_args(ratio_thresh, MergeResult(d["ids"], d["scores"], d["lens"])) if merged else None
                 r = self.search(q_dev, k, out=w, am=am)  # prepare -> scan -> re-score + select + auto-merge: 3 kernels
@@ -594,6 +638,11 @@ class DeviceIndex:
         finally:
             _CAPTURE_LOCK.release()
 
+    @staticmethod
+    def _host_slot(lane: int):
+        """Workspace slot of a host lane (lane 0 shares slot 0 with plain ``search`` callers, as it always has)."""
+        return 0 if lane == 0 else ("host-lane", lane)
+
     def retrieve_host(self, q_host: torch.Tensor, k: int, ratio_thresh: float = 0.5, merge: bool = True, row_filter=None):
         """Query embeddings in host memory -> merged ``(ids, scores, lens)`` in host memory (numpy).
         The H2D copy of the queries and the single D2H read of the result record are part of the call;
@@ -604,9 +653,9 @@ class DeviceIndex:
             parts = [self.retrieve_host(q_host[i:i + MAX_HOST_BATCH], k, ratio_thresh, merge, row_filter)
                      for i in range(0, int(q_host.shape[0]), MAX_HOST_BATCH)]
             return tuple(np.concatenate([p[j] for p in parts], axis=0) for j in range(3))
-        with self._lock:
+        with self._host_lane() as lane:
             b = int(q_host.shape[0])
-            g = (self._pipeline_graph(b, k, ratio_thresh, merged)
+            g = (self._pipeline_graph(b, k, ratio_thresh, merged, lane)
                  if (row_filter is None and q_host.dim() == 2 and q_host.shape[1] == self.dim) else None)
             if g is not None:
                 if q_host.dtype == torch.float32 and q_host.device.type == "cpu":
@@ -621,9 +670,9 @@ class DeviceIndex:
                 q = q_host.to(self.device, torch.float32, non_blocking=True)
                 q = self._check_queries(q)
                 vb = self._result_rows(b)
-                rec = self._record(vb, k, merged)
+                rec = self._record(vb, k, merged, lane=lane)
                 d, h = rec["d"], rec["hn"]
-                w = dict(self._buffers(vb, k))
+                w = dict(self._buffers(vb, k, slot=self._host_slot(lane)))
                 w["margin"] = d["margin"]
                 if not merged:
                     w["ids"], w["scores"] = d["ids"], d["scores"]
@@ -634,11 +683,12 @@ class DeviceIndex:
             _lib.check_status(self._dev_index)                     # PyTorch costs ~15 us of Python per query)
             bad = np.nonzero(~(h["margin"] > r.eps))[0]
             if bad.size:  # not proven exact: re-run those queries (tighter scan, then the exact fp64 scan)
-                self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only, row_filter=row_filter)
-                if merged:
-                    self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
-                rec["host"].copy_(rec["dev"], non_blocking=True)
-                check(self.lib.tt_stream_synchronize(self._stream()))
+                with self._repair_lock:
+                    self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only, row_filter=row_filter)
+                    if merged:
+                        self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
+                    rec["host"].copy_(rec["dev"], non_blocking=True)
+                    check(self.lib.tt_stream_synchronize(self._stream()))
                 _lib.check_status(self._dev_index)
             ids, scores = h["ids"].copy(), h["scores"].astype(np.float64)
             lens = h["lens"].copy() if merged else (ids >= 0).sum(axis=1).astype(np.int32)

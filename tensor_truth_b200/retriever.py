@@ -19,6 +19,7 @@ fallback.
 from __future__ import annotations
 
 import contextlib
+import copy
 import threading
 from array import array
 from typing import Any, Callable, List, Optional, Sequence, Union
@@ -94,13 +95,16 @@ class B200VectorIndexRetriever(_RetrieverBase):
 
     def __init__(self, index, similarity_top_k: int = 10, embed_model: Any = None,
                  node_table: Optional[NodeTable] = None, filters: Any = None,
-                 leaf_metadata: Optional[Sequence[Optional[dict]]] = None):
+                 leaf_metadata: Optional[Sequence[Optional[dict]]] = None, lane: Optional[int] = None):
         """``index``: a ``DeviceIndex``, or a ``ShardedIndex`` (row-sharded over GPUs; every rank then makes the same calls).
         ``filters``: what ``index.as_retriever(..., filters=...)`` takes upstream -- a LlamaIndex ``MetadataFilters`` or the
         reference's filter-spec dict (``_build_metadata_filters``, rag_engine.py:301-365); evaluated once, here, over
         ``leaf_metadata`` (one dict per corpus row; default: the ``.metadata`` of the node table's leaves) and applied
-        to every search as a row gate (filters.py).  Single-GPU indexes only."""
+        to every search as a row gate (filters.py).  Single-GPU indexes only.
+        ``lane``: for a ``ShardedIndex`` served by several threads -- thread t of every rank uses the retriever
+        ``for_lane(t)`` (``ShardedIndex.retrieve_host``).  A ``DeviceIndex`` pipelines concurrent callers by itself."""
         self.index = index
+        self.lane = lane
         self.similarity_top_k = int(similarity_top_k)
         self.embed_model = embed_model
         self.node_table = node_table or NodeTable(node_ids=getattr(index.tree, "node_ids", None) if index.tree else None)
@@ -138,8 +142,20 @@ class B200VectorIndexRetriever(_RetrieverBase):
             return torch.frombuffer(array("f", emb), dtype=torch.float32).reshape(1, -1)
         return torch.as_tensor(np.asarray(emb, dtype=np.float32)).reshape(1, -1)
 
-    def _retrieve(self, query_bundle: QueryBundle) -> List[NodeWithScore]:
+    def _call_kw(self) -> dict:
         kw = {"row_filter": self.row_filter} if self.row_filter is not None else {}
+        if self.lane is not None:
+            kw["lane"] = self.lane
+        return kw
+
+    def for_lane(self, lane: int) -> "B200VectorIndexRetriever":
+        """The same retriever bound to a host lane of a ``ShardedIndex`` (a shallow copy: index and node table shared)."""
+        other = copy.copy(self)
+        other.lane = int(lane)
+        return other
+
+    def _retrieve(self, query_bundle: QueryBundle) -> List[NodeWithScore]:
+        kw = self._call_kw()
         ids, scores, lens = self.index.retrieve_host(self._query_tensor(query_bundle), self.similarity_top_k, merge=False, **kw)
         return [NodeWithScore(node=self.node_table(int(o)), score=float(s))
                 for o, s in zip(ids[0, :lens[0]], scores[0, :lens[0]])]
@@ -165,10 +181,15 @@ class B200AutoMergingRetriever(_RetrieverBase):
     def _wrap(self, ids, scores, n) -> List[NodeWithScore]:
         return [NodeWithScore(node=self.node_table(int(o)), score=float(s)) for o, s in zip(ids[:n], scores[:n])]
 
+    def for_lane(self, lane: int) -> "B200AutoMergingRetriever":
+        """This retriever bound to a host lane of a ``ShardedIndex``: one per serving thread, the same lane on every rank."""
+        other = copy.copy(self)
+        other._vector_retriever = self._vector_retriever.for_lane(lane)
+        return other
+
     def _retrieve(self, query_bundle: QueryBundle) -> List[NodeWithScore]:
         q = self._vector_retriever._query_tensor(query_bundle)
-        rf = self._vector_retriever.row_filter
-        kw = {"row_filter": rf} if rf is not None else {}
+        kw = self._vector_retriever._call_kw()
         ids, scores, lens = self.index.retrieve_host(q, self._vector_retriever.similarity_top_k,
                                                      self._simple_ratio_thresh, merge=True, **kw)
         if lens[0] < 0:
@@ -178,8 +199,7 @@ class B200AutoMergingRetriever(_RetrieverBase):
     # ---- batch extension (not in the reference; what the bench drives)
     def retrieve_batch(self, embeddings) -> List[List[NodeWithScore]]:
         q = torch.as_tensor(np.asarray(embeddings, dtype=np.float32)) if not torch.is_tensor(embeddings) else embeddings
-        rf = self._vector_retriever.row_filter
-        kw = {"row_filter": rf} if rf is not None else {}
+        kw = self._vector_retriever._call_kw()
         ids, scores, lens = self.index.retrieve_host(q, self._vector_retriever.similarity_top_k,
                                                      self._simple_ratio_thresh, merge=True, **kw)
         if (lens < 0).any():

@@ -10,7 +10,9 @@ Record layout per rank (what travels):  ``[ keys float32 B*k | pad to 8 B | ids 
 
 from __future__ import annotations
 
+import contextlib
 import os
+import threading
 from typing import Callable, Optional, Tuple
 
 import torch
@@ -169,16 +171,18 @@ class PeerBuffers:
 
         check(lib.tt_peer_barrier(C.byref(self._x[self.lanes]), stream))
 
-    def send_record(self):
-        """A local record in the layout of one source's slice of a receive region (for tt_exchange_push): the uint8
-        buffer and its keys [B,k] / ids [B,k] / margins [B] views."""
+    def send_record(self, lane: int = 0):
+        """A local record in the layout of one source's slice of a receive region (for tt_exchange_push), one per lane:
+        the uint8 buffer and its keys [B,k] / ids [B,k] / margins [B] views."""
         if not hasattr(self, "_send"):
+            self._send = {}
+        if lane not in self._send:
             buf = torch.zeros(self.rec_stride, dtype=torch.uint8, device=self.buf.device)
             b, k = self.b, self.k
-            self._send = (buf, buf[: b * k * 4].view(torch.float32).view(b, k),
-                          buf[self.ids_off: self.ids_off + b * k * 8].view(torch.int64).view(b, k),
-                          buf[self.margins_off: self.margins_off + 4 * b].view(torch.float32))
-        return self._send
+            self._send[lane] = (buf, buf[: b * k * 4].view(torch.float32).view(b, k),
+                                buf[self.ids_off: self.ids_off + b * k * 8].view(torch.int64).view(b, k),
+                                buf[self.margins_off: self.margins_off + 4 * b].view(torch.float32))
+        return self._send[lane]
 
 
 class ShardedIndex:
@@ -196,6 +200,8 @@ class ShardedIndex:
         self.device = local_index.device
         self._margins = None
         self._local = _local
+        self._lane_locks = [threading.Lock() for _ in range(self.LANES)]
+        self._lane_streams: dict = {}
         self.plumbing = ShardedSearch(self._local_search, self._merge, self.device, group)
         if _local is not None:
             self.plumbing.world, self.plumbing.rank = _local[0], _local[1]
@@ -366,11 +372,11 @@ class ShardedIndex:
         self.plumbing._bufs.clear()
         self.local.close()
 
-    def _finish_host(self, mids, scores, b, k, ratio_thresh, merged, extra=None):
+    def _finish_host(self, mids, scores, b, k, ratio_thresh, merged, extra=None, lane=0):
         """Auto-merge (or copy) the merged top-k into the result record and start its D2H copy; ``extra`` = (device
         tensor, pinned host tensor) copied along.  The caller synchronises on the record's event."""
         local = self.local
-        rec = local._record(b, k, merged)
+        rec = local._record(b, k, merged, lane=lane)
         d = rec["d"]
         if merged:
             from .index import MergeResult
@@ -393,14 +399,14 @@ class ShardedIndex:
         return ids_h, scores_h, lens
 
     # ------------------------------------------------------------------ host in / host out, peer transport
-    def _host_push(self, pb, q, rec, b, k):
-        """First half of a host round on lane 0: local scan + stage 2, which pushes this rank's record (and margins) to
+    def _host_push(self, pb, q, rec, b, k, lane=0):
+        """First half of a host round on a lane: local scan + stage 2, which pushes this rank's record (and margins) to
         every peer; this rank's margins land in the result record."""
-        w = dict(self.local._buffers(b, k, slot=("host", 0)))
+        w = dict(self.local._buffers(b, k, slot=("host", lane)))
         w["margin"] = rec["d"]["margin"]
-        return self.local.search(q, k, out=w, xchg=pb.desc(0))
+        return self.local.search(q, k, out=w, xchg=pb.desc(lane))
 
-    def _host_merge(self, pb, rec, b, k, ratio_thresh, merged):
+    def _host_merge(self, pb, rec, b, k, ratio_thresh, merged, lane=0):
         """Second half: flag-wait + merge (+ auto-merge), everything landing in the result record ``rec`` -- merged lists
         and the margins EVERY rank pushed (``extra``: [world, B])."""
         import ctypes as C
@@ -410,30 +416,30 @@ class ShardedIndex:
         local = self.local
         d = rec["d"]
         L, ptr, check = self._lib.lib(), self._lib.ptr, self._lib.check
-        region = pb.region_ptr(0)
+        region = pb.region_ptr(lane)
         if merged:
-            o = self._outputs(b, k, ("host", 0))
+            o = self._outputs(b, k, ("host", lane))
             am = local._am_args(ratio_thresh, MergeResult(d["ids"], d["scores"], d["lens"]))
         else:
             o, am = (d["scores"], d["ids"]), None
         with local._on_device():
             check(L.tt_merge_topk_fused(region, region + pb.ids_off, pb.world, pb.rec_stride // 4, pb.rec_stride // 8, b, k,
-                                        k, local.score_mode, ptr(o[0]), ptr(o[1]), C.byref(pb.desc(0)), ptr(d["extra"]),
+                                        k, local.score_mode, ptr(o[0]), ptr(o[1]), C.byref(pb.desc(lane)), ptr(d["extra"]),
                                         C.byref(am) if am is not None else None, local._stream()))
 
-    def _host_round(self, pb, q, rec, b, k, ratio_thresh, merged):
+    def _host_round(self, pb, q, rec, b, k, ratio_thresh, merged, lane=0):
         """Both halves back to back (what the captured graph of the host path holds)."""
-        r = self._host_push(pb, q, rec, b, k)
-        self._host_merge(pb, rec, b, k, ratio_thresh, merged)
+        r = self._host_push(pb, q, rec, b, k, lane)
+        self._host_merge(pb, rec, b, k, ratio_thresh, merged, lane)
         return r
 
-    def _host_graph(self, pb, b, k, ratio_thresh, merged):
+    def _host_graph(self, pb, b, k, ratio_thresh, merged, lane=0):
         """The first round of ``retrieve_host`` as ONE CUDA graph: H2D of the queries from a pinned staging buffer ->
         the four kernels of ``_host_round`` -> D2H of the result record.  Captured after ``GRAPH_AFTER`` eager calls of
-        the shape (every rank counts alike, so all ranks switch on the same call)."""
+        the (shape, lane) -- every rank counts alike, so all ranks switch on the same call of that lane."""
         from .index import GRAPH_AFTER, capture_on_side_stream
 
-        key = ("host", b, k, float(ratio_thresh), merged)
+        key = ("host", b, k, float(ratio_thresh), merged, lane)
         g = self._graphs.get(key)
         if g is None:
             g = self._graphs[key] = {"calls": 0, "graph": None, "dead": bool(os.environ.get("TT_NO_GRAPH"))}
@@ -443,24 +449,25 @@ class ShardedIndex:
         if g["dead"] or g["calls"] <= GRAPH_AFTER:
             return None
         local = self.local
-        rec = local._record(b, k, merged, extra_f32=pb.world * b)
+        rec = local._record(b, k, merged, extra_f32=pb.world * b, lane=lane)
         q_pin = torch.zeros((b, local.dim), dtype=torch.float32).pin_memory()
         q_dev = torch.zeros((b, local.dim), dtype=torch.float32, device=self.device)
         out = {}
 
         def fn():
             q_dev.copy_(q_pin, non_blocking=True)
-            out["r"] = self._host_round(pb, q_dev, rec, b, k, ratio_thresh, merged)
+            out["r"] = self._host_round(pb, q_dev, rec, b, k, ratio_thresh, merged, lane)
             rec["host"].copy_(rec["dev"], non_blocking=True)
 
         # the eager run inside capture_on_side_stream is a real exchange round (with whatever q_pin holds: zeros);
-        # every rank makes it, so the lane's epochs stay in lockstep
+        # every rank makes it, so the lane's epochs stay in lockstep.  The capture never waits for the device
+        # (index.capturing), so holding the capture lock cannot stall a peer
         with local._on_device():
             graph, _ = capture_on_side_stream(self.device, fn)
         g.update(graph=graph, q_pin=q_pin, q_pin_np=q_pin.numpy(), q_dev=q_dev, result=out["r"], rec=rec)
         return g
 
-    def _host_phases(self, pb, q_host, b, k, ratio_thresh, merged):
+    def _host_phases(self, pb, q_host, b, k, ratio_thresh, merged, lane=0):
         """Peer transport, ONE host synchronisation per query batch: the selecting kernel pushes this rank's record AND
         its certificate margins to every peer, the merging kernel copies all ranks' margins into the result record, so
         they come back with the answer.  Only if some rank's top-k was not proven (every rank sees that, from identical
@@ -470,7 +477,7 @@ class ShardedIndex:
         import ctypes as C
 
         local = self.local
-        g = self._host_graph(pb, b, k, ratio_thresh, merged) if self._local is None else None
+        g = self._host_graph(pb, b, k, ratio_thresh, merged, lane) if self._local is None else None
         if g is not None:
             if q_host.dtype == torch.float32 and q_host.device.type == "cpu":
                 g["q_pin_np"][...] = q_host.numpy()  # the common case: a plain memory copy into the pinned staging buffer
@@ -481,10 +488,10 @@ class ShardedIndex:
                 g["graph"].replay()
         else:
             q = local._check_queries(q_host.to(self.device, torch.float32, non_blocking=True))
-            rec = local._record(b, k, merged, extra_f32=pb.world * b)
-            r = self._host_push(pb, q, rec, b, k)
+            rec = local._record(b, k, merged, extra_f32=pb.world * b, lane=lane)
+            r = self._host_push(pb, q, rec, b, k, lane)
             yield
-            self._host_merge(pb, rec, b, k, ratio_thresh, merged)
+            self._host_merge(pb, rec, b, k, ratio_thresh, merged, lane)
             rec["host"].copy_(rec["dev"], non_blocking=True)
         self.last = r
         self._lib.check(self._lib.lib().tt_stream_synchronize(local._stream()))
@@ -494,23 +501,25 @@ class ShardedIndex:
         if not proven.all():
             mine = (~proven[pb.rank]).nonzero()[0]
             if mine.size:
-                local._repair(q, k, r, torch.from_numpy(mine).to(self.device), hi_lo_first=r.hi_only)
-            send, s_keys, s_ids, s_margins = pb.send_record()
+                with local._repair_lock:  # the ladder's workspaces are shared between lanes; nothing in it waits for a peer
+                    local._repair(q, k, r, torch.from_numpy(mine).to(self.device), hi_lo_first=r.hi_only)
+                    self._lib.check(self._lib.lib().tt_stream_synchronize(local._stream()))
+            send, s_keys, s_ids, s_margins = pb.send_record(lane)
             s_keys.copy_(r.keys)
             s_ids.copy_(r.ids)
             s_margins.fill_(float("inf"))         # what is sent now is exact (proven before, or repaired)
             with local._on_device():
-                self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), pb.rec_bytes // 4 * 4, C.byref(pb.desc(0)),
+                self._lib.check(self._lib.lib().tt_exchange_push(send.data_ptr(), pb.rec_bytes // 4 * 4, C.byref(pb.desc(lane)),
                                                                  local._stream()))
             yield
-            scores, mids = self._merge_pulled(pb, 0, b, k, k, ("host", 1))
-            rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged)
+            scores, mids = self._merge_pulled(pb, lane, b, k, k, ("host2", lane))
+            rec = self._finish_host(mids, scores, b, k, ratio_thresh, merged, lane=lane)
             rec["event"].synchronize()
             self._lib.check_status(local._dev_index)
             self.second_rounds += 1
         return self._unpack_host(rec, merged)
 
-    def _retrieve_host_phases(self, q_host, k, ratio_thresh, merge):
+    def _retrieve_host_phases(self, q_host, k, ratio_thresh, merge, lane=0):
         """``retrieve_host`` as a phased procedure (peer transport), or None when this index exchanges through NCCL."""
         merged = bool(merge and self.local.tree is not None)
         if q_host.dim() != 2 or q_host.shape[1] != self.local.dim:
@@ -519,13 +528,39 @@ class ShardedIndex:
         if self.transport == "peer":
             pb0 = self.peers(b, k)
             if pb0 is not None:
-                return self._host_phases(pb0, q_host, b, k, ratio_thresh, merged)
+                return self._host_phases(pb0, q_host, b, k, ratio_thresh, merged, lane)
         return None
 
-    def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True):
+    def _lane_ctx(self, lane: int):
+        """Lock + stream of a host lane: lane 0 runs on the caller's current stream, the others on their own."""
+        if not 0 <= lane < self.LANES:
+            raise ValueError(f"lane {lane}: this index has {self.LANES} lanes")
+        stack = contextlib.ExitStack()
+        stack.enter_context(self._lane_locks[lane])
+        if lane:
+            st = self._lane_streams.get(lane)
+            if st is None:
+                st = self._lane_streams[lane] = torch.cuda.Stream(self.device)
+                st.wait_stream(torch.cuda.current_stream(self.device))
+            stack.enter_context(torch.cuda.stream(st))
+        return stack
+
+    def retrieve_host(self, q_host, k, ratio_thresh: float = 0.5, merge: bool = True, lane: int = 0):
         """Host queries in, merged (+ auto-merged) lists out (numpy), with the certificate enforced per rank.
-        Same contract as ``DeviceIndex.retrieve_host``, so the retriever classes take either; every rank must call it."""
-        phases = self._retrieve_host_phases(q_host, k, ratio_thresh, merge)
+        Same contract as ``DeviceIndex.retrieve_host``, so the retriever classes take either; every rank must call it.
+
+        ``lane`` (< ``LANES``): concurrent callers -- one serving thread per lane -- are pipelined, each lane with its own
+        stream, exchange ring, buffers and captured graph, so one caller's exchange + host work overlaps the other's
+        corpus scan.  Unlike ``DeviceIndex`` the lane is the CALLER's choice: every rank must issue the same sequence of
+        queries per lane, which only the caller can arrange (thread t of every rank serves lane t).  Calls on the same lane
+        are serialised.  The NCCL transport has one lane: its collectives are ordered process-wide."""
+        if self.transport != "peer":
+            lane = 0
+        with self._lane_ctx(lane):
+            return self._retrieve_host_locked(q_host, k, ratio_thresh, merge, lane)
+
+    def _retrieve_host_locked(self, q_host, k, ratio_thresh, merge, lane):
+        phases = self._retrieve_host_phases(q_host, k, ratio_thresh, merge, lane)
         if phases is not None:
             return self._run(phases)
         merged = bool(merge and self.local.tree is not None)

@@ -607,6 +607,60 @@ def test_near_duplicate_corpus_walks_the_repair_ladder():
     assert _np(r.ids)[0].tolist() == [123, 5000, 39_999]
 
 
+def test_concurrent_callers_are_pipelined_over_host_lanes_and_stay_exact():
+    """Four threads call retrieve_host of ONE index at once: at most HOST_LANES calls are in flight (own stream, buffers,
+    record and graph per lane), the others wait for a lane; easy queries (proven by the certificate) and hard ones (between
+    near-duplicate rows: repaired under the shared repair lock) interleave, past the point where each lane captures its
+    graph.  Every answer must be the oracle's."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from tensor_truth_b200.index import HOST_LANES
+
+    rng = np.random.default_rng(23)
+    tree, bits0, inv, q0 = make_small(20_000, 8, dim=1024, levels=3, seed=41)
+    base = rng.standard_normal(1024).astype(np.float32)
+    dup = oracle.f32_to_bf16_bits(base[None, :] * (1.0 + 2e-3 * rng.standard_normal((20_000, 1024)).astype(np.float32)))
+    bits = np.concatenate([bits0, dup])
+    hard = (base[None, :] * (1.0 + 1e-3 * rng.standard_normal((4, 1024)))).astype(np.float32)
+    q = np.concatenate([q0, hard])                       # 8 easy + 4 hard
+    ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
+    idx = _index(bits, None)
+    in_flight, peak, guard = [0], [0], __import__("threading").Lock()
+    orig = idx._host_lane
+
+    def counted():
+        ctx = orig()
+
+        class Wrap:
+            def __enter__(self_w):
+                lane = ctx.__enter__()
+                with guard:
+                    in_flight[0] += 1
+                    peak[0] = max(peak[0], in_flight[0])
+                return lane
+
+            def __exit__(self_w, *a):
+                with guard:
+                    in_flight[0] -= 1
+                return ctx.__exit__(*a)
+
+        return Wrap()
+
+    idx._host_lane = counted
+
+    def one(i):
+        qi = i % len(q)
+        ids, scores, lens = idx.retrieve_host(torch.from_numpy(q[qi:qi + 1]), 10, merge=False)
+        return qi, ids[0], scores[0]
+
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        got = list(pool.map(one, range(72)))
+    for qi, ids, scores in got:
+        assert (ids == ids_o[qi]).all() and (scores == sc_o[qi].astype(np.float64)).all(), qi
+    assert idx.fallbacks > 0 and 1 <= peak[0] <= HOST_LANES
+    assert sum(1 for key in idx._ws if isinstance(key, tuple) and key[0] == "graph" and idx._ws[key]["graph"] is not None) >= 1
+
+
 def test_empty_index_and_empty_batch():
     bits = np.zeros((0, 128), np.uint16)
     idx = _index(bits, None)
@@ -630,7 +684,7 @@ def test_retrieve_host_graph_replay_equals_eager(c1, monkeypatch):
     want = [eager.retrieve_host(torch.from_numpy(q[i:i + 1]), 10) for i in range(12)]
     monkeypatch.setattr(index_mod, "GRAPH_AFTER", 2)        # ... `idx` does on its third call
     got = [idx.retrieve_host(torch.from_numpy(q[i:i + 1]), 10) for i in range(12)]
-    g = idx._ws[("graph", 1, 10, 0.5, True)]
+    g = idx._ws[("graph", 1, 10, 0.5, True, 0)]
     assert g["graph"] is not None, "the pipeline was not captured"
     for a, b in zip(want, got):
         for x, y in zip(a, b):
@@ -643,7 +697,7 @@ def test_retrieve_host_graph_replay_equals_eager(c1, monkeypatch):
         ids_b, sc_b, lens_b = idx.retrieve_host(torch.from_numpy(q[8 * rep:8 * rep + 8]), 10, merge=False)
         ids_o, sc_o, _ = cport.scan_topk(bits, q[8 * rep:8 * rep + 8], 10)
         assert (ids_b == ids_o).all() and (sc_b == sc_o.astype(np.float64)).all()
-    assert idx._ws[("graph", 8, 10, 0.5, False)]["graph"] is not None
+    assert idx._ws[("graph", 8, 10, 0.5, False, 0)]["graph"] is not None
 
 
 def test_graph_replay_still_repairs_unproven_queries(monkeypatch):
@@ -660,7 +714,7 @@ def test_graph_replay_still_repairs_unproven_queries(monkeypatch):
     for i in range(6):
         ids, scores, lens = idx.retrieve_host(torch.from_numpy(q[i:i + 1]), 10, merge=False)
         assert (ids[0] == ids_o[i]).all() and (scores[0] == sc_o[i].astype(np.float64)).all()
-    assert idx._ws[("graph", 1, 10, 0.5, False)]["graph"] is not None and idx.fallbacks >= 4
+    assert idx._ws[("graph", 1, 10, 0.5, False, 0)]["graph"] is not None and idx.fallbacks >= 4
 
 
 def test_c2_full_size_10m_rows_properties():

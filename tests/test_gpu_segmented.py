@@ -70,7 +70,7 @@ def test_segmented_retrieve_host_equals_per_index_retrieve(parts):
             got = [(seg.segment_of(int(o)), float(sc)) for o, sc in zip(ids[s, 0, :lens[s, 0]], scores[s, 0, :lens[s, 0]])]
             assert [(g[0][1], g[1]) for g in got] == exp, (rep, s)
             assert all(g[0][0] == s for g in got)
-    assert seg._ws[("graph", 1, 10, 0.5, True)]["graph"] is not None
+    assert seg._ws[("graph", 1, 10, 0.5, True, 0)]["graph"] is not None
 
 
 @pytest.mark.parametrize("strategy", ["top_k_per_index", "none"])

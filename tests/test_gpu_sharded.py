@@ -83,6 +83,31 @@ def _worker(rank, world, port, transport, out_dir):
             ids_h, sc_h, lens = sh.retrieve_host(torch.from_numpy(q[rep:rep + 1]), 10)
             exp = oracle.retrieve(bits, q[rep], 10, tree)
             assert [(int(o), float(s)) for o, s in zip(ids_h[0, :lens[0]], sc_h[0, :lens[0]])] == exp, rep
+    if transport == "peer":
+        # two serving threads per rank, thread t on lane t of every rank (different query sequences per lane), past the
+        # point where each lane captures its graph: the lanes' exchanges interleave freely, every answer is the oracle's
+        import threading
+
+        errs = []
+
+        def serve(t):
+            try:
+                torch.cuda.set_device(rank)
+                for i in range(10):
+                    qi = (7 * t + 3 * i) % 64
+                    ids_t, sc_t, lens_t = sh.retrieve_host(torch.from_numpy(q[qi:qi + 1]), 10, lane=t)
+                    exp_t = oracle.retrieve(bits, q[qi], 10, tree)
+                    assert [(int(o), float(s)) for o, s in zip(ids_t[0, :lens_t[0]], sc_t[0, :lens_t[0]])] == exp_t, (t, i)
+            except BaseException as exc:  # noqa: BLE001
+                errs.append(exc)
+
+        threads = [threading.Thread(target=serve, args=(t,)) for t in range(2)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errs:
+            raise errs[0]
     ids_h, sc_h, lens = sh.retrieve_host(torch.from_numpy(q[:3]), 10)
     for b in range(3):
         exp = oracle.retrieve(bits, q[b], 10, tree)
