@@ -271,13 +271,17 @@ class Bench:
             return self.idx.step_graph(batch, k, 0.5, lane)
         return None  # NCCL transport: eager steps
 
-    def timed(self, batch: int, steps: int, warm: int, sample_clocks: bool, depth: int, k: int = 0, pool=None):
+    def timed(self, batch: int, steps: int, warm: int, sample_clocks: bool, depth: int, k: int = 0, pool=None,
+              serial_graph: bool = False):
         """K steps of the device pipeline, queries resident in HBM.
         depth = 1: strictly serial on one stream, eager launches with CUDA events around every stage-1 launch (the
         roofline numbers; the host stays ahead of the GPU, so the events see device time only).
         depth = 2: the throughput configuration -- every lane (stream) replays the CUDA graph of the whole step
         (prepare -> scan -> re-score+select(+push) -> (flag-wait+merge+)auto-merge), steps alternate between the lanes, so
-        step i+1's scan overlaps step i's tail.  Both loops start behind a device-side rendezvous of all ranks."""
+        step i+1's scan overlaps step i's tail.
+        depth = 1 with ``serial_graph``: one lane's graph replayed back to back on one stream -- the serial step without
+        the host's launch gaps (what the device alone needs for scan + tail).
+        All loops start behind a device-side rendezvous of all ranks."""
         from tensor_truth_b200.index import MergeResult
 
         ctx, idx, sharded = self.ctx, self.idx, self.sharded
@@ -288,7 +292,7 @@ class Bench:
         margins = torch.full((steps + warm, batch), float("inf"), dtype=torch.float32, device=device)
         streams = [torch.cuda.Stream(device) for _ in range(depth)]
         eps = [idx.eps]
-        graphs = [self.step_graph(batch, k, s) for s in range(depth)] if depth > 1 else [None]
+        graphs = [self.step_graph(batch, k, s) for s in range(depth)] if (depth > 1 or serial_graph) else [None]
         use_graph = graphs[0] is not None
         launches = [0]
         if not use_graph:
@@ -326,7 +330,7 @@ class Bench:
         for st in streams:
             cur.wait_stream(st)
         ctx.barrier()
-        idx.scan_events = [] if depth == 1 else None
+        idx.scan_events = [] if (depth == 1 and not use_graph) else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sampler = ClockSampler(physical_index(ctx.local_rank)) if sample_clocks else None
         if sampler:
@@ -363,6 +367,7 @@ class Bench:
     def hbm_section(self, steps, warm, peak, peak_src, batch=1, sample_clocks=False, label=""):
         """Serial loop (roofline of the stage-1 kernel) + pipelined loop (throughput) at one batch size."""
         ser = self.timed(batch, steps, warm, False, depth=1)
+        sg = self.timed(batch, steps, warm, False, depth=1, serial_graph=True)
         pip = self.timed(batch, steps, warm, sample_clocks, depth=2)
         local_bytes = float(self.rows_local) * DIM * 2
         achieved = local_bytes / (ser["scan_ms"] / 1e3) / 1e9
@@ -370,10 +375,14 @@ class Bench:
             "value": steps * batch / (pip["ms"] / 1e3), "unit": UNIT, "ms_per_step": pip["ms"] / steps, "steps": steps,
             "warmup": warm, "batch": batch, "k": self.k, "rows_total": self.n_rows, "rows_per_gpu": self.rows_local,
             "serial": {"value": steps * batch / (ser["ms"] / 1e3), "ms_per_step": ser["ms"] / steps},
+            "serial_graph": ({"value": steps * batch / (sg["ms"] / 1e3), "ms_per_step": sg["ms"] / steps,
+                              "note": "same K steps, one lane's CUDA graph replayed back to back on one stream: no overlap between "
+                                      "steps and no host launch gaps"} if sg["graph"] else None),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "scan_tc_kernel", "bytes_per_launch": local_bytes,
                          "kernel_ms": ser["scan_ms"], "peak_source": peak_src,
                          "step_share": ser["scan_ms"] * ser["scan_calls_per_step"] / (ser["ms"] / steps),
+                         "step_share_graph": (ser["scan_ms"] * ser["scan_calls_per_step"] / (sg["ms"] / steps)) if sg["graph"] else None,
                          "measured_in": "serial loop, CUDA events around each stage-1 launch"},
             "hbm_frac_of_step": local_bytes / (pip["ms"] / steps / 1e3) / 1e9 / peak,
             "certificate_failures": ser["bad"] + pip["bad"], "min_margin": pip["min_margin"], "eps": pip["eps"],
@@ -837,6 +846,7 @@ def run_b200(args):
             "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": args.warmup,
             "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "serial": dict(head["serial"], note="same K steps with no overlap between consecutive steps (one stream, eager launches)"),
+            "serial_graph": head.get("serial_graph"),
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"{args.tag}: exact cosine top-{TOP_K} + auto-merge, {args.rows} x {DIM} bf16 leaf embeddings, "
                                    f"{LEVELS}-level tree, batch-1 queries, corpus row-sharded over {world} GPU(s)",

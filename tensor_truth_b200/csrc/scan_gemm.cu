@@ -52,6 +52,7 @@ struct Params {
 };
 
 constexpr int STG_CAP = 64;  // staged survivors per epilogue warp (16 B each)
+constexpr int DIRECT_MIN = 24;  // survivors in a 32 x 32 chunk from which they bypass the staging (one reservation per column)
 constexpr int SCHED_SLOTS = 4;  // work-item ring between CTA 0's producer and every other role of the pair
 
 // v[j] for a warp-uniform j: a select tree instead of dynamic register indexing
@@ -337,6 +338,30 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
                     if (!row_ok) hm = 0u;
                     uint32_t any = __reduce_or_sync(0xffffffffu, hm);
                     const int q0 = qb * NQB + col0 + c32;
+                    if (__reduce_add_sync(0xffffffffu, __popc(hm)) >= DIRECT_MIN) {
+                        // a dense chunk (the early phases, whose thresholds are still weak): ONE reservation per query
+                        // column -- lane j reserves for column j, all 32 atomics in flight together -- and the entries go
+                        // straight to the buffers; the staged path would pay an atomic round trip per 32 survivors.
+                        uint32_t mine = 0u;
+                        for (uint32_t rest = any; rest; rest &= rest - 1u) {
+                            const int j = __ffs(rest) - 1;
+                            const uint32_t who = __ballot_sync(0xffffffffu, (hm >> j) & 1u);
+                            if (lane == j) mine = who;
+                        }
+                        int base = 0;
+                        if (mine) base = atomicAdd(p.cnt + q0 + lane, __popc(mine));
+                        for (uint32_t rest = any; rest; rest &= rest - 1u) {
+                            const int j = __ffs(rest) - 1;
+                            const uint32_t who = __shfl_sync(0xffffffffu, mine, j);
+                            const int b0 = __shfl_sync(0xffffffffu, base, j);
+                            const float val = pick32(v, j) * inv;
+                            if ((hm >> j) & 1u) {
+                                const int slot = b0 + __popc(who & ((1u << lane) - 1u));
+                                if (slot < p.cap) p.buf[size_t(q0 + j) * p.cap + slot] = pack_entry(val, uint32_t(row));
+                            }
+                        }
+                        any = 0u;
+                    }
                     while (any) {
                         const int j = __ffs(any) - 1;
                         any &= any - 1u;
@@ -505,9 +530,19 @@ static uint32_t pick_perm_mul(uint32_t n) {
 
 }  // namespace tc3
 
+// Entries a query's survivor buffer holds.  A phase appends about growth x K' entries per query (the rows that beat the
+// K'-th score of the rows seen before it), so 16 K' leaves a 4x margin at growth 4.  Small batches -- the HBM-bound
+// regime, where every extra phase costs a launch + ramp + cut (~15 us of a ~2.9 ms pass at 10M rows) -- get twice the
+// buffer and with it a dense first phase four to eight times as long and growth 8 at the same 4x margin: 5 phases
+// instead of 7 at 10M rows.  Measured at 10M rows: 32 queries hi+lo 2.94 -> 2.91 ms, 64 queries 3.01 -> 2.98 ms (top-10),
+// 3.21 -> 3.07 ms (top-100).  Not beyond 64 queries: a dense tile appends 256 x n_q entries through the staging
+// buffers, and at 128 queries the longer dense phase costs more than the phases saved (3.20 -> 3.46 ms).
+static inline bool gemm_small_batch(int n_q, int kprime) { return n_q <= 64 && kprime <= 256; }
+static inline int gemm_cap(int n_q, int kprime) { return (gemm_small_batch(n_q, kprime) ? 32 : 16) * kprime; }
+
 size_t scan_gemm_workspace_bytes(int n_q, int kprime) {
     const size_t n_pad = size_t((n_q + tc3::NQB_MAX - 1) / tc3::NQB_MAX) * tc3::NQB_MAX;
-    return 3 * n_pad * 4 + 16 /* work-item counter */ + size_t(n_q) * size_t(16 * kprime) * 8;
+    return 3 * n_pad * 4 + 16 /* work-item counter */ + size_t(n_q) * size_t(gemm_cap(n_q, kprime)) * 8;
 }
 
 bool scan_gemm_supported(int dim, int kprime, int n_lists) {
@@ -524,7 +559,8 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
     constexpr int STAGE_BYTES = CH * (CHUNK_BYTES + NH * 128);
     const int n_qb = (n_q + NQB - 1) / NQB;
     const int n_pad = (n_q + NQB_MAX - 1) / NQB_MAX * NQB_MAX;  // the layout scan_gemm_workspace_bytes() sized
-    const int cap = 16 * kprime;
+    const bool small = gemm_small_batch(n_q, kprime) && !getenv("TT_GEMM_SMALL_OFF");
+    const int cap = gemm_cap(n_q, kprime);
     int* cnt = reinterpret_cast<int*>(ws);
     float* tau = reinterpret_cast<float*>(cnt + n_pad);
     int* ovf = reinterpret_cast<int*>(tau + n_pad);
@@ -574,15 +610,16 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
     TT_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_LIMIT));
     TT_CUDA_OK(cudaFuncSetAttribute(gemm_cut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (cap + kprime) * 8));
 
-    // phases: the first visits ~4 K' rows, each later one `growth` times the rows visited before it
-    int growth = 4;
+    // phases: the first visits ~4 K' rows (small batches: as many rows as the buffer holds -- it is dense, every row of
+    // it is appended), each later one `growth` times the rows visited before it
+    int growth = small ? 8 : 4;
     if (const char* e = getenv("TT_GEMM_GROWTH")) {
         const int g = atoi(e);
         if (g >= 1 && g <= 64) growth = g;
     }
     const int grid = n_sms & ~1;
     int seen = 0;
-    int next = (4 * kprime + 255) / 256;
+    int next = small ? cap / 256 : (4 * kprime + 255) / 256;
     bool done = p.n_super == 0;
     if (done) {
         gemm_cut_kernel<<<n_q, CUT_THREADS, (cap + kprime) * 8, st>>>(buf, cnt, tau, ovf, cap, kprime, 1, id_base, out_ids,
