@@ -537,7 +537,13 @@ static uint32_t pick_perm_mul(uint32_t n) {
 // instead of 7 at 10M rows.  Measured at 10M rows: 32 queries hi+lo 2.94 -> 2.91 ms, 64 queries 3.01 -> 2.98 ms (top-10),
 // 3.21 -> 3.07 ms (top-100).  Not beyond 64 queries: a dense tile appends 256 x n_q entries through the staging
 // buffers, and at 128 queries the longer dense phase costs more than the phases saved (3.20 -> 3.46 ms).
-static inline bool gemm_small_batch(int n_q, int kprime) { return n_q <= 64 && kprime <= 256; }
+static inline bool gemm_small_batch(int n_q, int kprime) {
+    static const int max_q = [] {
+        const char* e = getenv("TT_GEMM_SMALL_MAX");  // tuning knob
+        return e ? atoi(e) : 64;
+    }();
+    return n_q <= max_q && kprime <= 256;
+}
 static inline int gemm_cap(int n_q, int kprime) { return (gemm_small_batch(n_q, kprime) ? 32 : 16) * kprime; }
 
 size_t scan_gemm_workspace_bytes(int n_q, int kprime) {
