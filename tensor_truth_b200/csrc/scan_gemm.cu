@@ -49,6 +49,7 @@ struct Params {
     unsigned long long* buf;  // [n_q, cap] packed (approx key, local row) entries
     int* cnt;             // [>= n_qb * NQB] entries appended so far (may exceed cap: overflow)
     int cap;
+    int direct_min;       // survivors in a 32 x 32 chunk from which they bypass the staging (DIRECT_MIN; tuning knob)
 };
 
 constexpr int STG_CAP = 64;  // staged survivors per epilogue warp (16 B each)
@@ -338,7 +339,7 @@ scan_gemm_kernel(const __grid_constant__ CUtensorMap map_c, const __grid_constan
                     if (!row_ok) hm = 0u;
                     uint32_t any = __reduce_or_sync(0xffffffffu, hm);
                     const int q0 = qb * NQB + col0 + c32;
-                    if (__reduce_add_sync(0xffffffffu, __popc(hm)) >= DIRECT_MIN) {
+                    if (__reduce_add_sync(0xffffffffu, __popc(hm)) >= p.direct_min) {
                         // a dense chunk (the early phases, whose thresholds are still weak): ONE reservation per query
                         // column -- lane j reserves for column j, all 32 atomics in flight together -- and the entries go
                         // straight to the buffers; the staged path would pay an atomic round trip per 32 survivors.
@@ -602,6 +603,8 @@ static int run_phases(const void* corpus, int64_t n_rows, int dim, int64_t strid
     p.buf = buf;
     p.cnt = cnt;
     p.cap = cap;
+    p.direct_min = DIRECT_MIN;
+    if (const char* e = getenv("TT_GEMM_DIRECT_MIN")) p.direct_min = atoi(e) > 0 ? atoi(e) : DIRECT_MIN;
 
     CUtensorMap map_c, map_q, map_q2;
     if (n_rows > 0) {
