@@ -18,23 +18,32 @@ namespace tt {
 constexpr int SIMT_THREADS = 512;
 constexpr int SIMT_WARPS = SIMT_THREADS / 32;
 
+// Row access is split in two: `fetch` only issues the 16-byte global loads of one 8-element chunk, `unpack` turns them
+// into floats.  The scan loop fetches several chunks of both rows before it unpacks the first one, so that every warp
+// keeps a few KB in flight (ncu had the exact scan latency-bound -- long-scoreboard stalls, DRAM at 34 % -- with one chunk
+// per row in flight).
 template <typename CT>
 struct RowLoader;
 template <>
 struct RowLoader<__nv_bfloat16> {
-    // chunk = 8 consecutive elements
-    __device__ static __forceinline__ void load(const __nv_bfloat16* row, int chunk, float* f) {
-        uint4 v = ldg_stream_u4(reinterpret_cast<const uint4*>(row) + chunk);
-        unpack_bf16x8(v, f);
+    struct Raw { uint4 v; };
+    static constexpr int DEPTH = 4;  // chunks per row fetched ahead: 2 rows x 4 x 512 B = 4 KB per warp
+    __device__ static __forceinline__ Raw fetch(const __nv_bfloat16* row, int chunk) {
+        return Raw{ldg_stream_u4(reinterpret_cast<const uint4*>(row) + chunk)};
     }
+    __device__ static __forceinline__ void unpack(const Raw& r, float* f) { unpack_bf16x8(r.v, f); }
 };
 template <>
 struct RowLoader<float> {
-    __device__ static __forceinline__ void load(const float* row, int chunk, float* f) {
-        uint4 a = ldg_stream_u4(reinterpret_cast<const uint4*>(row) + 2 * chunk);
-        uint4 b = ldg_stream_u4(reinterpret_cast<const uint4*>(row) + 2 * chunk + 1);
-        f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
-        f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+    struct Raw { uint4 a, b; };
+    static constexpr int DEPTH = 2;  // 2 rows x 2 x 1 KB = 4 KB per warp
+    __device__ static __forceinline__ Raw fetch(const float* row, int chunk) {
+        return Raw{ldg_stream_u4(reinterpret_cast<const uint4*>(row) + 2 * chunk),
+                   ldg_stream_u4(reinterpret_cast<const uint4*>(row) + 2 * chunk + 1)};
+    }
+    __device__ static __forceinline__ void unpack(const Raw& r, float* f) {
+        f[0] = __uint_as_float(r.a.x); f[1] = __uint_as_float(r.a.y); f[2] = __uint_as_float(r.a.z); f[3] = __uint_as_float(r.a.w);
+        f[4] = __uint_as_float(r.b.x); f[5] = __uint_as_float(r.b.y); f[6] = __uint_as_float(r.b.z); f[7] = __uint_as_float(r.b.w);
     }
 };
 
@@ -119,25 +128,40 @@ scan_simt_kernel(const CT* __restrict__ corpus, int64_t n_rows, int dim, int64_t
         Acc nn0 = Acc(0), nn1 = Acc(0);
 #pragma unroll
         for (int qi = 0; qi < QT; ++qi) { dot0[qi] = Acc(0); dot1[qi] = Acc(0); }
-        for (int c = lane; c < chunks; c += 32) {
-            float f0[8], f1[8];
-            RowLoader<CT>::load(row0, c, f0);
-            RowLoader<CT>::load(row1, c, f1);
-            Acc a0[8], a1[8];
+        constexpr int DEPTH = RowLoader<CT>::DEPTH;
+        for (int cb = lane; cb < chunks; cb += 32 * DEPTH) {
+            typename RowLoader<CT>::Raw raw0[DEPTH], raw1[DEPTH];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { a0[e] = Acc(f0[e]); a1[e] = Acc(f1[e]); }
-            if (EXACT) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { nn0 += a0[e] * a0[e]; nn1 += a1[e] * a1[e]; }
+            for (int u = 0; u < DEPTH; ++u) {
+                const int c = cb + 32 * u;
+                if (c < chunks) {
+                    raw0[u] = RowLoader<CT>::fetch(row0, c);
+                    raw1[u] = RowLoader<CT>::fetch(row1, c);
+                }
             }
 #pragma unroll
-            for (int qi = 0; qi < QT; ++qi) {
-                Acc qv[8];
-                QLayout<Acc>::load8(q_s + qi * dim, c, chunks, qv);
+            for (int u = 0; u < DEPTH; ++u) {
+                const int c = cb + 32 * u;
+                if (c >= chunks) break;
+                float f0[8], f1[8];
+                RowLoader<CT>::unpack(raw0[u], f0);
+                RowLoader<CT>::unpack(raw1[u], f1);
+                Acc a0[8], a1[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    dot0[qi] += qv[e] * a0[e];
-                    dot1[qi] += qv[e] * a1[e];
+                for (int e = 0; e < 8; ++e) { a0[e] = Acc(f0[e]); a1[e] = Acc(f1[e]); }
+                if (EXACT) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { nn0 += a0[e] * a0[e]; nn1 += a1[e] * a1[e]; }
+                }
+#pragma unroll
+                for (int qi = 0; qi < QT; ++qi) {
+                    Acc qv[8];
+                    QLayout<Acc>::load8(q_s + qi * dim, c, chunks, qv);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        dot0[qi] += qv[e] * a0[e];
+                        dot1[qi] += qv[e] * a1[e];
+                    }
                 }
             }
         }
@@ -251,19 +275,22 @@ int scan_simt_exact(const void* corpus, int corpus_dtype, int64_t n_rows, int di
                     const float* q_f32, int n_q, int kprime, int64_t id_base, int mode,
                     uint64_t* out_packed, int n_lists, cudaStream_t st, const float* row_gate) {
     const int E = kprime_to_E(kprime);
-#define TT_SIMT_X(EE, CT)                                                                                       \
-    return launch_simt<EE, 1, CT, double, true>(corpus, n_rows, dim, stride, row_gate, nullptr, nullptr, q_f32, n_q, \
-                                                id_base, mode, nullptr, nullptr, nullptr, out_packed, n_lists, st)
+    // several queries per corpus pass when there are several (a batch of failed certificates, the parity checks): the
+    // rows are loaded, widened and squared once for all of them
+#define TT_SIMT_X(EE, QQ, CT)                                                                                    \
+    return launch_simt<EE, QQ, CT, double, true>(corpus, n_rows, dim, stride, row_gate, nullptr, nullptr, q_f32, n_q, \
+                                                 id_base, mode, nullptr, nullptr, nullptr, out_packed, n_lists, st)
+    const int qt = n_q >= 3 ? 4 : n_q == 2 ? 2 : 1;
     if (corpus_dtype == TT_DTYPE_BF16) {
-        if (E == 1) TT_SIMT_X(1, __nv_bfloat16);
-        if (E == 2) TT_SIMT_X(2, __nv_bfloat16);
-        if (E == 4) TT_SIMT_X(4, __nv_bfloat16);
-        if (E == 8) TT_SIMT_X(8, __nv_bfloat16);
+        if (E == 1) { if (qt == 4) TT_SIMT_X(1, 4, __nv_bfloat16); if (qt == 2) TT_SIMT_X(1, 2, __nv_bfloat16); TT_SIMT_X(1, 1, __nv_bfloat16); }
+        if (E == 2) { if (qt >= 2) TT_SIMT_X(2, 2, __nv_bfloat16); TT_SIMT_X(2, 1, __nv_bfloat16); }
+        if (E == 4) TT_SIMT_X(4, 1, __nv_bfloat16);
+        if (E == 8) TT_SIMT_X(8, 1, __nv_bfloat16);
     } else {
-        if (E == 1) TT_SIMT_X(1, float);
-        if (E == 2) TT_SIMT_X(2, float);
-        if (E == 4) TT_SIMT_X(4, float);
-        if (E == 8) TT_SIMT_X(8, float);
+        if (E == 1) { if (qt == 4) TT_SIMT_X(1, 4, float); if (qt == 2) TT_SIMT_X(1, 2, float); TT_SIMT_X(1, 1, float); }
+        if (E == 2) { if (qt >= 2) TT_SIMT_X(2, 2, float); TT_SIMT_X(2, 1, float); }
+        if (E == 4) TT_SIMT_X(4, 1, float);
+        if (E == 8) TT_SIMT_X(8, 1, float);
     }
 #undef TT_SIMT_X
     set_error("k %d unsupported by the exact scan", kprime);
