@@ -543,8 +543,8 @@ def test_c5_shape_four_levels_top200():
         assert any(o >= tree.level_offsets[2] for o, _ in got)  # merges cascade at least two levels up
 
 
-@pytest.mark.parametrize("mode", ["default_l2_exp", "cosine"])
-def test_importer_end_to_end_fp32_store(mode):
+@pytest.mark.parametrize("mode", ["default_l2_exp", "cosine", "persisted_docstore_json"])
+def test_importer_end_to_end_fp32_store(mode, tmp_path):
     """a (duck-typed) Chroma collection + docstore snapshot -> DeviceIndex -> retriever; the stored
     embeddings are fp32, so the scan runs on the bf16 shadow and the exact answer comes from the fp32 master.
     By default the importer scores like the reference's Chroma collection (exp(-squared L2)): the merged parents' mean
@@ -552,7 +552,7 @@ def test_importer_end_to_end_fp32_store(mode):
     from tensor_truth_b200.importer import load_device_index
     from tensor_truth_b200.retriever import B200AutoMergingRetriever, B200VectorIndexRetriever, NodeTable
     from tensor_truth_b200.schema import QueryBundle
-    from test_host_logic import _fake_docstore
+    from test_host_logic import _fake_docstore, _persisted_docstore
 
     tree, bits, inv, q = make_small(20_000, 6, dim=256, levels=3, seed=21)
     emb = oracle.bf16_bits_to_f32(bits) * (1.0 + 1e-3 * np.random.default_rng(0).standard_normal(bits.shape).astype(np.float32))
@@ -564,9 +564,13 @@ def test_importer_end_to_end_fp32_store(mode):
             assert include == ["embeddings"]
             return {"ids": [f"uuid-{o:05d}" for o in order], "embeddings": emb[order]}
 
-    kw = {} if mode == "default_l2_exp" else {"score_mode": _lib.SCORE_COSINE}
-    idx, nodes = load_device_index(Collection(), type("DS", (), {"docs": docs})(), device=torch.device("cuda:0"), **kw)
-    smode = _lib.SCORE_CHROMA_L2_EXP if mode == "default_l2_exp" else _lib.SCORE_COSINE
+    kw = {"score_mode": _lib.SCORE_COSINE} if mode == "cosine" else {}
+    docstore = type("DS", (), {"docs": docs})()
+    if mode == "persisted_docstore_json":  # the relations straight from the file on disk: no llama_index objects at all
+        (tmp_path / "docstore.json").write_text(json.dumps(_persisted_docstore(tree)))
+        docstore = str(tmp_path)
+    idx, nodes = load_device_index(Collection(), docstore, device=torch.device("cuda:0"), **kw)
+    smode = _lib.SCORE_COSINE if mode == "cosine" else _lib.SCORE_CHROMA_L2_EXP
     assert idx.score_mode == smode
     am = B200AutoMergingRetriever(B200VectorIndexRetriever(idx, 10, None, NodeTable(nodes=nodes)), None)
     merged_any = False

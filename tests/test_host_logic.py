@@ -179,6 +179,71 @@ def test_importer_flattens_docstore_and_collection():
     assert tree2.child_count[tree2.parent_of[stray[0]]] == len(nodes2[tree2.parent_of[stray[0]]].child_ids)
 
 
+def _persisted_docstore(tree):
+    """``docstore.json`` as upstream's SimpleDocumentStore persists it [U]: nodes wrapped in {"__data__", "__type__"},
+    relationships keyed by the NodeRelationship VALUE ("1" source ... "5" child), CHILD a list, the others single."""
+    nid = lambda o: f"uuid-{o:05d}"  # noqa: E731
+
+    def rel(o, node_type="1"):
+        return {"node_id": nid(o), "node_type": node_type, "metadata": {}, "hash": f"h{o}", "class_name": "RelatedNodeInfo"}
+
+    kids = {o: [] for o in range(tree.n_nodes)}
+    for o in range(tree.n_nodes):
+        if tree.parent_of[o] >= 0:
+            kids[int(tree.parent_of[o])].append(o)
+    data = {}
+    for o in range(tree.n_nodes):
+        r = {"1": {"node_id": "doc-0", "node_type": "4", "metadata": {}, "hash": "d", "class_name": "RelatedNodeInfo"}}
+        if tree.prev_id[o] >= 0:
+            r["2"] = rel(int(tree.prev_id[o]))
+        if tree.next_id[o] >= 0:
+            r["3"] = rel(int(tree.next_id[o]))
+        if tree.parent_of[o] >= 0:
+            r["4"] = rel(int(tree.parent_of[o]))
+        if kids[o]:
+            r["5"] = [rel(c) for c in kids[o]]
+        data[nid(o)] = {"__type__": "1",
+                        "__data__": {"id_": nid(o), "embedding": None, "metadata": {"file_name": "a.md", "page": o % 7},
+                                     "excluded_embed_metadata_keys": [], "excluded_llm_metadata_keys": [], "relationships": r,
+                                     "text": f"text {o}", "mimetype": "text/plain", "start_char_idx": 0, "end_char_idx": 6,
+                                     "text_template": "{metadata_str}\n\n{content}", "metadata_template": "{key}: {value}",
+                                     "metadata_seperator": "\n", "class_name": "TextNode"}}
+    return {"docstore/metadata": {k: {"doc_hash": "x", "ref_doc_id": "doc-0"} for k in data},
+            "docstore/data": data, "docstore/ref_doc_info": {"doc-0": {"node_ids": list(data), "metadata": {}}}}
+
+
+def test_importer_reads_the_persisted_docstore_json(tmp_path):
+    """The relations come out of ``docstore.json`` itself -- no llama_index -- and give the same flat tree as the loaded
+    docstore's node objects do (``flatten_index`` over either)."""
+    import json
+
+    from tensor_truth_b200.importer import StoredNode, flatten_index, load_docstore_json
+
+    t = build_uniform_tree(300, levels=3, seed=2)
+    index_dir = tmp_path / "index"
+    index_dir.mkdir()
+    (index_dir / "docstore.json").write_text(json.dumps(_persisted_docstore(t)))
+    stored = load_docstore_json(str(index_dir))            # the directory, as document_index.py:138 names the file
+    assert stored.keys() == load_docstore_json(str(index_dir / "docstore.json")).keys()
+    assert len(stored) == t.n_nodes and all(isinstance(n, StoredNode) for n in stored.values())
+    n0 = stored["uuid-00000"]
+    assert n0.node_id == "uuid-00000" and n0.get_content() == "text 0" and n0.metadata == {"file_name": "a.md", "page": 0}
+    assert n0.source_node.node_id == "doc-0" and n0.parent_node is not None and n0.child_nodes is None
+    rng = np.random.default_rng(1)
+    order = rng.permutation(300)
+    leaf_ids = [f"uuid-{o:05d}" for o in order]
+    emb = rng.standard_normal((300, 16)).astype(np.float32)
+    corpus_a, tree_a, nodes_a = flatten_index(leaf_ids, emb, stored)
+    corpus_b, tree_b, nodes_b = flatten_index(leaf_ids, emb, _fake_docstore(t))
+    for name in ("parent_of", "child_count", "prev_id", "next_id"):
+        assert (getattr(tree_a, name) == getattr(tree_b, name)).all(), name
+    assert tree_a.n_leaf == tree_b.n_leaf == 300 and [n.id_ for n in nodes_a] == [n.id_ for n in nodes_b]
+    # a file that is not a SimpleDocumentStore dump is refused by name, not by a KeyError somewhere downstream
+    (index_dir / "other.json").write_text("{}")
+    with pytest.raises(ValueError, match="docstore/data"):
+        load_docstore_json(str(index_dir / "other.json"))
+
+
 def test_importer_defaults_to_the_score_the_reference_reports():
     """the reference opens Chroma with the default (squared-L2) space, ChromaVectorStore reports
     exp(-distance); the importer must default to that, refuse other spaces, and let the caller override."""
