@@ -119,75 +119,99 @@ scan_simt_kernel(const CT* __restrict__ corpus, int64_t n_rows, int dim, int64_t
     const int64_t n_warps = int64_t(gridDim.x) * SIMT_WARPS;
     const int64_t gw = int64_t(blockIdx.x) * SIMT_WARPS + warp;
 
-    for (int64_t r0 = gw; r0 < n_rows; r0 += 2 * n_warps) {
-        const int64_t r1 = r0 + n_warps;
-        const bool has1 = r1 < n_rows;
-        const CT* row0 = corpus + r0 * stride;
-        const CT* row1 = corpus + (has1 ? r1 : r0) * stride;
-        Acc dot0[QT], dot1[QT];
-        Acc nn0 = Acc(0), nn1 = Acc(0);
+    // The rows of a pair are consumed in fetch groups of DEPTH chunks per lane.  The loop is software-pipelined over the
+    // sequence of groups (across row pairs): the loads of group i + 1 are issued before group i is unpacked, so a warp
+    // has its next 4 KB in flight while it does the arithmetic of the current ones.
+    constexpr int DEPTH = RowLoader<CT>::DEPTH;
+    using Raw = typename RowLoader<CT>::Raw;
+    const int groups = (chunks + 32 * DEPTH - 1) / (32 * DEPTH);
+    auto fetch_group = [&](int64_t ra, int g, Raw (&x0)[DEPTH], Raw (&x1)[DEPTH]) {
+        const int64_t rb = ra + n_warps;
+        const CT* row0 = corpus + ra * stride;
+        const CT* row1 = corpus + (rb < n_rows ? rb : ra) * stride;
 #pragma unroll
-        for (int qi = 0; qi < QT; ++qi) { dot0[qi] = Acc(0); dot1[qi] = Acc(0); }
-        constexpr int DEPTH = RowLoader<CT>::DEPTH;
-        for (int cb = lane; cb < chunks; cb += 32 * DEPTH) {
-            typename RowLoader<CT>::Raw raw0[DEPTH], raw1[DEPTH];
-#pragma unroll
-            for (int u = 0; u < DEPTH; ++u) {
-                const int c = cb + 32 * u;
-                if (c < chunks) {
-                    raw0[u] = RowLoader<CT>::fetch(row0, c);
-                    raw1[u] = RowLoader<CT>::fetch(row1, c);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < DEPTH; ++u) {
-                const int c = cb + 32 * u;
-                if (c >= chunks) break;
-                float f0[8], f1[8];
-                RowLoader<CT>::unpack(raw0[u], f0);
-                RowLoader<CT>::unpack(raw1[u], f1);
-                Acc a0[8], a1[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { a0[e] = Acc(f0[e]); a1[e] = Acc(f1[e]); }
-                if (EXACT) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { nn0 += a0[e] * a0[e]; nn1 += a1[e] * a1[e]; }
-                }
-#pragma unroll
-                for (int qi = 0; qi < QT; ++qi) {
-                    Acc qv[8];
-                    QLayout<Acc>::load8(q_s + qi * dim, c, chunks, qv);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        dot0[qi] += qv[e] * a0[e];
-                        dot1[qi] += qv[e] * a1[e];
-                    }
-                }
+        for (int u = 0; u < DEPTH; ++u) {
+            const int c = (g * DEPTH + u) * 32 + lane;
+            if (c < chunks) {
+                x0[u] = RowLoader<CT>::fetch(row0, c);
+                x1[u] = RowLoader<CT>::fetch(row1, c);
             }
         }
-        // inv_norm doubles as the ROW GATE: a row whose entry is NaN does not exist for this search (metadata filters).
-        // The approximate scan inherits that from the arithmetic (NaN scores are never inserted); the exact scan, which
-        // computes its own norms, reads the array only for the gate.
-        float in0 = 1.f, in1 = 1.f;
-        if (inv_norm) { in0 = inv_norm[r0]; in1 = inv_norm[has1 ? r1 : r0]; }
-        const bool ok0 = in0 == in0, ok1 = has1 && in1 == in1;
-        if (EXACT) { nn0 = Acc(warp_sum_f64(double(nn0))); nn1 = Acc(warp_sum_f64(double(nn1))); }
+    };
+    Raw nxt0[DEPTH] = {}, nxt1[DEPTH] = {};
+    Acc dot0[QT], dot1[QT];
+    Acc nn0 = Acc(0), nn1 = Acc(0);
+    int64_t r0 = gw;
+    int g = 0;
+    if (r0 < n_rows) fetch_group(r0, 0, nxt0, nxt1);
+    while (r0 < n_rows) {
+        Raw cur0[DEPTH], cur1[DEPTH];
 #pragma unroll
-        for (int qi = 0; qi < QT; ++qi) {
-            float k0, k1;
+        for (int u = 0; u < DEPTH; ++u) { cur0[u] = nxt0[u]; cur1[u] = nxt1[u]; }
+        int g2 = g + 1;
+        int64_t r2 = r0;
+        if (g2 == groups) { g2 = 0; r2 += 2 * n_warps; }
+        if (r2 < n_rows) fetch_group(r2, g2, nxt0, nxt1);
+        if (g == 0) {
+            nn0 = Acc(0);
+            nn1 = Acc(0);
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) { dot0[qi] = Acc(0); dot1[qi] = Acc(0); }
+        }
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+            const int c = (g * DEPTH + u) * 32 + lane;
+            if (c >= chunks) break;
+            float f0[8], f1[8];
+            RowLoader<CT>::unpack(cur0[u], f0);
+            RowLoader<CT>::unpack(cur1[u], f1);
+            Acc a0[8], a1[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a0[e] = Acc(f0[e]); a1[e] = Acc(f1[e]); }
             if (EXACT) {
-                double d0 = warp_sum_f64(double(dot0[qi])), d1 = warp_sum_f64(double(dot1[qi]));
-                k0 = exact_key(d0, qq_s[qi], double(nn0), mode);
-                k1 = exact_key(d1, qq_s[qi], double(nn1), mode);
-            } else {
-                k0 = warp_sum_f32(float(dot0[qi])) * in0;
-                k1 = warp_sum_f32(float(dot1[qi])) * in1;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { nn0 += a0[e] * a0[e]; nn1 += a1[e] * a1[e]; }
             }
-            if (qi < nq_here) {
-                if (ok0) lists[qi].insert(pack_entry(k0, uint32_t(r0)));
-                if (ok1) lists[qi].insert(pack_entry(k1, uint32_t(r1)));
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) {
+                Acc qv[8];
+                QLayout<Acc>::load8(q_s + qi * dim, c, chunks, qv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    dot0[qi] += qv[e] * a0[e];
+                    dot1[qi] += qv[e] * a1[e];
+                }
             }
         }
+        if (g == groups - 1) {
+            const int64_t r1 = r0 + n_warps;
+            const bool has1 = r1 < n_rows;
+            // inv_norm doubles as the ROW GATE: a row whose entry is NaN does not exist for this search (metadata
+            // filters).  The approximate scan inherits that from the arithmetic (NaN scores are never inserted); the exact
+            // scan, which computes its own norms, reads the array only for the gate.
+            float in0 = 1.f, in1 = 1.f;
+            if (inv_norm) { in0 = inv_norm[r0]; in1 = inv_norm[has1 ? r1 : r0]; }
+            const bool ok0 = in0 == in0, ok1 = has1 && in1 == in1;
+            if (EXACT) { nn0 = Acc(warp_sum_f64(double(nn0))); nn1 = Acc(warp_sum_f64(double(nn1))); }
+#pragma unroll
+            for (int qi = 0; qi < QT; ++qi) {
+                float k0, k1;
+                if (EXACT) {
+                    double d0 = warp_sum_f64(double(dot0[qi])), d1 = warp_sum_f64(double(dot1[qi]));
+                    k0 = exact_key(d0, qq_s[qi], double(nn0), mode);
+                    k1 = exact_key(d1, qq_s[qi], double(nn1), mode);
+                } else {
+                    k0 = warp_sum_f32(float(dot0[qi])) * in0;
+                    k1 = warp_sum_f32(float(dot1[qi])) * in1;
+                }
+                if (qi < nq_here) {
+                    if (ok0) lists[qi].insert(pack_entry(k0, uint32_t(r0)));
+                    if (ok1) lists[qi].insert(pack_entry(k1, uint32_t(r1)));
+                }
+            }
+        }
+        g = g2;
+        r0 = r2;
     }
 
     // ---- CTA merge: SIMT_WARPS lists of KP -> top KP, per query
