@@ -129,6 +129,29 @@ def _worker(rank, world, port, transport, out_dir):
         assert (ids_h == ids_m).all() and (sc_h == sc_m.astype(np.float64)).all(), rep
     if transport == "peer":
         assert sh2.second_rounds == 3      # every rank took the second round, every time
+        # the same hard batch from two serving threads at once (lane t each): both lanes take second rounds concurrently --
+        # per-lane send records and rings, the repair ladder's shared workspaces behind its lock -- and stay exact
+        import threading
+
+        errs2 = []
+
+        def serve_hard(t):
+            try:
+                torch.cuda.set_device(rank)
+                for rep in range(3):
+                    ids_t, sc_t, _ = sh2.retrieve_host(torch.from_numpy(q2), 10, merge=False, lane=t)
+                    assert (ids_t == ids_m).all() and (sc_t == sc_m.astype(np.float64)).all(), (t, rep)
+            except BaseException as exc:  # noqa: BLE001
+                errs2.append(exc)
+
+        threads = [threading.Thread(target=serve_hard, args=(t,)) for t in range(2)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errs2:
+            raise errs2[0]
+        assert sh2.second_rounds == 9
     assert (sh2.local.fallbacks > 0) == (rank == 1)
     open(os.path.join(out_dir, f"ok-{transport}-{rank}"), "w").write("ok")
     dist.destroy_process_group()
