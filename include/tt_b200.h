@@ -91,6 +91,21 @@ int tt_scan_max_kprime(void);
 int tt_prepare_queries(const float* q_f32, int n_q, int dim, void* q_hi_bf16, void* q_lo_bf16, void* stream);
 
 /*
+ * The same, and out_rho[q] = |q/|q| - q_hi|_2 rounded up: the part of the query a hi-only scan (q_lo not used) never
+ * sees.  By Cauchy-Schwarz it bounds that scan's score error for EVERY row, so it replaces the worst-case 2^-8 the
+ * hi-only certificate budgets for it (typically 2.5x smaller).
+ */
+int tt_prepare_queries_rho(const float* q_f32, int n_q, int dim, void* q_hi_bf16, void* q_lo_bf16, float* out_rho,
+                           void* stream);
+
+/*
+ * Hands a hi-only scan's per-query slack max(0, eps_hi_only - rho[q]) to the certificate by lowering the query's
+ * stage-1 thresholds (cand_thresh [n_q, n_lists], between stage 1 and stage 2): margin = s_k - max thresh grows by it,
+ * and every consumer keeps comparing the margin with the nominal eps.  -inf / +inf thresholds keep their meaning.
+ */
+int tt_certificate_credit(float* cand_thresh, int n_q, int n_lists, const float* rho, float eps_hi_only, void* stream);
+
+/*
  * Stage 1 -- dense scan + fused on-chip shortlist.  Replaces the vector-store query behind
  * `index.as_retriever(similarity_top_k=k).retrieve()` (rag_engine.py:639; ChromaVectorStore.query
  * -> collection.query(query_embeddings, n_results=k)).

@@ -24,6 +24,7 @@ for b, k in cases:
     r = idx.search(qq, k)
     torch.cuda.synchronize()
     ok = float((r.margin > r.eps).float().mean())
+    min_margin = float(r.margin.min())
     idx.scan_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -36,4 +37,4 @@ for b, k in cases:
     idx.scan_events = None
     tf = 2.0 * b * n * 1024 / (scan * 1e-3) / 1e12
     print(f"B={b:6d} k={k:4d} gemm={idx._use_gemm(b)} search {ms:9.2f} ms  stage1 {scan:9.2f} ms  {tf:7.1f} TFLOP/s  "
-          f"{b / ms * 1e3:9.0f} q/s  certified {ok:.4f}", flush=True)
+          f"{b / ms * 1e3:9.0f} q/s  certified {ok:.4f}  min margin {min_margin:.5f} (eps {r.eps:.5f})", flush=True)

@@ -31,6 +31,8 @@ SIGNATURES = {
     "tt_scan_num_lists": (_I, [_I]),
     "tt_scan_max_kprime": (_I, []),
     "tt_prepare_queries": (_I, [_P, _I, _I, _P, _P, _P]),
+    "tt_prepare_queries_rho": (_I, [_P, _I, _I, _P, _P, _P, _P]),
+    "tt_certificate_credit": (_I, [_P, _I, _I, _P, C.c_float, _P]),
     "tt_scan_workspace_bytes": (_Z, []),
     "tt_scan_topk_bf16": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _I, _P, _P, _P, _P, _Z, _P]),
     "tt_scan_topk_bf16_segmented": (_I, [_P, _L, _I, _L, _P, _P, _P, _I, _I, _L, _P, _I, _P, _P, _P, _P, _Z, _P]),

@@ -9,7 +9,8 @@
 namespace tt {
 
 // ---- implemented in the kernel translation units
-int launch_prepare_queries(const float* q, int n_q, int dim, void* q_hi, void* q_lo, cudaStream_t st);
+int launch_prepare_queries(const float* q, int n_q, int dim, void* q_hi, void* q_lo, float* rho, cudaStream_t st);
+int launch_certificate_credit(float* thresh, int n_q, int n_lists, const float* rho, float eps_hi_only, cudaStream_t st);
 int scan_simt_approx(const void* corpus, int64_t n_rows, int dim, int64_t stride, const float* inv_norm,
                      const void* q_hi, const void* q_lo, int n_q, int kprime, int64_t id_base, int64_t* out_ids,
                      float* out_approx, float* out_thresh, int n_lists, cudaStream_t st);
@@ -133,7 +134,7 @@ using namespace tt;
 
 extern "C" {
 
-int tt_version(void) { return 200; }
+int tt_version(void) { return 201; }
 
 const char* tt_last_error(void) { return g_err; }
 
@@ -191,7 +192,20 @@ size_t tt_scan_workspace_bytes(void) { return 256; }
 int tt_prepare_queries(const float* q_f32, int n_q, int dim, void* q_hi_bf16, void* q_lo_bf16, void* stream) {
     TT_CHECK_ARG(n_q >= 0 && dim > 0, "tt_prepare_queries: n_q=%d dim=%d", n_q, dim);
     TT_CHECK_ARG(n_q == 0 || (q_f32 && q_hi_bf16), "tt_prepare_queries: null pointer");
-    return launch_prepare_queries(q_f32, n_q, dim, q_hi_bf16, q_lo_bf16, TT_STREAM(stream));
+    return launch_prepare_queries(q_f32, n_q, dim, q_hi_bf16, q_lo_bf16, nullptr, TT_STREAM(stream));
+}
+
+int tt_prepare_queries_rho(const float* q_f32, int n_q, int dim, void* q_hi_bf16, void* q_lo_bf16, float* out_rho, void* stream) {
+    TT_CHECK_ARG(n_q >= 0 && dim > 0, "tt_prepare_queries_rho: n_q=%d dim=%d", n_q, dim);
+    TT_CHECK_ARG(n_q == 0 || (q_f32 && q_hi_bf16 && out_rho), "tt_prepare_queries_rho: null pointer");
+    return launch_prepare_queries(q_f32, n_q, dim, q_hi_bf16, q_lo_bf16, out_rho, TT_STREAM(stream));
+}
+
+int tt_certificate_credit(float* cand_thresh, int n_q, int n_lists, const float* rho, float eps_hi_only, void* stream) {
+    TT_CHECK_ARG(n_q >= 0 && n_lists >= 1 && eps_hi_only >= 0.f, "tt_certificate_credit: n_q=%d n_lists=%d eps=%f", n_q, n_lists,
+                 double(eps_hi_only));
+    TT_CHECK_ARG(n_q == 0 || (cand_thresh && rho), "tt_certificate_credit: null pointer");
+    return launch_certificate_credit(cand_thresh, n_q, n_lists, rho, eps_hi_only, TT_STREAM(stream));
 }
 
 int tt_scan_topk_bf16(const void* corpus_bf16, int64_t n_rows, int dim, int64_t row_stride_elems,

@@ -15,8 +15,10 @@ TT_DEFINE_STATUS_HOOKS(rescore)
 // one CTA per query: q_hat = q/|q| (fp32), hi = bf16(q_hat), lo = bf16(q_hat - hi)
 __global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __restrict__ q, int dim,
                                                               __nv_bfloat16* __restrict__ q_hi,
-                                                              __nv_bfloat16* __restrict__ q_lo) {
+                                                              __nv_bfloat16* __restrict__ q_lo,
+                                                              float* __restrict__ rho_out) {
     __shared__ double red[8];
+    __shared__ double red2[8];
     pdl_launch_dependents();  // the scan may become resident now: all it needs from this kernel it waits for (pdl_wait)
     const float* qb = q + size_t(blockIdx.x) * dim;
     double a = 0.0;
@@ -27,13 +29,41 @@ __global__ void __launch_bounds__(256) prepare_queries_kernel(const float* __res
     double tot = 0.0;
     for (int w = 0; w < int(blockDim.x >> 5); ++w) tot += red[w];
     const double inv = tot > 0.0 ? 1.0 / sqrt(tot) : 0.0;
+    double res = 0.0;  // |q/|q| - hi|^2: what a hi-only scan does not see of this query
     for (int d = threadIdx.x; d < dim; d += blockDim.x) {
-        float qh = float(double(qb[d]) * inv);
+        const double qd = double(qb[d]) * inv;
+        float qh = float(qd);
         __nv_bfloat16 hi = __float2bfloat16_rn(qh);
         size_t o = size_t(blockIdx.x) * dim + d;
         q_hi[o] = hi;
         if (q_lo) q_lo[o] = __float2bfloat16_rn(qh - __bfloat162float(hi));
+        const double r = qd - double(__bfloat162float(hi));
+        res += r * r;
     }
+    if (rho_out) {  // block-uniform
+        res = warp_sum_f64(res);
+        if ((threadIdx.x & 31) == 0) red2[threadIdx.x >> 5] = res;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t2 = 0.0;
+            for (int w = 0; w < int(blockDim.x >> 5); ++w) t2 += red2[w];
+            rho_out[blockIdx.x] = float(sqrt(t2) * 1.001 + 2e-6);  // rounded up: it is used as an upper bound
+        }
+    }
+}
+
+// Per-query certificate credit for hi-only scans.  The certificate's error bound has a term for the part of the query
+// the tensor cores never saw, |<q/|q| - hi, c>| / |c| <= |q/|q| - hi| =: rho (Cauchy-Schwarz), budgeted at its worst case
+// 2^-8 (EPS_HI_ONLY, every element rounded by half a bf16 ulp at the bottom of its binade).  The actual rho of a query
+// is known exactly (prepare_queries_kernel) and typically 2.5x smaller.  margin = s_k - max thresh is compared with the
+// nominal eps everywhere (host, peers), so the slack eps_hi_only - rho is handed over by LOWERING this query's thresholds
+// by it: every later consumer sees margin + credit without knowing.
+__global__ void certificate_credit_kernel(float* __restrict__ thresh, int n_q, int n_lists, const float* __restrict__ rho,
+                                          float eps_hi_only) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_q * n_lists) return;
+    const float credit = eps_hi_only - rho[i / n_lists];
+    if (credit > 0.f) thresh[i] -= credit;  // -inf (nothing dropped) and +inf (overflow: never certify) stay what they are
 }
 
 // ------------------------------------------------------------------ re-score
@@ -919,11 +949,19 @@ int launch_rescore_select(const void* corpus, int dtype, int64_t n_rows, int dim
                          out_ids, out_margin, st, xh, xh != nullptr, false, l2, q, dim, amh, nullptr, &rs);
 }
 
-int launch_prepare_queries(const float* q, int n_q, int dim, void* q_hi, void* q_lo, cudaStream_t st) {
+int launch_prepare_queries(const float* q, int n_q, int dim, void* q_hi, void* q_lo, float* rho, cudaStream_t st) {
     if (n_q == 0) return TT_OK;
     prepare_queries_kernel<<<n_q, 256, 0, st>>>(q, dim, reinterpret_cast<__nv_bfloat16*>(q_hi),
-                                                reinterpret_cast<__nv_bfloat16*>(q_lo));
+                                                reinterpret_cast<__nv_bfloat16*>(q_lo), rho);
     TT_LAUNCH_OK("prepare_queries_kernel");
+    return TT_OK;
+}
+
+int launch_certificate_credit(float* thresh, int n_q, int n_lists, const float* rho, float eps_hi_only, cudaStream_t st) {
+    const int64_t n = int64_t(n_q) * n_lists;
+    if (n == 0) return TT_OK;
+    certificate_credit_kernel<<<int((n + 255) / 256), 256, 0, st>>>(thresh, n_q, n_lists, rho, eps_hi_only);
+    TT_LAUNCH_OK("certificate_credit_kernel");
     return TT_OK;
 }
 

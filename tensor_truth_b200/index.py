@@ -47,7 +47,10 @@ GEMM_SLICE = 4096          # queries per GEMM-shaped corpus pass (candidate buff
 
 def gemm_kprime(k: int) -> int:
     """Shortlist length per query of the GEMM-shaped stage 1 (a single global list, so it is much deeper than k)."""
-    return 128 if k <= 16 else 256 if k <= 64 else 512
+    forced = os.environ.get("TT_GEMM_KPRIME")  # tuning knob
+    if forced and int(forced) >= k:
+        return int(forced)
+    return 128 if k <= 16 else 256 if k <= 128 else 512
 
 
 _NULL_CTX = contextlib.nullcontext()
@@ -280,6 +283,7 @@ class DeviceIndex:
                 "scores": torch.empty((b, k), dtype=torch.float32, device=dev),
                 "ids": torch.empty((b, k), dtype=torch.int64, device=dev),
                 "margin": torch.empty((b,), dtype=torch.float32, device=dev),
+                "rho": torch.empty((b,), dtype=torch.float32, device=dev),
             }
             self._ws[key] = w
         if w is None:
@@ -296,6 +300,7 @@ class DeviceIndex:
                 "scores": torch.empty((b, k), dtype=torch.float32, device=dev),
                 "ids": torch.empty((b, k), dtype=torch.int64, device=dev),
                 "margin": torch.empty((b,), dtype=torch.float32, device=dev),
+                "rho": torch.empty((b,), dtype=torch.float32, device=dev),
                 "scan_ws": torch.zeros(int(self.lib.tt_scan_workspace_bytes()), dtype=torch.uint8, device=dev),
             }
             self._ws[key] = w
@@ -403,7 +408,14 @@ class DeviceIndex:
         kprime = w.get("kprime", self.kprime)
         n_cand, n_lists = (kprime, 1) if gemm else (self.n_lists * kprime, self.n_lists)
         with self._on_device():
-            check(L.tt_prepare_queries(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), st))
+            credit = hi_only and not os.environ.get("TT_NO_CERT_CREDIT")
+            if credit:  # hi-only: also measure what the scan will not see of each query (certificate credit, below)
+                rho = w.get("rho")
+                if rho is None:
+                    rho = w["rho"] = torch.empty((b,), dtype=torch.float32, device=self.device)
+                check(L.tt_prepare_queries_rho(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), ptr(rho), st))
+            else:
+                check(L.tt_prepare_queries(ptr(q), b, self.dim, ptr(w["q_hi"]), ptr(w["q_lo"]), st))
             if self.scan_events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
@@ -440,6 +452,10 @@ class DeviceIndex:
             if self.scan_events is not None:
                 e1.record()
                 self.scan_events.append((e0, e1))
+            if credit:
+                # the hi-only part of eps is a worst case (2^-8); this query's actual |q/|q| - hi| is known: hand the
+                # difference to the certificate by lowering the query's thresholds (tt_certificate_credit)
+                check(L.tt_certificate_credit(ptr(w["cand_thresh"]), b, n_lists, ptr(w["rho"]), EPS_HI_ONLY, st))
             self._stage2(q, b, w, n_cand, n_lists, k, xchg, cert, am, eps)
         # cosine: proven iff margin > eps;  L2: the bound already contains eps, proven iff margin > 0
         return SearchResult(w["keys"], w["scores"], w["ids"], w["margin"], 0.0 if l2 else eps, bool(hi_only))

@@ -259,3 +259,53 @@ def test_hilo_pass_17_to_32_queries(mid, b):
     ids_o, sc_o, _ = cport.scan_topk(bits, q[:b], 10)
     assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
     assert r.eps < 1e-3 and not r.hi_only and idx.retries == idx.deep_rescans == idx.fallbacks == 0
+
+
+def test_hi_only_certificate_credit(mid, monkeypatch):
+    """A hi-only scan's error bound budgets 2^-8 for the part of the query the tensor cores never see; the actual
+    rho = |q/|q| - bf16(q/|q|)| is measured per query (tt_prepare_queries_rho) and the difference is handed to the
+    certificate by lowering the query's thresholds (tt_certificate_credit).  Checked: rho against numpy (an upper bound,
+    and a tight one), the margins grow by exactly eps_hi_only - rho, the true score error of every row stays below
+    eps_bf16 + rho (what the credited certificate assumes), and the certified answers are the exact ones."""
+    tree, bits, inv, q = mid
+    idx = _index(bits, tree)
+    L, ptr = idx.lib, _lib.ptr
+    b = 96
+    qd = torch.from_numpy(q[:b]).cuda()
+    q_hi = torch.empty((b, idx.dim), dtype=torch.bfloat16, device="cuda")
+    rho = torch.empty((b,), dtype=torch.float32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.tt_prepare_queries_rho(ptr(qd), b, idx.dim, ptr(q_hi), None, ptr(rho), st))
+    torch.cuda.synchronize()
+    qn = q[:b].astype(np.float64)
+    qn /= np.linalg.norm(qn, axis=1, keepdims=True)
+    hi = q_hi.float().cpu().numpy().astype(np.float64)
+    true_rho = np.linalg.norm(qn - hi, axis=1)
+    got = _np(rho).astype(np.float64)
+    assert (got >= true_rho).all() and (got <= true_rho * 1.002 + 3e-6).all()
+    assert got.max() < index_mod.EPS_HI_ONLY and got.mean() < 0.6 * index_mod.EPS_HI_ONLY  # the point of measuring it
+    # the hi-only approximate score of EVERY row is within eps_bf16 + rho of the exact cosine
+    cos = _exact_cosines(bits, q[:b])
+    c = oracle.bf16_bits_to_f32(bits).astype(np.float64)
+    approx_all = (hi @ c.T) / np.linalg.norm(c, axis=1)[None, :]
+    assert (np.abs(approx_all - cos).max(axis=1) <= index_mod.EPS_BF16_CORPUS + got).all()
+    # margins with and without the credit
+    r1 = idx.search(qd, 10)
+    m1 = _np(r1.margin).copy()
+    ids1 = _np(r1.ids).copy()
+    monkeypatch.setenv("TT_NO_CERT_CREDIT", "1")
+    r0 = idx.search(qd, 10)
+    m0 = _np(r0.margin).copy()
+    monkeypatch.delenv("TT_NO_CERT_CREDIT")
+    assert r1.eps == r0.eps == pytest.approx(EPS_HI)
+    np.testing.assert_allclose(m1 - m0, index_mod.EPS_HI_ONLY - got, rtol=0, atol=2e-6)
+    ids_o, sc_o, _ = cport.scan_topk(bits, q[:b], 10)
+    proven = m1 > r1.eps
+    assert proven.all() and (ids1 == ids_o).all()
+    # the unit of the credit kernel itself: -inf / +inf thresholds keep their meaning, finite ones drop by the credit
+    th = torch.tensor([[0.5, -float("inf")], [float("inf"), 0.25]], dtype=torch.float32, device="cuda")
+    rr = torch.tensor([0.001, 0.5], dtype=torch.float32, device="cuda")  # second query: rho > eps -> no credit
+    _lib.check(L.tt_certificate_credit(ptr(th), 2, 2, ptr(rr), 0.004, st))
+    torch.cuda.synchronize()
+    out = _np(th)
+    assert out[0, 0] == pytest.approx(0.497, abs=1e-6) and np.isneginf(out[0, 1]) and np.isposinf(out[1, 0]) and out[1, 1] == 0.25
