@@ -168,6 +168,8 @@ class DeviceIndex:
                 c = self.corpus[lo:lo + step].float()
                 inv_norm[lo:lo + step] = (c * c).sum(dim=1).clamp_min(1e-30).rsqrt()
         self.inv_norm = inv_norm.to(self.device, torch.float32).contiguous()
+        if self.master is not None and self.n_rows and not os.environ.get("TT_NO_STORE_EPS"):
+            self.eps = min(EPS_F32_CORPUS, EPS_BF16_CORPUS + self._shadow_gap())
         # bounds on the stored rows' norms: what lets the cosine-ordered shortlist certify chroma_l2_exp mode
         self.norm_lo, self.norm_hi = 0.0, 0.0
         if self.n_rows:
@@ -195,6 +197,24 @@ class DeviceIndex:
         self.retries = 0               # queries of a hi-only batch re-run through the hi+lo scan
         self.deep_rescans = 0          # queries re-run hi+lo with K' = 128 shortlists before the exact scan is tried
         self.scan_events = None        # bench hook: a list collects (start, end) CUDA events around every stage-1 launch
+
+    def _shadow_gap(self) -> float:
+        """fp32 store: what scanning the bf16 shadow instead of the master can cost any query, measured instead of
+        budgeted.  Stage 1 scores row r as <q, c'_r * inv_norm_r> (c' the shadow row), the exact cosine is
+        <q, c_r / |c_r|>; for a unit query the difference is at most g_r = |c'_r * inv_norm_r - c_r / |c_r||_2
+        (Cauchy-Schwarz).  ``EPS_F32_CORPUS`` budgets the worst case 2^-8 for it; the maximum of g_r over the rows that are
+        actually stored (one fp64 pass at load time, rounded up) is typically 2.5x smaller, which narrows both the
+        certificate and stage 2's 2-eps pre-filter window."""
+        g_max, step = 0.0, 1 << 17
+        for a in range(0, self.n_rows, step):
+            m = self.master[a:a + step].double()
+            nrm = m.norm(dim=1, keepdim=True)
+            unit = torch.where(nrm > 0, m / nrm.clamp_min(1e-300), torch.zeros_like(m))
+            m = self.corpus[a:a + step].double() * self.inv_norm[a:a + step].double().unsqueeze(1)
+            g = (m - unit).norm(dim=1)
+            g = torch.where(nrm.squeeze(1) > 0, g, torch.zeros_like(g))  # an all-zero row scores 0 either way
+            g_max = max(g_max, float(g.max()))
+        return g_max * 1.001 + 2e-6
 
     # ------------------------------------------------------------------ tree
     def set_tree(self, tree: Optional[NodeTree]) -> None:

@@ -205,6 +205,12 @@ class ShardedIndex:
         self.plumbing = ShardedSearch(self._local_search, self._merge, self.device, group)
         if _local is not None:
             self.plumbing.world, self.plumbing.rank = _local[0], _local[1]
+        elif self.plumbing.world > 1:
+            # every rank decides from the SAME margins whether a second round is due, so all must compare them with the same
+            # eps: a measured store eps (fp32 master, index._shadow_gap) differs per shard -- take the largest
+            e = torch.tensor([float(local_index.eps)], dtype=torch.float64, device=self.device)
+            dist.all_reduce(e, op=dist.ReduceOp.MAX, group=group)
+            local_index.eps = float(e.item())
         self._out: dict = {}
         self.group = group
         self._peers: dict = {}
@@ -604,6 +610,9 @@ class LocalShardGroup:
     def __init__(self, shards):
         registry: dict = {}
         world = len(shards)
+        eps = max(float(s.eps) for s in shards)
+        for s in shards:
+            s.eps = eps  # one eps for all ranks (see ShardedIndex.__init__)
         self.ranks = [ShardedIndex(s, _local=(world, r, registry)) for r, s in enumerate(shards)]
         self.streams = [torch.cuda.Stream(s.device) for s in shards]
 

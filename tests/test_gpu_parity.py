@@ -357,6 +357,38 @@ def test_fp32_stored_corpus_uses_master_for_rescoring():
     assert (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
 
 
+def test_fp32_store_eps_is_measured_not_budgeted(monkeypatch):
+    """fp32 master scanned through its bf16 shadow: the certificate's store term is the largest gap
+    |c'_r * inv_norm_r - c_r / |c_r|| over the stored rows, measured at load (``_shadow_gap``), not the worst case 2^-8.
+    Checked against numpy: the measured eps bounds the hi+lo stage-1 score error of EVERY row for every query, and it is
+    well below the budgeted constant; TT_NO_STORE_EPS=1 restores the constant; answers are exact either way."""
+    from tensor_truth_b200 import index as index_mod
+
+    rng = np.random.default_rng(12)
+    c = (rng.standard_normal((6000, 512)) * rng.uniform(0.5, 2.0, (6000, 1))).astype(np.float32)
+    c[17] = 0.0                                            # an all-zero row must not poison the maximum
+    q = (c[rng.integers(100, 6000, 5)] + 0.05 * rng.standard_normal((5, 512))).astype(np.float32)
+    idx = _index(c, None)
+    shadow = idx.corpus.float().cpu().numpy().astype(np.float64)
+    inv = idx.inv_norm.cpu().numpy().astype(np.float64)
+    cd = c.astype(np.float64)
+    nrm = np.linalg.norm(cd, axis=1, keepdims=True)
+    unit = np.divide(cd, nrm, out=np.zeros_like(cd), where=nrm > 0)
+    gap = np.linalg.norm(shadow * inv[:, None] - unit, axis=1)
+    gap[17] = 0.0
+    assert index_mod.EPS_BF16_CORPUS + gap.max() <= idx.eps <= index_mod.EPS_BF16_CORPUS + gap.max() * 1.002 + 3e-6
+    assert idx.eps < 0.6 * index_mod.EPS_F32_CORPUS
+    qn = q.astype(np.float64) / np.linalg.norm(q.astype(np.float64), axis=1, keepdims=True)
+    approx = qn @ (shadow * inv[:, None]).T                # what a perfect hi+lo stage 1 would report
+    assert np.abs(approx - qn @ unit.T).max() <= idx.eps - index_mod.EPS_BF16_CORPUS + 1e-9
+    ids_o, sc_o, _ = oracle.exact_topk(c, q, 10)
+    r = idx.search_certified(torch.from_numpy(q).cuda(), 10)
+    torch.cuda.synchronize()
+    assert r.eps == idx.eps and (_np(r.ids) == ids_o).all() and (_np(r.scores) == sc_o).all()
+    monkeypatch.setenv("TT_NO_STORE_EPS", "1")
+    assert _index(c, None).eps == index_mod.EPS_F32_CORPUS
+
+
 def test_merge_topk_matches_oracle(golden_dir):
     g = np.load(os.path.join(golden_dir, "mini_scan.npz"))
     bits, q = g["bits"], g["queries"]
