@@ -75,7 +75,9 @@ def test_gpu_arm_prints_one_json_line_with_the_contract_keys():
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["bytes_per_launch"] == 300000 * 1024 * 2
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 and e["d2h_bytes_per_step"] > 0 and e["callers"] == 1
+    assert e["two_callers"]["value"] > 0 and e["two_callers"]["callers"] == 2 and e["two_callers"]["equals_single_caller_answer"]
+    assert d["serial_graph"]["ms_per_step"] > 0 and 0 < r["step_share_graph"] <= 1.05
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
     # prepare, scan, re-score + select + auto-merge: three kernels per step on one GPU
@@ -88,7 +90,8 @@ def test_gpu_arm_prints_one_json_line_with_the_contract_keys():
     assert d["c3"]["roofline"]["bound"] == "hbm" and d["c3"]["scaling"] == "weak" and d["c3"]["rows_per_gpu"] == 200000
     assert d["c4"]["roofline"]["bound"] == "tensor" and d["c4"]["rows_per_gpu"] == 100000
     assert d["c5"]["k"] == 200 and d["c5"]["roofline"]["bound"] == "hbm" and d["c5"]["certificate_failures"] == 0
-    assert d["fp32_store"]["eps"] > 4e-3 and d["fp32_store"]["certificate_failures"] == 0
+    # the fp32 store's eps is measured from the stored rows (index._shadow_gap): above the bf16 store's, below the budgeted 4.2e-3
+    assert 2.5e-4 < d["fp32_store"]["eps"] <= 4.2e-3 and d["fp32_store"]["certificate_failures"] == 0
     h = d["hard_queries"]
     assert h["deep_rung"]["matches_exact_scan"] and h["exact_fallback"]["matches_exact_scan"]
     assert h["deep_rung"]["deep_rescans_kprime128"] > 0 and h["exact_fallback"]["exact_fp64_fallbacks"] > 0
