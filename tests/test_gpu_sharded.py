@@ -1,5 +1,10 @@
-"""Row-sharded path on real GPUs (needs >= 2; skipped otherwise): ShardedIndex with the fused peer exchange and
-with the NCCL all-gather transport must both reproduce the whole-corpus oracle answer bit-exactly."""
+"""Row-sharded path, one process per rank: ShardedIndex with the fused peer exchange and with the all-gather transport
+must both reproduce the whole-corpus oracle answer bit-exactly.
+
+With two GPUs (``gpurun --gpus 2``) the ranks sit on their own devices: NVLink peer mappings / NCCL.  On a ONE-GPU box
+nothing is skipped: the all-gather transport runs as two processes sharing GPU 0 over the ``gloo`` backend (which moves
+CUDA tensors), and the peer transport -- whose symmetric-memory rendezvous wants one device per rank -- runs the same
+scenario through ``LocalShardGroup`` (two simulated ranks in one process, plain device buffers as the peer mappings)."""
 
 import os
 import socket
@@ -21,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, transport, out_dir):
+def _worker(rank, world, port, transport, out_dir, one_gpu=False):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
 
@@ -32,9 +37,15 @@ def _worker(rank, world, port, transport, out_dir):
     from tensor_truth_b200.synth import make_small
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), TT_EXCHANGE=transport)
-    torch.cuda.set_device(rank)
-    dev = torch.device(f"cuda:{rank}")
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    if one_gpu:  # both ranks on GPU 0, collectives through gloo (the all-gather transport only)
+        assert transport == "nccl"
+        torch.cuda.set_device(0)
+        dev = torch.device("cuda:0")
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        torch.cuda.set_device(rank)
+        dev = torch.device(f"cuda:{rank}")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     tree, bits, inv, q = make_small(50_000, 300, dim=1024, levels=3, seed=31)
     lo, hi = shard_bounds(bits.shape[0], world, rank)
     idx = DeviceIndex(bits[lo:hi], tree, id_base=lo, device=dev)
@@ -157,11 +168,52 @@ def _worker(rank, world, port, transport, out_dir):
     dist.destroy_process_group()
 
 
+def _peer_scenario_on_one_gpu():
+    """The peer-transport scenario of ``_worker`` with both ranks simulated in this process (LocalShardGroup)."""
+    import oracle
+    from oracle import cport
+    from tensor_truth_b200 import _lib
+    from tensor_truth_b200.index import DeviceIndex
+    from tensor_truth_b200.sharded import LocalShardGroup, shard_bounds
+    from tensor_truth_b200.synth import make_small
+
+    dev = torch.device("cuda:0")
+    _lib.set_wait_timeout_ms(0, 3000)
+    try:
+        tree, bits, inv, q = make_small(50_000, 300, dim=1024, levels=3, seed=31)
+        shards = []
+        for r in range(2):
+            lo, hi = shard_bounds(bits.shape[0], 2, r)
+            shards.append(DeviceIndex(bits[lo:hi], tree, id_base=lo, device=dev))
+        grp = LocalShardGroup(shards)
+        assert all(rk.transport == "peer" for rk in grp.ranks)
+        ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
+        qd = torch.from_numpy(q).to(dev)
+        for rep in range(4):
+            for b in (1, 12):
+                for scores, ids in grp.search(qd[:b], 10):
+                    torch.cuda.synchronize()
+                    assert (ids.cpu().numpy() == ids_o[:b]).all() and (scores.cpu().numpy() == sc_o[:b]).all(), (rep, b)
+        assert shards[0]._use_gemm(300)  # a wide batch: every rank's stage 1 is the GEMM-shaped scan, same exchange
+        for scores, ids in grp.search(qd, 10):
+            torch.cuda.synchronize()
+            assert (ids.cpu().numpy() == ids_o).all() and (scores.cpu().numpy() == sc_o).all()
+        for ids_h, sc_h, lens in grp.retrieve_host(torch.from_numpy(q[:3]), 10):
+            for b in range(3):
+                exp = oracle.retrieve(bits, q[b], 10, tree)
+                assert [(int(o), float(s)) for o, s in zip(ids_h[b, :lens[b]], sc_h[b, :lens[b]])] == exp
+        _lib.check_status(0)
+    finally:
+        _lib.set_wait_timeout_ms(0, 0)
+
+
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
-def test_sharded_index_two_gpus(tmp_path, transport):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+def test_sharded_index_two_ranks(tmp_path, transport):
     import torch.multiprocessing as mp
 
-    mp.spawn(_worker, args=(2, _free_port(), transport, str(tmp_path)), nprocs=2, join=True)
+    one_gpu = torch.cuda.device_count() < 2
+    if one_gpu and transport == "peer":
+        _peer_scenario_on_one_gpu()  # (the second round after a repair: tests/test_gpu_exchange_one_device.py)
+        return
+    mp.spawn(_worker, args=(2, _free_port(), transport, str(tmp_path), one_gpu), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"ok-{transport}-{r}") for r in range(2))
