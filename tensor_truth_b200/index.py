@@ -18,7 +18,6 @@ from __future__ import annotations
 import contextlib
 import ctypes as C
 import os
-import queue
 import threading
 from dataclasses import dataclass
 from typing import Optional
@@ -132,6 +131,42 @@ def _as_device_corpus(corpus, device):
     return t.contiguous()
 
 
+class _HostLane:
+    """``DeviceIndex._host_lane()``: a semaphore, one lock per lane and a plain context class (no generator, no queue):
+    this sits on the latency path of every ``retrieve()``."""
+
+    __slots__ = ("idx", "lane", "ctx")
+
+    def __init__(self, idx):
+        self.idx, self.lane, self.ctx = idx, -1, None
+
+    def __enter__(self) -> int:
+        idx = self.idx
+        idx._lane_sem.acquire()              # at most HOST_LANES callers get past this point ...
+        for lane, lock in enumerate(idx._lane_locks):
+            if lock.acquire(False):          # ... so one of the lanes is free
+                self.lane = lane
+                break
+        if self.lane > 0:
+            st = idx._lane_streams.get(self.lane)
+            if st is None:
+                st = idx._lane_streams[self.lane] = torch.cuda.Stream(idx.device)
+                st.wait_stream(torch.cuda.current_stream(idx.device))
+            self.ctx = torch.cuda.stream(st)
+            self.ctx.__enter__()
+        return self.lane
+
+    def __exit__(self, *exc) -> bool:
+        idx = self.idx
+        try:
+            if self.ctx is not None:
+                self.ctx.__exit__(*exc)
+        finally:
+            idx._lane_locks[self.lane].release()
+            idx._lane_sem.release()
+        return False
+
+
 class DeviceIndex:
     """One shard of one index on one GPU."""
 
@@ -186,9 +221,8 @@ class DeviceIndex:
         # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420) and the web app serves requests
         # concurrently: ``retrieve_host`` callers are pipelined over HOST_LANES lanes (own stream, buffers, result record
         # and captured graph each), so one caller's tail + host work overlaps the next caller's corpus scan
-        self._lanes: "queue.LifoQueue[int]" = queue.LifoQueue()
-        for lane in reversed(range(HOST_LANES)):
-            self._lanes.put(lane)
+        self._lane_sem = threading.Semaphore(HOST_LANES)             # callers in flight
+        self._lane_locks = [threading.Lock() for _ in range(HOST_LANES)]
         self._lane_streams: dict = {}
         self._repair_lock = threading.Lock()  # the repair ladder's workspaces are shared; repairs are rare
         self.set_tree(tree)
@@ -220,7 +254,9 @@ class DeviceIndex:
     def set_tree(self, tree: Optional[NodeTree]) -> None:
         """Install (or drop) the node tree.  Captured pipelines bake the old tree arrays' addresses in, so every cached
         graph / step graph is dropped with them."""
-        held = [self._lanes.get() for _ in range(HOST_LANES)]  # no retrieve_host call in flight while the tree changes
+        sem = getattr(self, "_lane_sem", None)
+        for _ in range(HOST_LANES if sem is not None else 0):  # no retrieve_host call in flight while the tree changes
+            sem.acquire()
         try:
             ws = getattr(self, "_ws", None)
             if ws:
@@ -228,26 +264,13 @@ class DeviceIndex:
                     del ws[key]
             self._set_tree_locked(tree)
         finally:
-            for lane in reversed(held):
-                self._lanes.put(lane)
+            for _ in range(HOST_LANES if sem is not None else 0):
+                sem.release()
 
-    @contextlib.contextmanager
     def _host_lane(self):
-        """Take a free host lane (blocks while all are busy).  Lane 0 runs on the caller's current stream, the others on
-        a stream of their own, which is current inside the context."""
-        lane = self._lanes.get()
-        try:
-            if lane == 0:
-                yield 0
-            else:
-                st = self._lane_streams.get(lane)
-                if st is None:
-                    st = self._lane_streams[lane] = torch.cuda.Stream(self.device)
-                    st.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(st):
-                    yield lane
-        finally:
-            self._lanes.put(lane)
+        """Context: take a free host lane (blocks while all are busy).  Lane 0 runs on the caller's current stream, the
+        others on a stream of their own, which is current inside the context.  ``with ... as lane``."""
+        return _HostLane(self)
 
     def _set_tree_locked(self, tree: Optional[NodeTree]) -> None:
         self.tree = tree
