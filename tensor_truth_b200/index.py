@@ -294,7 +294,7 @@ class DeviceIndex:
         """17-32 hi+lo queries: the 64-column pass of the GEMM-shaped scan with every query on two MMA columns (hi, lo).
         The resident-query kernel needs 128 KB of shared memory for such a block and starves its TMA ring (3.56 ms per
         pass at 10M rows); the streaming pipeline keeps its bytes in flight."""
-        return (HILO_GEMM_FROM <= b <= 32 and self.variant in (SCAN_AUTO, _lib.SCAN_TCGEN05) and self.dim % 64 == 0
+        return (int(os.environ.get("TT_HILO_GEMM_FROM", HILO_GEMM_FROM)) <= b <= 32 and self.variant in (SCAN_AUTO, _lib.SCAN_TCGEN05) and self.dim % 64 == 0
                 and self.n_rows > 0 and not os.environ.get("TT_NO_GEMM") and not os.environ.get("TT_NO_GEMM_HILO"))
 
     def _buffers(self, b: int, k: int, slot: int = 0, hi_only: Optional[bool] = None, kprime: Optional[int] = None):
