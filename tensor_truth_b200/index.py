@@ -39,6 +39,7 @@ MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist work
 HILO_GEMM_FROM = 17        # hi+lo batches of 17-32 queries take the 64-column GEMM-shaped pass with (hi, lo) column pairs
 GEMM_ABOVE = 33            # hi-only batches at least this large take the GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass
                            # per 4096 queries, one list per query (64 queries: 3.04 ms at 10M rows vs 3.35 ms for the pair kernel)
+COALESCE_MAX = 8            # queries per coalesced batch of concurrent retrieve_host callers (a scan pass costs the same up to 8)
 HOST_LANES = 2             # concurrent retrieve_host callers in flight per index (own stream, buffers, record and graph each)
 GRAPH_AFTER = 3            # retrieve_host: eager calls of a (batch, k) shape before its pipeline is captured in a CUDA graph
 GEMM_SLICE = 4096          # queries per GEMM-shaped corpus pass (candidate buffers: 16 K' * 8 B per query)
@@ -131,22 +132,37 @@ def _as_device_corpus(corpus, device):
     return t.contiguous()
 
 
+class _HostRequest:
+    """One ``retrieve_host`` call waiting for a lane (``DeviceIndex.retrieve_host``: coalescing of concurrent callers)."""
+
+    __slots__ = ("q", "n", "key", "taken", "done", "result", "error")
+
+    def __init__(self, q, n, key):
+        self.q, self.n, self.key = q, n, key
+        self.taken, self.done, self.result, self.error = False, threading.Event(), None, None
+
+
 class _HostLane:
-    """``DeviceIndex._host_lane()``: a semaphore, one lock per lane and a plain context class (no generator, no queue):
-    this sits on the latency path of every ``retrieve()``."""
+    """``DeviceIndex._host_lane()``: waits for a free host lane -- or, for a coalescable request, until some other caller
+    has taken the request along in its batch, whichever comes first (then no lane is taken and ``-1`` is returned: a
+    caller whose answer is being computed must not queue for a lane it does not need, or callers that re-enter quickly
+    would starve it).  One condition variable guards the free-lane list and the pending requests."""
 
-    __slots__ = ("idx", "lane", "ctx")
+    __slots__ = ("idx", "req", "lane", "ctx")
 
-    def __init__(self, idx):
-        self.idx, self.lane, self.ctx = idx, -1, None
+    def __init__(self, idx, req=None):
+        self.idx, self.req, self.lane, self.ctx = idx, req, -1, None
 
     def __enter__(self) -> int:
-        idx = self.idx
-        idx._lane_sem.acquire()              # at most HOST_LANES callers get past this point ...
-        for lane, lock in enumerate(idx._lane_locks):
-            if lock.acquire(False):          # ... so one of the lanes is free
-                self.lane = lane
-                break
+        idx, req = self.idx, self.req
+        with idx._lane_cv:
+            while True:
+                if req is not None and req.taken:
+                    return -1
+                if idx._free_lanes:
+                    self.lane = idx._free_lanes.pop(0)
+                    break
+                idx._lane_cv.wait()
         if self.lane > 0:
             st = idx._lane_streams.get(self.lane)
             if st is None:
@@ -157,18 +173,24 @@ class _HostLane:
         return self.lane
 
     def __exit__(self, *exc) -> bool:
+        if self.lane < 0:
+            return False
         idx = self.idx
         try:
             if self.ctx is not None:
                 self.ctx.__exit__(*exc)
         finally:
-            idx._lane_locks[self.lane].release()
-            idx._lane_sem.release()
+            with idx._lane_cv:
+                idx._free_lanes.append(self.lane)
+                idx._free_lanes.sort()       # lane 0 (the caller's own stream) first
+                idx._lane_cv.notify_all()
         return False
 
 
 class DeviceIndex:
     """One shard of one index on one GPU."""
+
+    COALESCE = True  # concurrent retrieve_host callers may be served as one batch (SegmentedIndex: one result per segment -- off)
 
     def __init__(self, corpus, tree: Optional[NodeTree] = None, inv_norm: Optional[torch.Tensor] = None,
                  id_base: int = 0, device: Optional[torch.device] = None, kprime: int = 32,
@@ -221,8 +243,11 @@ class DeviceIndex:
         # MultiIndexRetriever calls retrievers from a thread pool (rag_engine.py:420) and the web app serves requests
         # concurrently: ``retrieve_host`` callers are pipelined over HOST_LANES lanes (own stream, buffers, result record
         # and captured graph each), so one caller's tail + host work overlaps the next caller's corpus scan
-        self._lane_sem = threading.Semaphore(HOST_LANES)             # callers in flight
-        self._lane_locks = [threading.Lock() for _ in range(HOST_LANES)]
+        self._pending: list = []                                     # retrieve_host requests waiting for a lane
+        self._lane_cv = threading.Condition()                        # guards _free_lanes, _pending and the requests' flags
+        self._free_lanes = list(range(HOST_LANES))
+        self._coalesce = not os.environ.get("TT_NO_COALESCE")
+        self.coalesced = 0                                           # queries that rode along in another caller's batch
         self._lane_streams: dict = {}
         self._repair_lock = threading.Lock()  # the repair ladder's workspaces are shared; repairs are rare
         self.set_tree(tree)
@@ -254,9 +279,7 @@ class DeviceIndex:
     def set_tree(self, tree: Optional[NodeTree]) -> None:
         """Install (or drop) the node tree.  Captured pipelines bake the old tree arrays' addresses in, so every cached
         graph / step graph is dropped with them."""
-        sem = getattr(self, "_lane_sem", None)
-        for _ in range(HOST_LANES if sem is not None else 0):  # no retrieve_host call in flight while the tree changes
-            sem.acquire()
+        held = self._hold_all_lanes() if hasattr(self, "_lane_cv") else None  # no retrieve_host call in flight meanwhile
         try:
             ws = getattr(self, "_ws", None)
             if ws:
@@ -264,13 +287,27 @@ class DeviceIndex:
                     del ws[key]
             self._set_tree_locked(tree)
         finally:
-            for _ in range(HOST_LANES if sem is not None else 0):
-                sem.release()
+            if held is not None:
+                self._release_lanes(held)
 
-    def _host_lane(self):
+    def _hold_all_lanes(self):
+        """Wait until no ``retrieve_host`` call is in flight and keep every lane (``set_tree``; tests)."""
+        with self._lane_cv:
+            while len(self._free_lanes) < HOST_LANES:
+                self._lane_cv.wait()
+            held, self._free_lanes = self._free_lanes, []
+        return held
+
+    def _release_lanes(self, held) -> None:
+        with self._lane_cv:
+            self._free_lanes = sorted(self._free_lanes + list(held))
+            self._lane_cv.notify_all()
+
+    def _host_lane(self, req=None):
         """Context: take a free host lane (blocks while all are busy).  Lane 0 runs on the caller's current stream, the
-        others on a stream of their own, which is current inside the context.  ``with ... as lane``."""
-        return _HostLane(self)
+        others on a stream of their own, which is current inside the context.  ``with ... as lane``; with a coalescable
+        request ``req`` the wait also ends -- with lane -1 -- when another caller has taken the request along."""
+        return _HostLane(self, req)
 
     def _set_tree_locked(self, tree: Optional[NodeTree]) -> None:
         self.tree = tree
@@ -707,51 +744,111 @@ class DeviceIndex:
         The H2D copy of the queries and the single D2H read of the result record are part of the call;
         the certificate is checked on the host from the margins in that record.  ``row_filter``: a metadata filter
         resolved by ``row_filter()`` (such calls take the eager pipeline: the captured graph reads the ungated norms)."""
-        merged = bool(merge and self.tree is not None)
         if int(q_host.shape[0]) > MAX_HOST_BATCH:  # bound the workspaces: large batches go through in slices
             parts = [self.retrieve_host(q_host[i:i + MAX_HOST_BATCH], k, ratio_thresh, merge, row_filter)
                      for i in range(0, int(q_host.shape[0]), MAX_HOST_BATCH)]
             return tuple(np.concatenate([p[j] for p in parts], axis=0) for j in range(3))
-        with self._host_lane() as lane:
-            b = int(q_host.shape[0])
-            g = (self._pipeline_graph(b, k, ratio_thresh, merged, lane)
-                 if (row_filter is None and q_host.dim() == 2 and q_host.shape[1] == self.dim) else None)
-            if g is not None:
-                if q_host.dtype == torch.float32 and q_host.device.type == "cpu":
-                    g["q_pin_np"][...] = q_host.numpy()  # the common case: a plain memory copy into the pinned staging buffer
-                else:
-                    g["q_pin"].copy_(q_host)
-                q, r, rec = g["q_dev"], g["result"], g["rec"]
-                d, h = rec["d"], rec["hn"]
-                with self._on_device():
-                    g["graph"].replay()
+        n = int(q_host.shape[0])
+        if not (self.COALESCE and self._coalesce and 0 < n <= COALESCE_MAX and q_host.dim() == 2 and q_host.shape[1] == self.dim
+                and q_host.dtype == torch.float32 and q_host.device.type == "cpu"):
+            with self._host_lane() as lane:
+                return self._retrieve_host_lane(lane, q_host, k, ratio_thresh, merge, row_filter)
+        # Callers that arrive while every lane is busy are COALESCED: whoever gets the next free lane takes all compatible
+        # waiting requests along as one batch (the scan costs the same for 1 ... 8 queries), the others find their answer
+        # ready.  One caller alone leads a batch of itself; two callers share the two lanes; from three on, batches form.
+        req = _HostRequest(q_host, n, (int(k), float(ratio_thresh), bool(merge), id(row_filter) if row_filter is not None else 0))
+        with self._lane_cv:
+            self._pending.append(req)
+        batch = None
+        with self._host_lane(req) as lane:
+            if lane >= 0:
+                with self._lane_cv:
+                    if not req.taken:  # (it may have been taken between getting the lane and getting here)
+                        batch, total, rest = [req], n, []
+                        req.taken = True
+                        for r in self._pending:
+                            if r is req:
+                                continue
+                            if r.key == req.key and total + r.n <= COALESCE_MAX:
+                                r.taken = True
+                                batch.append(r)
+                                total += r.n
+                            else:
+                                rest.append(r)
+                        self._pending = rest
+                        if len(batch) > 1:
+                            self._lane_cv.notify_all()  # the callers taken along stop queueing for a lane
+            if batch is not None:
+                try:
+                    if len(batch) == 1:
+                        req.result = self._retrieve_host_lane(lane, q_host, k, ratio_thresh, merge, row_filter)
+                    else:
+                        # padded to a power of two (repeating the last query): four batch shapes -- and captured graphs --
+                        # per lane instead of eight, at no cost (the pass is as long for 8 queries as for 5)
+                        parts = [r.q for r in batch]
+                        pad = (1 << (total - 1).bit_length()) - total
+                        if pad:
+                            parts.append(parts[-1][-1:].expand(pad, -1))
+                        ids, scores, lens = self._retrieve_host_lane(lane, torch.cat(parts), k, ratio_thresh, merge, row_filter)
+                        a = 0
+                        for r in batch:
+                            r.result = (ids[a:a + r.n], scores[a:a + r.n], lens[a:a + r.n])
+                            a += r.n
+                        self.coalesced += len(batch) - 1
+                except BaseException as exc:  # noqa: BLE001 -- every caller of the batch sees what its leader saw
+                    for r in batch:
+                        r.error = exc
+                finally:
+                    for r in batch[1:]:
+                        r.done.set()
+        if batch is None:
+            req.done.wait()
+        if req.error is not None:
+            raise req.error
+        return req.result
+
+    def _retrieve_host_lane(self, lane: int, q_host: torch.Tensor, k: int, ratio_thresh: float, merge: bool, row_filter):
+        """``retrieve_host`` on a host lane the caller holds."""
+        merged = bool(merge and self.tree is not None)
+        b = int(q_host.shape[0])
+        g = (self._pipeline_graph(b, k, ratio_thresh, merged, lane)
+             if (row_filter is None and q_host.dim() == 2 and q_host.shape[1] == self.dim) else None)
+        if g is not None:
+            if q_host.dtype == torch.float32 and q_host.device.type == "cpu":
+                g["q_pin_np"][...] = q_host.numpy()  # the common case: a plain memory copy into the pinned staging buffer
             else:
-                q = q_host.to(self.device, torch.float32, non_blocking=True)
-                q = self._check_queries(q)
-                vb = self._result_rows(b)
-                rec = self._record(vb, k, merged, lane=lane)
-                d, h = rec["d"], rec["hn"]
-                w = dict(self._buffers(vb, k, slot=self._host_slot(lane)))
-                w["margin"] = d["margin"]
-                if not merged:
-                    w["ids"], w["scores"] = d["ids"], d["scores"]
-                am = self._am_args(ratio_thresh, MergeResult(d["ids"], d["scores"], d["lens"])) if merged else None
-                r = self.search(q, k, out=w, am=am, row_filter=row_filter)
+                g["q_pin"].copy_(q_host)
+            q, r, rec = g["q_dev"], g["result"], g["rec"]
+            d, h = rec["d"], rec["hn"]
+            with self._on_device():
+                g["graph"].replay()
+        else:
+            q = q_host.to(self.device, torch.float32, non_blocking=True)
+            q = self._check_queries(q)
+            vb = self._result_rows(b)
+            rec = self._record(vb, k, merged, lane=lane)
+            d, h = rec["d"], rec["hn"]
+            w = dict(self._buffers(vb, k, slot=self._host_slot(lane)))
+            w["margin"] = d["margin"]
+            if not merged:
+                w["ids"], w["scores"] = d["ids"], d["scores"]
+            am = self._am_args(ratio_thresh, MergeResult(d["ids"], d["scores"], d["lens"])) if merged else None
+            r = self.search(q, k, out=w, am=am, row_filter=row_filter)
+            rec["host"].copy_(rec["dev"], non_blocking=True)
+        check(self.lib.tt_stream_synchronize(self._stream()))  # one GIL-releasing call (an event record + wait through
+        _lib.check_status(self._dev_index)                     # PyTorch costs ~15 us of Python per query)
+        bad = np.nonzero(~(h["margin"] > r.eps))[0]
+        if bad.size:  # not proven exact: re-run those queries (tighter scan, then the exact fp64 scan)
+            with self._repair_lock:
+                self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only, row_filter=row_filter)
+                if merged:
+                    self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
                 rec["host"].copy_(rec["dev"], non_blocking=True)
-            check(self.lib.tt_stream_synchronize(self._stream()))  # one GIL-releasing call (an event record + wait through
-            _lib.check_status(self._dev_index)                     # PyTorch costs ~15 us of Python per query)
-            bad = np.nonzero(~(h["margin"] > r.eps))[0]
-            if bad.size:  # not proven exact: re-run those queries (tighter scan, then the exact fp64 scan)
-                with self._repair_lock:
-                    self._repair(q, k, r, torch.from_numpy(bad).to(self.device), hi_lo_first=r.hi_only, row_filter=row_filter)
-                    if merged:
-                        self.automerge(r.ids, r.scores, ratio_thresh, out=MergeResult(d["ids"], d["scores"], d["lens"]))
-                    rec["host"].copy_(rec["dev"], non_blocking=True)
-                    check(self.lib.tt_stream_synchronize(self._stream()))
-                _lib.check_status(self._dev_index)
-            ids, scores = h["ids"].copy(), h["scores"].astype(np.float64)
-            lens = h["lens"].copy() if merged else (ids >= 0).sum(axis=1).astype(np.int32)
-            return ids, scores, lens
+                check(self.lib.tt_stream_synchronize(self._stream()))
+            _lib.check_status(self._dev_index)
+        ids, scores = h["ids"].copy(), h["scores"].astype(np.float64)
+        lens = h["lens"].copy() if merged else (ids >= 0).sum(axis=1).astype(np.int32)
+        return ids, scores, lens
 
     def close(self) -> None:
         """Drop device memory (``RAGService.clear`` -> ``MultiIndexRetriever.clear_cache`` path, rag_service.py:720)."""

@@ -26,6 +26,8 @@ from .tree import NodeTree, concat_trees, locate
 class SegmentedIndex(DeviceIndex):
     """``DeviceIndex`` over the concatenation of several indexes; every search answers per segment."""
 
+    COALESCE = False  # results come back as one list per (segment, query): concurrent callers are pipelined, not batched
+
     def __init__(self, corpora: Sequence, trees: Optional[Sequence[Optional[NodeTree]]] = None,
                  device: Optional[torch.device] = None, kprime: int = 32, score_mode: int = SCORE_COSINE):
         if not 1 <= len(corpora) <= _lib.MAX_SEGMENTS:

@@ -645,7 +645,7 @@ def test_near_duplicate_corpus_walks_the_repair_ladder():
 
 def test_concurrent_callers_are_pipelined_over_host_lanes_and_stay_exact():
     """Four threads call retrieve_host of ONE index at once: at most HOST_LANES calls are in flight (own stream, buffers,
-    record and graph per lane), the others wait for a lane; easy queries (proven by the certificate) and hard ones (between
+    record and graph per lane), the others wait for a lane or ride along in a leader's batch; easy queries (proven by the certificate) and hard ones (between
     near-duplicate rows: repaired under the shared repair lock) interleave, past the point where each lane captures its
     graph.  Every answer must be the oracle's."""
     from concurrent.futures import ThreadPoolExecutor
@@ -664,20 +664,22 @@ def test_concurrent_callers_are_pipelined_over_host_lanes_and_stay_exact():
     in_flight, peak, guard = [0], [0], __import__("threading").Lock()
     orig = idx._host_lane
 
-    def counted():
-        ctx = orig()
+    def counted(req=None):
+        ctx = orig(req)
 
         class Wrap:
             def __enter__(self_w):
-                lane = ctx.__enter__()
-                with guard:
-                    in_flight[0] += 1
-                    peak[0] = max(peak[0], in_flight[0])
-                return lane
+                self_w.lane = ctx.__enter__()
+                if self_w.lane >= 0:  # (-1: the request rode along in another caller's batch, no lane taken)
+                    with guard:
+                        in_flight[0] += 1
+                        peak[0] = max(peak[0], in_flight[0])
+                return self_w.lane
 
             def __exit__(self_w, *a):
-                with guard:
-                    in_flight[0] -= 1
+                if self_w.lane >= 0:
+                    with guard:
+                        in_flight[0] -= 1
                 return ctx.__exit__(*a)
 
         return Wrap()
@@ -694,7 +696,54 @@ def test_concurrent_callers_are_pipelined_over_host_lanes_and_stay_exact():
     for qi, ids, scores in got:
         assert (ids == ids_o[qi]).all() and (scores == sc_o[qi].astype(np.float64)).all(), qi
     assert idx.fallbacks > 0 and 1 <= peak[0] <= HOST_LANES
-    assert sum(1 for key in idx._ws if isinstance(key, tuple) and key[0] == "graph" and idx._ws[key]["graph"] is not None) >= 1
+
+
+def test_callers_waiting_for_a_lane_are_served_as_one_batch(c1):
+    """Both host lanes busy (held by the test), five callers arrive and queue up; when a lane frees, the first caller to
+    get it takes the other four along as ONE batch of five (a scan pass costs the same for 1 ... 8 queries) -- every
+    caller still gets exactly its own oracle answer.  A failing batch fails for every caller in it."""
+    import threading
+    import time
+
+    tree, bits, inv, q = c1
+    idx = _index(bits, tree)
+    want = {i: oracle.retrieve(bits, q[i], 10, tree) for i in range(5)}
+    held = idx._hold_all_lanes()
+    got, errs = {}, []
+
+    def call(i, k=10):
+        try:
+            ids, scores, lens = idx.retrieve_host(torch.from_numpy(q[i:i + 1]), k)
+            got[i] = [(int(o), float(s)) for o, s in zip(ids[0, :lens[0]], scores[0, :lens[0]])]
+        except Exception as exc:  # noqa: BLE001
+            errs.append((i, exc))
+
+    threads = [threading.Thread(target=call, args=(i,)) for i in range(5)]
+    for th in threads:
+        th.start()
+    t0 = time.time()
+    while len(idx._pending) < 5 and time.time() - t0 < 20:
+        time.sleep(0.005)
+    assert len(idx._pending) == 5
+    idx._release_lanes(held)
+    for th in threads:
+        th.join()
+    assert not errs and got == want and idx.coalesced == 4 and not idx._pending
+    # one caller alone: a batch of itself, nothing coalesced
+    call(0)
+    assert got[0] == want[0] and idx.coalesced == 4
+    # an error inside a coalesced batch reaches every caller of that batch
+    held = idx._hold_all_lanes()
+    threads = [threading.Thread(target=call, args=(i, 0)) for i in range(3)]  # k = 0: refused by the library
+    for th in threads:
+        th.start()
+    t0 = time.time()
+    while len(idx._pending) < 3 and time.time() - t0 < 20:
+        time.sleep(0.005)
+    idx._release_lanes(held)
+    for th in threads:
+        th.join()
+    assert sorted(i for i, _ in errs) == [0, 1, 2] and len({id(e) for _, e in errs}) == 1
 
 
 def test_empty_index_and_empty_batch():
