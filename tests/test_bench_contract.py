@@ -77,6 +77,7 @@ def test_gpu_arm_prints_one_json_line_with_the_contract_keys():
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 4096 and e["d2h_bytes_per_step"] > 0 and e["callers"] == 1
     assert e["two_callers"]["value"] > 0 and e["two_callers"]["callers"] == 2 and e["two_callers"]["equals_single_caller_answer"]
+    assert e["eight_callers"]["value"] > 0 and e["eight_callers"]["callers"] == 8 and e["eight_callers"]["equals_single_caller_answer"]
     assert d["serial_graph"]["ms_per_step"] > 0 and 0 < r["step_share_graph"] <= 1.05
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
