@@ -1,5 +1,6 @@
 """Concurrent retrieve_host callers on one index: throughput, coalesced batch sizes, per-batch latency.  GPU box."""
 import collections
+import faulthandler
 import os
 import sys
 import threading
@@ -11,6 +12,7 @@ import torch
 from tensor_truth_b200.index import DeviceIndex
 from tensor_truth_b200.synth import SynthCorpus
 
+faulthandler.dump_traceback_later(int(os.environ.get("WATCHDOG_S", 150)), exit=True)  # a hang prints every thread's stack
 n = int(os.environ.get("ROWS", 10_000_000))
 callers = int(os.environ.get("CALLERS", 8))
 per = int(os.environ.get("PER", 60))
@@ -18,6 +20,10 @@ sc = SynthCorpus(n, 1024, 3, 1234, device="cuda")
 corpus, inv = sc.rows(0, n)
 q = sc.finish_queries(sc.queries(64, lookup=lambda t: corpus[t])).cpu()
 idx = DeviceIndex(corpus, sc.tree, inv_norm=inv)
+if os.environ.get("WAIT_TIMEOUT_MS"):  # bounded device-side waits: a stuck ring / exchange wait surfaces as a TTError
+    from tensor_truth_b200 import _lib
+
+    _lib.set_wait_timeout_ms(0, int(os.environ["WAIT_TIMEOUT_MS"]))
 sizes, lat = collections.Counter(), collections.defaultdict(list)
 inner = idx._retrieve_host_lane
 

@@ -39,7 +39,11 @@ MAX_HOST_BATCH = 1024      # retrieve_host slices larger batches (shortlist work
 HILO_GEMM_FROM = 17        # hi+lo batches of 17-32 queries take the 64-column GEMM-shaped pass with (hi, lo) column pairs
 GEMM_ABOVE = 33            # hi-only batches at least this large take the GEMM-shaped stage 1 (scan_gemm.cu): one corpus pass
                            # per 4096 queries, one list per query (64 queries: 3.04 ms at 10M rows vs 3.35 ms for the pair kernel)
-COALESCE_MAX = 8            # queries per coalesced batch of concurrent retrieve_host callers (a scan pass costs the same up to 8)
+# Queries per coalesced batch of concurrent retrieve_host callers: a scan pass costs the same up to 8.  Larger caps were
+# tried with 16 / 32 caller threads (scripts/serving_probe.py): 16 gains nothing at 16 callers and 10 % at 32; with 32 --
+# batches of 17-32 queries, i.e. the hi+lo GEMM pass on both lanes next to every other shape -- two of three runs at 10M
+# rows ended in a device-side hang that fixed 32-query batches on two lanes do not reproduce (open issue).
+COALESCE_MAX = 8
 HOST_LANES = 2             # concurrent retrieve_host callers in flight per index (own stream, buffers, record and graph each)
 GRAPH_AFTER = 3            # retrieve_host: eager calls of a (batch, k) shape before its pipeline is captured in a CUDA graph
 GEMM_SLICE = 4096          # queries per GEMM-shaped corpus pass (candidate buffers: 16 K' * 8 B per query)
