@@ -2,9 +2,9 @@
 must both reproduce the whole-corpus oracle answer bit-exactly.
 
 With two GPUs (``gpurun --gpus 2``) the ranks sit on their own devices: NVLink peer mappings / NCCL.  On a ONE-GPU box
-nothing is skipped: the all-gather transport runs as two processes sharing GPU 0 over the ``gloo`` backend (which moves
-CUDA tensors), and the peer transport -- whose symmetric-memory rendezvous wants one device per rank -- runs the same
-scenario through ``LocalShardGroup`` (two simulated ranks in one process, plain device buffers as the peer mappings)."""
+the all-gather transport still runs, as two processes sharing GPU 0 over the ``gloo`` backend (which moves CUDA tensors);
+the peer transport's symmetric-memory rendezvous wants one device per rank, so that case is skipped here and covered by
+tests/test_gpu_exchange_one_device.py (the ABI protocol and ``ShardedIndex`` itself through ``LocalShardGroup``)."""
 
 import os
 import socket
@@ -168,52 +168,13 @@ def _worker(rank, world, port, transport, out_dir, one_gpu=False):
     dist.destroy_process_group()
 
 
-def _peer_scenario_on_one_gpu():
-    """The peer-transport scenario of ``_worker`` with both ranks simulated in this process (LocalShardGroup)."""
-    import oracle
-    from oracle import cport
-    from tensor_truth_b200 import _lib
-    from tensor_truth_b200.index import DeviceIndex
-    from tensor_truth_b200.sharded import LocalShardGroup, shard_bounds
-    from tensor_truth_b200.synth import make_small
-
-    dev = torch.device("cuda:0")
-    _lib.set_wait_timeout_ms(0, 3000)
-    try:
-        tree, bits, inv, q = make_small(50_000, 300, dim=1024, levels=3, seed=31)
-        shards = []
-        for r in range(2):
-            lo, hi = shard_bounds(bits.shape[0], 2, r)
-            shards.append(DeviceIndex(bits[lo:hi], tree, id_base=lo, device=dev))
-        grp = LocalShardGroup(shards)
-        assert all(rk.transport == "peer" for rk in grp.ranks)
-        ids_o, sc_o, _ = cport.scan_topk(bits, q, 10)
-        qd = torch.from_numpy(q).to(dev)
-        for rep in range(4):
-            for b in (1, 12):
-                for scores, ids in grp.search(qd[:b], 10):
-                    torch.cuda.synchronize()
-                    assert (ids.cpu().numpy() == ids_o[:b]).all() and (scores.cpu().numpy() == sc_o[:b]).all(), (rep, b)
-        assert shards[0]._use_gemm(300)  # a wide batch: every rank's stage 1 is the GEMM-shaped scan, same exchange
-        for scores, ids in grp.search(qd, 10):
-            torch.cuda.synchronize()
-            assert (ids.cpu().numpy() == ids_o).all() and (scores.cpu().numpy() == sc_o).all()
-        for ids_h, sc_h, lens in grp.retrieve_host(torch.from_numpy(q[:3]), 10):
-            for b in range(3):
-                exp = oracle.retrieve(bits, q[b], 10, tree)
-                assert [(int(o), float(s)) for o, s in zip(ids_h[b, :lens[b]], sc_h[b, :lens[b]])] == exp
-        _lib.check_status(0)
-    finally:
-        _lib.set_wait_timeout_ms(0, 0)
-
-
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
 def test_sharded_index_two_ranks(tmp_path, transport):
     import torch.multiprocessing as mp
 
     one_gpu = torch.cuda.device_count() < 2
     if one_gpu and transport == "peer":
-        _peer_scenario_on_one_gpu()  # (the second round after a repair: tests/test_gpu_exchange_one_device.py)
-        return
+        pytest.skip("the symmetric-memory rendezvous wants one GPU per rank; on one GPU the peer protocol and ShardedIndex "
+                    "are covered by tests/test_gpu_exchange_one_device.py (LocalShardGroup)")
     mp.spawn(_worker, args=(2, _free_port(), transport, str(tmp_path), one_gpu), nprocs=2, join=True)
     assert all(os.path.exists(tmp_path / f"ok-{transport}-{r}") for r in range(2))
