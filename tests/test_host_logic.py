@@ -477,3 +477,85 @@ def test_filter_spec_parser_equals_the_references_builder():
         assert (built is None) == (mine == []), fs
         if built is not None:
             assert clauses_from_filters(built) == mine, fs
+
+
+# --------------------------------------------------------------------------- host lanes + coalescing (no GPU: a fake device)
+def test_host_lanes_coalesce_concurrent_callers_without_starving_anyone(monkeypatch):
+    """The lane / coalescing logic of ``DeviceIndex.retrieve_host`` against a fake device that takes 2 ms per pass
+    whatever the batch: eight callers that re-enter immediately (no think time -- the pattern that starved the waiting
+    callers of an earlier version) all get THEIR answers, batches form (so throughput exceeds one query per pass), batch
+    shapes are powers of two, never more than HOST_LANES passes are in flight, and an error reaches the whole batch."""
+    import contextlib
+    import threading
+    import time
+
+    import torch
+
+    from tensor_truth_b200 import index as im
+
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: type("S", (), {"wait_stream": lambda self, o: None})())
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: None)
+    monkeypatch.setattr(torch.cuda, "stream", lambda st: contextlib.nullcontext())
+    idx = object.__new__(im.DeviceIndex)
+    idx._pending, idx._lane_cv, idx._coalesce, idx.coalesced = [], threading.Condition(), True, 0
+    idx._free_lanes, idx._lane_streams = list(range(im.HOST_LANES)), {}
+    idx.dim, idx.tree, idx.device = 4, None, None
+    device, state, shapes = threading.Lock(), {"in_flight": 0, "peak": 0}, []
+
+    def fake_pass(lane, q, k, ratio, merge, row_filter):
+        if k < 0:
+            raise ValueError("bad k")
+        with idx._lane_cv:
+            state["in_flight"] += 1
+            state["peak"] = max(state["peak"], state["in_flight"])
+            shapes.append(int(q.shape[0]))
+        with device:
+            time.sleep(0.002)
+        with idx._lane_cv:
+            state["in_flight"] -= 1
+        tag = q[:, 0].numpy().astype(np.int64)  # the answer of a query is its first coordinate
+        return tag[:, None].repeat(3, axis=1), tag[:, None].astype(np.float64), np.full(len(tag), 3, np.int32)
+
+    idx._retrieve_host_lane = fake_pass
+    wrong, per = [], 25
+
+    def caller(t):
+        for i in range(per):
+            v = 1000 * t + i
+            ids, scores, lens = idx.retrieve_host(torch.full((1, 4), float(v)), 10)
+            if ids.shape != (1, 3) or int(ids[0, 0]) != v or float(scores[0, 0]) != v or int(lens[0]) != 3:
+                wrong.append((t, i, ids))
+
+    threads = [threading.Thread(target=caller, args=(t,)) for t in range(8)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+    assert not any(th.is_alive() for th in threads), "a caller is stuck"
+    assert not wrong and not idx._pending and sorted(idx._free_lanes) == list(range(im.HOST_LANES))
+    assert state["peak"] <= im.HOST_LANES and idx.coalesced > 0
+    assert all(b & (b - 1) == 0 and b <= im.COALESCE_MAX for b in shapes) and max(shapes) > 1
+    assert len(shapes) < 8 * per  # fewer passes than queries: coalescing paid off
+    # one caller alone leads a batch of itself
+    n_before = idx.coalesced
+    assert int(idx.retrieve_host(torch.full((1, 4), 7.0), 10)[0][0, 0]) == 7 and idx.coalesced == n_before
+    # an error inside a coalesced batch reaches every caller of the batch
+    held = idx._hold_all_lanes()
+    errors = []
+
+    def failing():
+        try:
+            idx.retrieve_host(torch.zeros((1, 4)), -1)
+        except ValueError as exc:
+            errors.append(exc)
+
+    threads = [threading.Thread(target=failing) for _ in range(3)]
+    for th in threads:
+        th.start()
+    t0 = time.time()
+    while len(idx._pending) < 3 and time.time() - t0 < 10:
+        time.sleep(0.002)
+    idx._release_lanes(held)
+    for th in threads:
+        th.join(timeout=30)
+    assert len(errors) == 3 and len({id(e) for e in errors}) == 1
